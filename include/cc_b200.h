@@ -1,0 +1,164 @@
+/*
+ * cc_b200.h -- C ABI of the B200-native compressed-KV decode path.
+ *
+ * The reference (AnswerDotAI/cold-compress) is pure Python and has no FFI; the
+ * entry points below are what a binding for its hot path would call.  Each one
+ * names the reference interface it replaces (file:line relative to the
+ * reference checkout).  Plain pointers and sizes only: no torch types, no C++
+ * exceptions across the boundary.  Every function returns 0 on success and a
+ * negative CC_ERR_* code on failure; cc_last_error() gives the message of the
+ * last failure on the calling thread.
+ *
+ * All buffer pointers are DEVICE pointers owned by the caller (in the Python
+ * host they are the nn.Module buffers the reference registers in
+ * cache.py:195-227 / 574 / 668-679).  The library owns nothing persistent.
+ * Every call enqueues work on the caller's stream and returns without
+ * synchronising, so a whole decode step can be captured in a CUDA graph.
+ */
+#ifndef CC_B200_H
+#define CC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CC_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------- */
+#define CC_OK                     0
+#define CC_ERR_INVALID_ARG       -1  /* NULL pointer, bad enum, bad size        */
+#define CC_ERR_UNSUPPORTED_SHAPE -2  /* head_dim / group / length out of range  */
+#define CC_ERR_CUDA              -3  /* a CUDA runtime call failed              */
+#define CC_ERR_NO_DEVICE         -4  /* no sm_100 device / kernel image missing */
+
+/* ---- eviction policies (cache.py:1444-1478 get_cache_constructor) ------- */
+#define CC_POLICY_EXTERNAL       0  /* slot index supplied by the caller: full (cache.py:500-502),
+                                       random (519-524), keep_it_odd (1437-1441) compute it host-side */
+#define CC_POLICY_RECENT_GLOBAL  1  /* cache.py:552-556 */
+#define CC_POLICY_L2             2  /* cache.py:580-605 */
+#define CC_POLICY_HEAVY_HITTER   3  /* cache.py:690-765 */
+#define CC_POLICY_HYBRID         4  /* cache.py:844-1019 (FastGen, per-head strategy) */
+
+/* ---- attention numerics (attention_utils.py:8-54) ----------------------- */
+#define CC_ATTN_MATH_FP32   0  /* F.scaled_dot_product_attention, MATH backend: fp32 inside,
+                                  one rounding of y (attention_utils.py:27-35)              */
+#define CC_ATTN_NAIVE_BF16  1  /* return_attn path: bf16 after q.k, after *scale, after
+                                  softmax, after the GQA mean (attention_utils.py:36-54,
+                                  model.py:413-418)                                         */
+
+/* ---- phase flags: the fused step is EVICT|ATTEND|SCORE ------------------- */
+#define CC_PHASE_EVICT_FILL  1  /* KVCache.update_kv decode branch (cache.py:314-364)       */
+#define CC_PHASE_ATTEND      2  /* scaled_dot_product_attention + GQA pooling               */
+#define CC_PHASE_SCORE       4  /* KVCache.update_state decode branch (cache.py:690-723)    */
+#define CC_PHASE_ALL         7
+
+/* ---- hybrid per-head strategy bits (cache.py:896-950 substrings of the name) */
+#define CC_HYB_FULL          1
+#define CC_HYB_WINDOW        2
+#define CC_HYB_HEAVY_HITTER  4
+#define CC_HYB_SPECIAL       8
+#define CC_HYB_PUNC          16
+
+/*
+ * Per-layer cache state: mirrors the buffers of one KVCache module
+ * (cache.py:162-227).  Shapes drop the leading batch dimension (always 1,
+ * model.py:188-189).  bf16 tensors are passed as void*.
+ */
+typedef struct CcCacheState {
+    int32_t policy;            /* CC_POLICY_*                                            */
+    int32_t attn_mode;         /* CC_ATTN_*                                              */
+    int32_t n_kv_heads;        /* Hkv: local KV heads (config.n_local_heads)             */
+    int32_t q_per_kv;          /* G = n_head / n_local_heads (model.py:395-400)          */
+    int32_t head_dim;          /* D: 64 or 128                                           */
+    int32_t max_cache_length;  /* L: slots per head                                      */
+    int32_t global_tokens;     /* g                                                      */
+    int32_t recent_window;     /* per-layer int after setup_caches (generation_utils.py:362-372) */
+    int32_t history_window;    /* W: 1 => fp64 running sum, >1 => bf16 ring (cache.py:661-667)   */
+    int32_t pos_heads;         /* rows of `pos`: 1 (head-constant) or Hkv (head-specific)        */
+    int32_t cts_heads;         /* rows of `cache_cts`: 1, or Hkv for variable_length (hybrid)    */
+    int32_t reserved0;
+
+    void*    k_cache;          /* bf16 [Hkv, L, D]   cache.py:185,200                    */
+    void*    v_cache;          /* bf16 [Hkv, L, D]   cache.py:186,201                    */
+    int32_t* pos;              /* i32  [pos_heads, L], -1 = unfilled  cache.py:207-218   */
+    uint8_t* mask;             /* bool [Hkv, L]      cache.py:226-227                    */
+    int32_t* cache_cts;        /* i32  [cts_heads]   cache.py:219-222                    */
+
+    /* heavy_hitter / hybrid (cache.py:646-679) */
+    void*    attn_history_num;   /* f64 [Hkv, L] when W == 1; bf16 [Hkv, L, W] otherwise */
+    int32_t* attn_history_denom; /* i32 [Hkv, L]                                          */
+    int64_t* attn_counter;       /* i64 [1]                                               */
+
+    /* l2 (cache.py:573-574) */
+    void*    key_norm;           /* bf16 [Hkv, L]                                         */
+
+    /* hybrid (cache.py:803-834, 896-950); NULL for other policies */
+    const int32_t* hyb_strategy_bits;  /* i32 [Hkv] CC_HYB_* of the strategy chosen per head */
+    const int32_t* hyb_recent_window;  /* i32 [Hkv] round(recent_window * L)                 */
+    const int32_t* hyb_heavy_budget;   /* i32 [Hkv] round(heavy_hitter_frac * L)             */
+    uint8_t* special_mask;             /* bool [Hkv, L] or NULL                              */
+    uint8_t* punc_mask;                /* bool [Hkv, L] or NULL                              */
+    int32_t* num_special;              /* i32 [1] or NULL                                    */
+    int32_t* num_punc;                 /* i32 [1] or NULL                                    */
+
+    /* 8-byte-aligned scratch of cc_sync_words() int32 words, zero-initialised once by the
+       caller and after every reset(); orders shared-state writes after all heads have read. */
+    int32_t* sync_words;
+} CcCacheState;
+
+/* Per-call arguments of one decode step (one new token, one layer). */
+typedef struct CcDecodeArgs {
+    const void*    q;          /* bf16 [Hkv*G, D], post-RoPE (model.py:382-385)          */
+    const void*    k_new;      /* bf16 [Hkv, D],   post-RoPE                             */
+    const void*    v_new;      /* bf16 [Hkv, D]                                          */
+    const int32_t* input_pos;  /* i32 [1] on the device (generation_utils.py:482)        */
+    void*          y;          /* out bf16 [Hkv*G, D]                                    */
+    int64_t*       fill_idx;   /* policy EXTERNAL: in, i64 [pos_heads]; otherwise optional
+                                  out i64 [Hkv] (the eviction trace), may be NULL        */
+    void*          probs;      /* NAIVE mode: optional out bf16 [Hkv, L] GQA-pooled probabilities
+                                  (what update_state receives); with phases == CC_PHASE_SCORE
+                                  it is the input.  May be NULL in the fused step.        */
+    int32_t        is_punc;    /* hybrid: 1 if the new token id is punctuation (cache.py:969-971) */
+    int32_t        phases;     /* CC_PHASE_* mask; CC_PHASE_ALL for the fused step        */
+} CcDecodeArgs;
+
+/* ABI / build identification. */
+int         cc_abi_version(void);
+const char* cc_build_info(void);      /* e.g. "sm_100a nvcc 12.9" */
+const char* cc_last_error(void);      /* message of the last failing call on this thread */
+int         cc_sync_words(void);      /* number of int32 words `sync_words` must hold     */
+
+/*
+ * One decode step of one layer, as ONE kernel launch on `stream`:
+ * eviction decision -> in-place slot overwrite -> masked attention over the
+ * cache slots -> GQA pooling -> eviction-score update.
+ * Replaces model.py:389-427 (decode branch) = KVCache.update_kv (cache.py:314-340)
+ * + scaled_dot_product_attention (attention_utils.py:8-54) + KVCache.update_state.
+ * `stream` is a cudaStream_t passed as void*.
+ */
+int cc_decode_step(const CcCacheState* state, const CcDecodeArgs* args, void* stream);
+
+/* Launch-shape query for tests / the bench: cluster size the step would use. */
+int cc_decode_cluster_size(const CcCacheState* state);
+
+/*
+ * Key L2 norms of cached keys: key_norm[h, s] = bf16(||k_cache[h, s, :]||_2).
+ * Replaces KVCacheL2.update_state prefill branch (cache.py:607-612).
+ */
+int cc_key_norms(const void* k, void* key_norm, int32_t n_rows, int32_t head_dim, void* stream);
+
+/*
+ * Prompt compression gather (prompt_compression.py:82-88 + cache.py:381-401):
+ * k_cache[h, j, :] = k_prompt[h, keep_idx[h or 0, j], :] for j < n_keep, same for V,
+ * pos[h, j] = keep_idx[..], mask[h, j] = 1.
+ */
+int cc_prefill_gather(const CcCacheState* state, const void* k_prompt, const void* v_prompt,
+                      const int64_t* keep_idx, int32_t keep_heads, int32_t n_keep,
+                      int32_t prompt_len, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CC_B200_H */
