@@ -72,7 +72,7 @@ def test_oracle_reproduces_reference_trace(name):
             assert torch.allclose(oc.attn_history_num, num_ref, rtol=0, atol=4e-3 * max(1, prob_mismatch))
         else:
             ring_diff = (bits(oc.attn_history_num).astype(np.int32) - bits(num_ref).astype(np.int32))
-            assert np.abs(ring_diff).max() <= 1 and (ring_diff != 0).sum() <= max(2, prob_mismatch)
+            assert np.abs(ring_diff).max() <= 2 and (ring_diff != 0).sum() <= max(2, prob_mismatch)
     if oc.key_norm is not None:
         assert torch.equal(oc.key_norm, fin["key_norm"].reshape(oc.key_norm.shape))
     if g.policy == "hybrid":
