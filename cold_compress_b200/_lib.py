@@ -1,0 +1,79 @@
+"""ctypes binding of the C ABI in include/cc_b200.h.
+
+There is NO CPU fallback: if libcc_b200.so is missing or does not export every declared symbol,
+loading fails loudly.  On a machine without a GPU the library still loads (so the symbol table
+can be checked) but every compute call returns CC_ERR_NO_DEVICE / CC_ERR_CUDA.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+SO_PATH = PKG / "libcc_b200.so"
+
+ABI_VERSION = 1
+CC_OK = 0
+POLICY_EXTERNAL, POLICY_RECENT_GLOBAL, POLICY_L2, POLICY_HEAVY_HITTER, POLICY_HYBRID = range(5)
+ATTN_MATH_FP32, ATTN_NAIVE_BF16 = 0, 1
+PHASE_EVICT_FILL, PHASE_ATTEND, PHASE_SCORE, PHASE_ALL = 1, 2, 4, 7
+HYB_FULL, HYB_WINDOW, HYB_HEAVY_HITTER, HYB_SPECIAL, HYB_PUNC = 1, 2, 4, 8, 16
+
+_STATE_INTS = ("policy", "attn_mode", "n_kv_heads", "q_per_kv", "head_dim", "max_cache_length",
+               "global_tokens", "recent_window", "history_window", "pos_heads", "cts_heads", "reserved0")
+_STATE_PTRS = ("k_cache", "v_cache", "pos", "mask", "cache_cts", "attn_history_num", "attn_history_denom",
+               "attn_counter", "key_norm", "hyb_strategy_bits", "hyb_recent_window", "hyb_heavy_budget",
+               "special_mask", "punc_mask", "num_special", "num_punc", "sync_words")
+
+
+class CcCacheState(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in _STATE_INTS] + [(n, C.c_void_p) for n in _STATE_PTRS]
+
+
+class CcDecodeArgs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("q", "k_new", "v_new", "input_pos", "y", "fill_idx", "probs")] + [
+        ("is_punc", C.c_int32), ("phases", C.c_int32)]
+
+
+# every symbol include/cc_b200.h declares: name -> (restype, argtypes)
+EXPORTS = {
+    "cc_abi_version": (C.c_int, []),
+    "cc_build_info": (C.c_char_p, []),
+    "cc_last_error": (C.c_char_p, []),
+    "cc_sync_words": (C.c_int, []),
+    "cc_decode_step": (C.c_int, [C.POINTER(CcCacheState), C.POINTER(CcDecodeArgs), C.c_void_p]),
+    "cc_decode_cluster_size": (C.c_int, [C.POINTER(CcCacheState)]),
+    "cc_key_norms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "cc_prefill_gather": (C.c_int, [C.POINTER(CcCacheState), C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+}
+
+_lib = None
+
+
+class CcError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; raises if it has not been built (python -m cold_compress_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not SO_PATH.exists():
+        raise CcError(f"{SO_PATH} is missing: build it with `python -m cold_compress_b200.build` "
+                      "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the decode path.")
+    lib = C.CDLL(str(SO_PATH))
+    for name, (restype, argtypes) in EXPORTS.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.restype, fn.argtypes = restype, argtypes
+    if lib.cc_abi_version() != ABI_VERSION:
+        raise CcError(f"ABI mismatch: library {lib.cc_abi_version()} vs binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> int:
+    if rc < 0:
+        raise CcError(f"{what or 'cc call'} failed ({rc}): {load().cc_last_error().decode()}")
+    return rc

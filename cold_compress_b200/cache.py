@@ -1,0 +1,478 @@
+"""KV-cache policy layer: host-side mirror of the reference's cache.py surface.
+
+Drop-in boundary: `get_cache_constructor(strategy) -> (cls, relevant_kwargs)`,
+`cls(max_batch_size, n_heads, head_dim, dtype, **kwargs)`, `.update_kv / .update_state /
+.return_attn / .reset / .compute_statistics`, `add_cache_arguments`, `cache_compatibility`
+(reference cache.py:13-139, 152-346, 1444-1478).  Buffers carry the reference's names, shapes and
+dtypes (cache.py:185-227, 573-574, 646-679) so `.to()`, `state_dict()`, `reset()` and code that
+inspects them behave the same.
+
+What differs is everything behind the surface: there is no per-op PyTorch implementation of the
+decode step.  `decode_step()` runs eviction + overwrite + attention + score update as ONE CUDA
+kernel launch (csrc/decode_step.cu) through `torch.ops.cold_compress_b200.decode_step`; the
+three-call surface (`update_kv` -> attention -> `update_state`) maps onto the same kernel with a
+phase mask.  CUDA only: on CPU tensors the ops raise.
+"""
+from __future__ import annotations
+
+import argparse
+import math
+from collections import Counter
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .prompt_compression import get_prompt_compressor_constructor  # noqa: F401  (re-export, as the reference)
+
+# --------------------------------------------------------------------------- CLI arguments
+
+_STRATEGIES = ["full", "random", "recent_global", "heavy_hitter", "l2", "hybrid", "keep_it_odd"]
+
+# (flag, kwargs, on_group) -- same flags, defaults and types as reference cache.py:13-118
+_CACHE_FLAGS = [
+    ("--max_cache_length", dict(type=float, default=[1.0], nargs="+",
+                                help="Cache size per layer: 0<x<=1 is a fraction of |prompt|+max_new_tokens, >1 absolute. Tiled over layers."), True),
+    ("--cache_bits", dict(default=None, type=int, choices=[2, 4, 8], help="KV quantisation bits (not in this build)."), True),
+    ("--cache_length_pattern", dict(default="tile", choices=["tile", "repeat", "funnel", "pyramid"]), True),
+    ("--cache_strategy", dict(default=["full"], nargs="+",
+                              choices=_STRATEGIES + [f"debug_{s}" for s in _STRATEGIES]), True),
+    ("--cache_strategy_pattern", dict(default="tile", choices=["tile", "repeat"],
+                                      help="How cache_strategy is spread over layers."), True),
+    ("--feed_long_prompts", dict(default=False, action="store_true",
+                                 help="Prefill with prompt[:max_cache_length] and feed the rest token by token."), False),
+    ("--prompt_compression_strategy", dict(default=["recent_global"], nargs="+",
+                                           help="How a prompt longer than the cache is compressed into it."), True),
+    ("--global_tokens", dict(default=1, type=int, help="Leading tokens that are never evicted."), True),
+    ("--recent_window", dict(default=10, type=float, help="Most recent tokens spared from eviction (<1: fraction of cache)."), True),
+    ("--history_window_size", dict(default=1, type=int, help="Heavy-hitter history window (1 = full history)."), True),
+    ("--attn_thresholding", dict(default=False, action="store_true", help="Accumulate binary attention indicators."), True),
+    ("--min_recovery_frac", dict(default=0.9, type=float, help="Hybrid (FastGen): minimum recovered attention mass."), False),
+]
+
+
+def add_cache_arguments(parser: argparse.ArgumentParser):
+    group = parser.add_argument_group("cache_args")
+    for flag, kw, on_group in _CACHE_FLAGS:
+        (group if on_group else parser).add_argument(flag, **kw)
+
+
+def cache_compatibility(args):
+    """Same checks as reference cache.py:121-139."""
+    triples = zip(args.max_cache_length, args.cache_strategy, args.prompt_compression_strategy)
+    for length, strat, prompt_strat in triples:
+        if strat == "heavy_hitter" and prompt_strat != "heavy_hitter":
+            raise AssertionError("heavy_hitter caches need --prompt_compression_strategy heavy_hitter (it returns attention).")
+        if strat == "hybrid" and getattr(args, "compile", False):
+            raise AssertionError("hybrid is not supported with compile=True.")
+        if strat in ("full", "hybrid") and length != 1.0:
+            raise AssertionError(f"{strat} cache strategy only supports max_cache_length=1.0.")
+    print("The cache argument values you provided appear compatible with each other!")
+
+
+def create_window_attention_mask(seq_len, window_size, device, global_tokens: int = 4):
+    """[seq_len, seq_len] bool: globals + a causal sliding window (reference cache.py:142-149), vectorised."""
+    i = torch.arange(seq_len, device=device).view(-1, 1)
+    j = torch.arange(seq_len, device=device).view(1, -1)
+    return (j < global_tokens) | ((j <= i) & (j > i - window_size))
+
+
+# --------------------------------------------------------------------------- base class
+
+
+class KVCache(nn.Module):
+    relevant_kwargs = ["max_cache_length", "global_tokens", "max_seq_length", "cache_bits"]
+    policy = _lib.POLICY_EXTERNAL
+
+    def __init__(self, max_batch_size, n_heads, head_dim, dtype=torch.bfloat16, head_specific=False,
+                 variable_length=False, **kwargs):
+        super().__init__()
+        for key, value in kwargs.items():
+            setattr(self, key, value)
+        if max_batch_size != 1:
+            raise NotImplementedError("batch size is fixed to 1 (reference model.py:188-189)")
+        if getattr(self, "cache_bits", None) is not None:
+            raise NotImplementedError("--cache_bits (quantised KV) is not built yet; see DESIGN.md (next)")
+        self.cache_bits = None
+        self.quantize, self.n_bit = False, None
+        if not hasattr(self, "global_tokens"):
+            self.global_tokens = 0
+        self.n_heads, self.head_dim = n_heads, head_dim
+        self.head_specific, self.variable_length = head_specific, variable_length
+        L = self.max_cache_length
+        self.cache_shape = (max_batch_size, n_heads, L, head_dim)
+        self.register_buffer("k_cache", torch.zeros(self.cache_shape, dtype=dtype))
+        self.register_buffer("v_cache", torch.zeros(self.cache_shape, dtype=dtype))
+        self.register_buffer("pos", torch.full((max_batch_size, n_heads if head_specific else 1, L), -1, dtype=torch.int))
+        self.register_buffer("cache_cts", torch.zeros(n_heads if variable_length else 1, dtype=torch.int))
+        self.register_buffer("mask", torch.zeros((max_batch_size, n_heads, 1, L), dtype=torch.bool))
+        # kernel-side scratch (not part of the reference state)
+        self.register_buffer("_sync_words", torch.zeros(8, dtype=torch.int32), persistent=False)
+        self.register_buffer("_fill_idx", torch.zeros(n_heads, dtype=torch.int64), persistent=False)
+        self.register_buffer("_empty", torch.zeros(0, dtype=torch.uint8), persistent=False)
+        self._q_per_kv = None
+        self._out = {}
+
+    # ---- reference surface ------------------------------------------------------------
+    def reset(self):
+        self.k_cache.zero_()
+        self.v_cache.zero_()
+        self.mask.zero_()
+        self.cache_cts.zero_()
+        self.pos.fill_(-1)
+        self._sync_words.zero_()
+
+    def return_attn(self) -> bool:
+        return False
+
+    def memory_usage(self):
+        tensors = [t for n, t in vars(self).items() if torch.is_tensor(t)]
+        tensors += [b for n, b in self._buffers.items() if b is not None and not n.startswith("_")]
+        return sum(t.element_size() * t.numel() for t in tensors) / (1024 ** 3)
+
+    def compression_ratio(self, seq_len):
+        n = seq_len - 1  # the final token is never passed to the cache
+        assert torch.all(self.cache_cts <= self.max_cache_length)
+        return ((n - self.cache_cts.float()) / n).mean()
+
+    def compute_statistics(self, seq_len):
+        return {"compression_ratio": self.compression_ratio(seq_len).item(), "cache_memory_gb": self.memory_usage()}
+
+    def return_kv_cache(self):
+        return self.k_cache, self.v_cache, self.mask
+
+    def update_kv(self, input_pos, k_val, v_val, is_prefill, **kwargs):
+        """Reference cache.py:314-340.  Decode: eviction decision + in-place overwrite (kernel phase
+        EVICT_FILL).  Prefill: contiguous fill of the (already compressed) prompt."""
+        if is_prefill:
+            self._prefill_update(input_pos, k_val, v_val, **kwargs)
+        else:
+            self._launch(_lib.PHASE_EVICT_FILL, None, k_val, v_val, input_pos, **kwargs)
+        return self.return_kv_cache()
+
+    def update_state(self, input_pos, k_val, v_val, is_prefill, attn, **kwargs):
+        """No-op for caches that keep no score state (reference cache.py:342-346)."""
+        return None
+
+    # ---- fused / phased decode step -----------------------------------------------------
+    def attn_mode(self) -> int:
+        return _lib.ATTN_NAIVE_BF16 if self.return_attn() else _lib.ATTN_MATH_FP32
+
+    def decode_step(self, q, k_val, v_val, input_pos, **kwargs):
+        """ONE kernel: evict -> overwrite -> attend -> pool -> score.  q [1,Hq,1,D]; returns y [1,Hq,1,D]."""
+        return self._launch(_lib.PHASE_ALL, q, k_val, v_val, input_pos, **kwargs)
+
+    def attend(self, q, input_pos):
+        """Attention over the current cache content only (kernel phase ATTEND): (y, pooled probs or None)."""
+        y = self._launch(_lib.PHASE_ATTEND, q, None, None, input_pos)
+        return y, (self._out["probs"].view(1, self.n_heads, 1, -1) if self.return_attn() else None)
+
+    def _state_list(self):
+        e = self._empty
+        get = lambda n: getattr(self, n, None)  # noqa: E731
+        names = ops.STATE_ORDER
+        alias = {"sync_words": "_sync_words", "hyb_strategy_bits": "_hyb_bits", "hyb_recent_window": "_hyb_rw",
+                 "hyb_heavy_budget": "_hyb_hh"}
+        out = []
+        for n in names:
+            t = get(alias.get(n, n))
+            out.append(t if torch.is_tensor(t) else e)
+        return out
+
+    def _meta(self, G):
+        W = getattr(self, "history_window_size", 1)
+        return [self.policy, self.attn_mode(), self.n_heads, G, self.head_dim, self.max_cache_length,
+                int(self.global_tokens), int(getattr(self, "recent_window", 0) or 0), int(W),
+                self.pos.shape[1], self.cache_cts.numel(), 0]
+
+    def _outputs(self, G, device, dtype):
+        key = (G, device, dtype)
+        if self._out.get("key") != key:
+            self._out = {"key": key,
+                         "y": torch.empty(self.n_heads * G, self.head_dim, device=device, dtype=dtype),
+                         "probs": torch.empty(self.n_heads, self.max_cache_length, device=device, dtype=dtype)}
+        return self._out
+
+    def _external_fill_idx(self, input_pos):
+        raise NotImplementedError
+
+    def _launch(self, phases, q, k_val, v_val, input_pos, probs_in=None, **kwargs):
+        dev = self.k_cache.device
+        if dev.type != "cuda":
+            raise _lib.CcError("the compressed-KV decode path is CUDA-only: move the model to a B200 (no CPU fallback)")
+        if q is not None:
+            G = q.shape[1] // self.n_heads
+            self._q_per_kv = G
+        else:
+            G = self._q_per_kv or 1
+        out = self._outputs(G, dev, self.k_cache.dtype)
+        e = self._empty
+        fill_idx = self._fill_idx
+        if self.policy == _lib.POLICY_EXTERNAL and (phases & _lib.PHASE_EVICT_FILL):
+            fill_idx = self._external_fill_idx(input_pos).to(torch.int64).contiguous()
+        probs = out["probs"] if self.return_attn() else e
+        if probs_in is not None:
+            probs = probs_in.reshape(self.n_heads, -1).contiguous()
+        ip = input_pos if input_pos.dtype == torch.int32 else input_pos.int()
+        ops.decode_step(
+            q.reshape(-1, self.head_dim) if q is not None else e,
+            k_val.reshape(-1, self.head_dim) if k_val is not None else e,
+            v_val.reshape(-1, self.head_dim) if v_val is not None else e,
+            ip, self._state_list(), self._meta(G), out["y"], fill_idx, probs, phases,
+            bool(kwargs.get("is_punc", False)))
+        return out["y"].view(1, self.n_heads * G, 1, self.head_dim) if q is not None else None
+
+    # ---- prefill fill ---------------------------------------------------------------------
+    def _prefill_update(self, input_pos, k_val, v_val, **kwargs):
+        """Contiguous fill of slots [0, n) (reference cache.py:381-401)."""
+        n = input_pos.shape[-1]
+        self.pos[:, :, :n] = input_pos.int()
+        self.k_cache[:, :, :n, :] = k_val
+        self.v_cache[:, :, :n, :] = v_val
+        if kwargs.get("update_mask", True):
+            self.mask[:, :, :, :n] = True
+        self.cache_cts += n if not self.variable_length else 0
+
+    def fill_from_prompt(self, k_prompt, v_prompt, keep_idx):
+        """Fused prompt-compression gather + fill: cache[:, j] = prompt[:, keep_idx[.., j]] (cc_prefill_gather)."""
+        ops.prefill_gather(self._state_list(), self._meta(self._q_per_kv or 1), k_prompt.contiguous(),
+                           v_prompt.contiguous(), keep_idx.to(torch.int64).contiguous())
+        self.cache_cts += keep_idx.shape[-1] if not self.variable_length else 0
+
+
+class KVCacheHeadConstant(KVCache):
+    def __init__(self, max_batch_size, n_heads, head_dim, dtype=torch.bfloat16, **kwargs):
+        super().__init__(max_batch_size, n_heads, head_dim, dtype, head_specific=False, **kwargs)
+
+
+class KVCacheHeadSpecific(KVCache):
+    def __init__(self, max_batch_size, n_heads, head_dim, dtype=torch.bfloat16, variable_length=False, **kwargs):
+        super().__init__(max_batch_size, n_heads, head_dim, dtype, head_specific=True,
+                         variable_length=variable_length, **kwargs)
+
+
+# --------------------------------------------------------------------------- host-side (EXTERNAL) policies
+# Their slot choice is a handful of integer ops on `pos`; the kernel takes the index and does the
+# overwrite + attention.  Not in BASELINE configs.
+
+
+def _base_eviction_idx(scores, pos_row, global_tokens):
+    """reference cache.py:366-379."""
+    scores = scores.clone().float().view(1, -1)
+    scores[:, :global_tokens] = float("inf")
+    scores.masked_fill_(pos_row.view(1, -1) == -1, float("-inf"))
+    return torch.argmin(scores, dim=-1)
+
+
+class KVCacheFull(KVCacheHeadConstant):
+    def __init__(self, max_batch_size, n_heads, head_dim, dtype=torch.bfloat16, **kwargs):
+        kwargs = dict(kwargs)
+        kwargs["global_tokens"] = 0  # every token is kept
+        super().__init__(max_batch_size, n_heads, head_dim, dtype, **kwargs)
+
+    def _external_fill_idx(self, input_pos):
+        return self.pos[0, 0].argmin().view(1)  # first unfilled slot (reference cache.py:500-502)
+
+
+class KVCacheRandom(KVCacheHeadConstant):
+    relevant_kwargs = ["max_cache_length", "max_seq_length", "cache_bits", "global_tokens", "recent_window"]
+
+    def _external_fill_idx(self, input_pos):
+        scores = torch.rand(self.max_cache_length, device=self.pos.device)
+        scores[self.pos[0, 0] >= input_pos - self.recent_window] = float("inf")
+        return _base_eviction_idx(scores, self.pos[0, 0], self.global_tokens)
+
+
+class KVCacheKeepItOdd(KVCacheHeadConstant):
+    relevant_kwargs = ["max_cache_length", "max_seq_length", "cache_bits", "global_tokens", "recent_window"]
+
+    def _external_fill_idx(self, input_pos):
+        p = self.pos[0, 0]
+        scores = (p % 2 == 1).float()
+        scores[p >= input_pos - self.recent_window] = float("inf")
+        return _base_eviction_idx(scores, p, self.global_tokens)
+
+
+# --------------------------------------------------------------------------- in-kernel policies
+
+
+class KVCacheRecentGlobal(KVCacheHeadConstant):
+    """Sliding window + global tokens; the window is max_cache_length - global_tokens (reference cache.py:527-556)."""
+    relevant_kwargs = ["max_cache_length", "max_seq_length", "cache_bits", "global_tokens"]
+    policy = _lib.POLICY_RECENT_GLOBAL
+
+
+class KVCacheL2(KVCacheHeadSpecific):
+    """Evicts the key with the largest L2 norm outside the recent window (reference cache.py:559-612)."""
+    relevant_kwargs = ["max_cache_length", "max_seq_length", "cache_bits", "global_tokens", "recent_window"]
+    policy = _lib.POLICY_L2
+
+    def __init__(self, max_batch_size, n_heads, head_dim, dtype=torch.bfloat16, **kwargs):
+        super().__init__(max_batch_size, n_heads, head_dim, dtype, **kwargs)
+        self.register_buffer("key_norm", torch.zeros((max_batch_size, n_heads, self.max_cache_length), dtype=dtype))
+
+    def reset(self):
+        super().reset()
+        self.key_norm.zero_()
+
+    def update_state(self, input_pos, k_val, v_val, is_prefill, attn, **kwargs):
+        if is_prefill:  # decode-time norms are written by the kernel together with the fill
+            ops.key_norms(self.k_cache, self.key_norm)
+
+
+class KVCacheHeavyHitter(KVCacheHeadSpecific):
+    """Accumulated-attention eviction (ScissorHands / H2O; reference cache.py:615-765)."""
+    relevant_kwargs = ["max_cache_length", "max_seq_length", "cache_bits", "global_tokens", "history_window_size",
+                       "recent_window", "attn_thresholding"]
+    policy = _lib.POLICY_HEAVY_HITTER
+
+    def __init__(self, max_batch_size, n_heads, head_dim, dtype=torch.bfloat16, variable_length=False, **kwargs):
+        super().__init__(max_batch_size, n_heads, head_dim, dtype, variable_length, **kwargs)
+        if getattr(self, "attn_thresholding", False):
+            raise NotImplementedError("attn_thresholding=True is not built (no BASELINE config uses it)")
+        W, L = self.history_window_size, self.max_cache_length
+        if W != 1 and self.policy == _lib.POLICY_HEAVY_HITTER:
+            raise NotImplementedError("heavy_hitter kernel supports history_window_size=1 (the YAML default)")
+        num_dtype = torch.float64 if W == 1 else dtype
+        self.register_buffer("attn_history_num", torch.zeros((max_batch_size, n_heads, L, W), dtype=num_dtype))
+        self.register_buffer("attn_history_denom", torch.zeros((max_batch_size, n_heads, L), dtype=torch.int32))
+        self.register_buffer("attn_counter", torch.zeros((1,), dtype=torch.int64))
+
+    def reset(self):
+        super().reset()
+        self.attn_history_num.zero_()
+        self.attn_history_denom.zero_()
+        self.attn_counter.zero_()
+
+    def return_attn(self) -> bool:
+        return True
+
+    def update_state(self, input_pos, k_val, v_val, is_prefill, attn, **kwargs):
+        if not is_prefill:
+            # kernel phase SCORE with the pooled probabilities the caller holds
+            self._launch(_lib.PHASE_SCORE, None, None, None, input_pos, probs_in=attn.to(self.k_cache.dtype))
+            return
+        self._seed_history(input_pos, attn)
+
+    def _seed_history(self, input_pos, attn):
+        """Prefill seed of the score history (reference cache.py:697-723): attn is either the full
+        [1,H,S,S] map or the already-reduced cumulative attention [1,H,n]."""
+        seq_len = attn.shape[-1]
+        if attn.ndim == 4:
+            attn = attn.squeeze(0).sum(dim=1) / (seq_len - input_pos)
+        attn = attn.reshape(1, self.n_heads, -1, 1)
+        n = attn.shape[2]
+        slot = int(self.attn_counter.item()) % self.history_window_size if self.history_window_size > 1 else 0
+        col = self.attn_history_num[:, :, :, slot]
+        if self.history_window_size == 1:
+            col[:, :, :n] += attn[..., 0].to(col.dtype)
+        else:
+            col.zero_()
+            col[:, :, :n] = attn[..., 0].to(col.dtype)
+        self.attn_history_denom += 1
+        self.attn_counter += 1
+
+
+class KVCacheHybrid(KVCacheHeavyHitter):
+    """FastGen-style per-head hybrid strategies (reference cache.py:768-1288).  Decode runs in the
+    fused kernel (policy HYBRID); head profiling at prefill is host-side tensor code."""
+    relevant_kwargs = ["max_cache_length", "max_seq_length", "cache_bits", "global_tokens", "token_ids",
+                       "min_recovery_frac", "hybrid_strategies"]
+    policy = _lib.POLICY_HYBRID
+
+    def __init__(self, max_batch_size, n_heads, head_dim, dtype=torch.bfloat16, **kwargs):
+        self.attn_thresholding = False
+        kwargs = dict(kwargs, history_window_size=400, recent_window=None, attn_thresholding=False)
+        super().__init__(max_batch_size, n_heads, head_dim, dtype, variable_length=True, **kwargs)
+        names = [s["strategy"] for s in self.hybrid_strategies]
+        L = self.max_cache_length
+        self.requires_special = any("special" in n for n in names)
+        self.requires_punc = any("punc" in n for n in names)
+        self.requires_heavy_hitter = any("heavy_hitter" in n for n in names)
+        if self.requires_special:
+            self.special_id_seqs = [list(ids) for ids in kwargs["token_ids"]["special"]]
+            self.register_buffer("special_mask", torch.zeros((max_batch_size, n_heads, L), dtype=torch.bool))
+            self.register_buffer("num_special", torch.zeros((1,), dtype=torch.int))
+        if self.requires_punc:
+            self.register_buffer("punc_ids", torch.tensor(kwargs["token_ids"]["punctuation"], dtype=torch.int64))
+            self.register_buffer("punc_mask", torch.zeros((max_batch_size, n_heads, L), dtype=torch.bool))
+            self.register_buffer("num_punc", torch.zeros((1,), dtype=torch.int))
+        self.register_buffer("cache_strategies", torch.zeros(n_heads, dtype=torch.int64))
+        self.register_buffer("_hyb_bits", torch.zeros(n_heads, dtype=torch.int32), persistent=False)
+        self.register_buffer("_hyb_rw", torch.zeros(n_heads, dtype=torch.int32), persistent=False)
+        self.register_buffer("_hyb_hh", torch.zeros(n_heads, dtype=torch.int32), persistent=False)
+
+    def return_attn(self):
+        return self.requires_heavy_hitter
+
+    @staticmethod
+    def strategy_bits(name: str) -> int:
+        if name == "full":
+            return _lib.HYB_FULL
+        table = {"window": _lib.HYB_WINDOW, "heavy_hitter": _lib.HYB_HEAVY_HITTER, "special": _lib.HYB_SPECIAL,
+                 "punc": _lib.HYB_PUNC}
+        return sum(bit for key, bit in table.items() if key in name)
+
+    def set_head_strategies(self, strategy_ids):
+        """Install the per-head strategy choice (reference: self.cache_strategies, cache.py:1200)."""
+        ids = torch.as_tensor(strategy_ids, dtype=torch.int64)
+        L = self.max_cache_length
+        bits = [self.strategy_bits(self.hybrid_strategies[int(i)]["strategy"]) for i in ids]
+        rw = [round(self.hybrid_strategies[int(i)].get("recent_window", 0) * L) for i in ids]
+        hh = [round(self.hybrid_strategies[int(i)].get("heavy_hitter_frac", 0) * L) for i in ids]
+        dev = self.cache_strategies.device
+        self.cache_strategies.copy_(ids.to(dev))
+        self._hyb_bits.copy_(torch.tensor(bits, dtype=torch.int32))
+        self._hyb_rw.copy_(torch.tensor(rw, dtype=torch.int32))
+        self._hyb_hh.copy_(torch.tensor(hh, dtype=torch.int32))
+        names = [self.hybrid_strategies[int(i)]["strategy"] for i in ids]
+        self.requires_heavy_hitter = any("heavy_hitter" in n for n in names)
+
+    def reset(self):
+        super().reset()
+        names = [s["strategy"] for s in self.hybrid_strategies]
+        self.requires_heavy_hitter = any("heavy_hitter" in n for n in names)
+        for n in ("special_mask", "num_special", "punc_mask", "num_punc"):
+            if hasattr(self, n):
+                getattr(self, n).zero_()
+
+    def _launch(self, phases, q, k_val, v_val, input_pos, probs_in=None, **kwargs):
+        if "is_punc" not in kwargs and hasattr(self, "punc_ids") and kwargs.get("input_ids") is not None:
+            kwargs["is_punc"] = bool(torch.isin(kwargs["input_ids"].reshape(-1)[-1:].to(self.punc_ids.device),
+                                                self.punc_ids).item())
+        return super()._launch(phases, q, k_val, v_val, input_pos, probs_in=probs_in, **kwargs)
+
+    def update_state(self, input_pos, k_val, v_val, is_prefill, attn, **kwargs):
+        if is_prefill:
+            raise NotImplementedError("hybrid head profiling at prefill (reference cache.py:1066-1272) is not built "
+                                      "yet: inject a profiled state (see tests) or use another strategy")
+        if self.requires_heavy_hitter:
+            super().update_state(input_pos, k_val, v_val, is_prefill, attn, **kwargs)
+
+    def compute_statistics(self, seq_len):
+        stats = super().compute_statistics(seq_len)
+        ids = self.cache_strategies.tolist()
+        cts = Counter(self.hybrid_strategies[i]["strategy"] for i in ids)
+        stats["avg_strategy_idx"] = sum(ids) / len(ids)
+        for name in sorted({s["strategy"] for s in self.hybrid_strategies}):
+            stats[name] = cts.get(name, 0) / len(ids)
+        return stats
+
+
+# --------------------------------------------------------------------------- registry
+
+_REGISTRY = {
+    "full": KVCacheFull, "l2": KVCacheL2, "random": KVCacheRandom, "recent_global": KVCacheRecentGlobal,
+    "heavy_hitter": KVCacheHeavyHitter, "hybrid": KVCacheHybrid, "keep_it_odd": KVCacheKeepItOdd,
+}
+
+
+def get_cache_constructor(cache_strategy):
+    """(constructor, relevant kwargs) for a strategy name (reference cache.py:1444-1478)."""
+    if cache_strategy in _REGISTRY:
+        cls = _REGISTRY[cache_strategy]
+        return cls, cls.relevant_kwargs
+    if cache_strategy.startswith("debug"):
+        raise NotImplementedError("debug_* (KVCacheAnalysis, reference cache.py:1291-1420) is out of the hot path; "
+                                  "listed as next in DESIGN.md")
+    raise ValueError(f"Invalid cache strategy: {cache_strategy}")

@@ -1,0 +1,53 @@
+// api.cu -- the extern "C" surface declared in include/cc_b200.h.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "internal.h"
+
+#define CC_STR2(x) #x
+#define CC_STR(x) CC_STR2(x)
+
+namespace cc {
+static thread_local char g_err[512] = "";
+int set_error(int code, const char* msg) {
+    strncpy(g_err, msg, sizeof(g_err) - 1);
+    g_err[sizeof(g_err) - 1] = 0;
+    return code;
+}
+int set_cuda_error(cudaError_t e, const char* where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return CC_ERR_CUDA;
+}
+}  // namespace cc
+
+extern "C" {
+
+int cc_abi_version(void) { return CC_ABI_VERSION; }
+
+const char* cc_build_info(void) {
+    return "cold_compress_b200 sm_100a nvcc " CC_STR(__CUDACC_VER_MAJOR__) "." CC_STR(__CUDACC_VER_MINOR__);
+}
+
+const char* cc_last_error(void) { return cc::g_err; }
+
+int cc_sync_words(void) { return 4; }
+
+int cc_decode_step(const CcCacheState* state, const CcDecodeArgs* args, void* stream) {
+    return cc::decode_step_impl(state, args, (cudaStream_t)stream);
+}
+
+int cc_decode_cluster_size(const CcCacheState* state) { return cc::decode_cluster_size_impl(state); }
+
+int cc_key_norms(const void* k, void* key_norm, int32_t n_rows, int32_t head_dim, void* stream) {
+    return cc::key_norms_impl(k, key_norm, n_rows, head_dim, (cudaStream_t)stream);
+}
+
+int cc_prefill_gather(const CcCacheState* state, const void* k_prompt, const void* v_prompt,
+                      const int64_t* keep_idx, int32_t keep_heads, int32_t n_keep, int32_t prompt_len,
+                      void* stream) {
+    return cc::prefill_gather_impl(state, k_prompt, v_prompt, keep_idx, keep_heads, n_keep, prompt_len,
+                                   (cudaStream_t)stream);
+}
+
+}  // extern "C"

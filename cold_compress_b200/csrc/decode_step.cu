@@ -1,0 +1,751 @@
+// decode_step.cu -- the fused per-layer decode step for sm_100a.
+//
+// One launch = eviction decision -> in-place slot overwrite -> masked attention over the live
+// cache slots -> GQA pooling -> eviction-score update, for every KV head of one layer.
+// Replaces the reference's decode branch of Attention.forward (model.py:389-427):
+// KVCache.update_kv (cache.py:314-364), scaled_dot_product_attention
+// (attention_utils.py:8-54), the group mean (model.py:413-418) and KVCache.update_state
+// (cache.py:690-723), which run there as ~25 ATen ops and materialise 4x K/V copies.
+//
+// Shape of the launch (HBM-latency bound: 4 MiB of K/V per layer at L=1024):
+//   * one thread-block CLUSTER per KV head, C CTAs (<=16) per cluster, each CTA owns a
+//     contiguous range of ceil(L/C) cache slots -> Hkv*C CTAs (128 of 148 SMs for Llama-3-8B);
+//   * K and V rows of that range are streamed by the TMA engine (cp.async.bulk, UBLKCP) into
+//     a shared-memory ring, all chunks in flight from the first instruction;
+//   * three DSMEM all-to-all exchanges per step: {arg-min candidate, row max}, {softmax sum},
+//     {P.V partials}; the first one carries both the eviction decision and the softmax max, so
+//     the evicted slot's old logit is excluded / the new token's logit included without a
+//     second pass;
+//   * arithmetic order is the bit-reproducible definition in common.cuh (canonical dot tree,
+//     det_expf, 2^-40 fixed-point sum), so the eviction indices do not depend on C or on the
+//     thread count.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cc_b200.h"
+#include "common.cuh"
+#include "internal.h"
+
+namespace cc {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kChunkRows = 64;   // rows per TMA chunk (16 KiB at D=128)
+constexpr int kMaxCluster = 16;
+constexpr int kMaxG = 8;
+constexpr int kRecWords = 2 + 2 * kMaxG;  // X1 record: key64, lmax[G], candlogit[G]
+constexpr uint64_t kNoKey = ~0ull;
+
+struct DecodeParams {
+    CcCacheState st;
+    CcDecodeArgs a;
+    int rows_per_cta;   // T
+    int n_stages;       // ring depth for K and for V
+    int lg_stride;      // floats per query head in the logit/prob array (>= T)
+    float scale;        // (float)(1/sqrt(D))
+};
+
+struct SmemLayout {
+    uint32_t kring, vring, lg, red, ypart, yx, rec, sums, x0, maskb, bars, misc, total;
+};
+
+__host__ __device__ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline SmemLayout make_layout(int D, int G, int T, int n_stages, int lg_stride) {
+    SmemLayout s;
+    uint32_t off = 0;
+    const uint32_t chunk_bytes = kChunkRows * D * 2;
+    s.kring = off; off += n_stages * chunk_bytes;
+    s.vring = off; off += n_stages * chunk_bytes;
+    s.lg = off;    off += align_up(G * lg_stride * 4, 128);
+    s.red = off;   off += kWarps * G * D * 4;
+    s.ypart = off; off += G * D * 4;
+    s.yx = off;    off += G * D * 4;
+    s.rec = off;   off += kMaxCluster * kRecWords * 4;
+    s.sums = off;  off += kMaxCluster * kMaxG * 8;
+    s.x0 = off;    off += kMaxCluster * 4 + 64;
+    s.maskb = off; off += align_up(T, 128);
+    s.bars = off;  off += align_up(2 * n_stages * 8, 128);
+    s.misc = off;  off += 512;
+    s.total = off;
+    return s;
+}
+
+// misc area (floats / ints), indices in 4-byte words
+enum : int {
+    kMiscNewLg = 0,        // [kMaxG] logits of the new token
+    kMiscLmax = 8,         // [kMaxG]
+    kMiscCandLg = 16,      // [kMaxG]
+    kMiscGmax = 24,        // [kMaxG]
+    kMiscSumF = 32,        // [kMaxG]
+    kMiscMyRec = 40,       // [kRecWords]
+    kMiscWarpKey = 64,     // [kWarps] u64 -> 16 words
+    kMiscWarpSum = 80,     // [kWarps][kMaxG] i64 -> 128 words (ends at 208) -- placed in red instead
+    kMiscWarpMax = 96,     // [kWarps]
+};
+
+template <int LPR>
+__device__ __forceinline__ float group_butterfly(float v) {
+#pragma unroll
+    for (int d = LPR / 2; d >= 1; d >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, d));
+    return v;
+}
+
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t k) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        uint64_t o = __shfl_xor_sync(0xffffffffu, k, d);
+        k = o < k ? o : k;
+    }
+    return k;
+}
+
+template <int D, int G, bool NAIVE>
+__global__ void __launch_bounds__(kThreads, 1)
+cc_decode_kernel(const __grid_constant__ DecodeParams p) {
+    constexpr int LPR = D / 8;        // lanes per cache row (16-byte slice each)
+    constexpr int RPW = 32 / LPR;     // rows per warp iteration
+    constexpr int NRG = kThreads / LPR;  // row groups in the P.V phase
+    constexpr uint32_t kRowBytes = D * 2;
+    constexpr uint32_t kChunkBytes = kChunkRows * kRowBytes;
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int li = lane % LPR, sub = lane / LPR;
+    const uint32_t C = cluster_nctarank(), rank = cluster_ctarank();
+    const int h = blockIdx.x / C;
+    const CcCacheState& st = p.st;
+    const int L = st.max_cache_length, T = p.rows_per_cta, H = st.n_kv_heads;
+    const int row0 = rank * T;
+    const int nrows = max(0, min(T, L - row0));
+    const int phases = p.a.phases;
+    const bool do_evict = phases & CC_PHASE_EVICT_FILL, do_attend = phases & CC_PHASE_ATTEND,
+               do_score = phases & CC_PHASE_SCORE;
+    const int policy = st.policy;
+    const int NS = p.n_stages, stride = p.lg_stride;
+    const bool needs_epoch = do_evict && (policy == CC_POLICY_RECENT_GLOBAL || policy == CC_POLICY_L2);
+
+    const SmemLayout lay = make_layout(D, G, T, NS, stride);
+    uint8_t* kring = smem + lay.kring;
+    uint8_t* vring = smem + lay.vring;
+    float* lg = reinterpret_cast<float*>(smem + lay.lg);
+    float* red = reinterpret_cast<float*>(smem + lay.red);
+    float* ypart = reinterpret_cast<float*>(smem + lay.ypart);
+    float* yx = reinterpret_cast<float*>(smem + lay.yx);
+    uint32_t* rec = reinterpret_cast<uint32_t*>(smem + lay.rec);
+    unsigned long long* sums = reinterpret_cast<unsigned long long*>(smem + lay.sums);
+    float* x0 = reinterpret_cast<float*>(smem + lay.x0);
+    uint8_t* maskb = smem + lay.maskb;
+    uint64_t* kbar = reinterpret_cast<uint64_t*>(smem + lay.bars);
+    uint64_t* vbar = kbar + NS;
+    float* misc = reinterpret_cast<float*>(smem + lay.misc);
+    uint32_t* miscu = reinterpret_cast<uint32_t*>(misc);
+
+    cluster_arrive_relaxed();  // B0: this CTA has started (its shared memory may be written by peers)
+    bool b0_waited = false;
+
+    const uint16_t* kc = reinterpret_cast<const uint16_t*>(st.k_cache) + (size_t)h * L * D;
+    const uint16_t* vc = reinterpret_cast<const uint16_t*>(st.v_cache) + (size_t)h * L * D;
+    const int n_chunks = do_attend ? (nrows + kChunkRows - 1) / kChunkRows : 0;
+
+    // ---- 0. barriers + all K/V chunks that fit the ring in flight
+    if (tid == 0) {
+        for (int s = 0; s < 2 * NS; ++s) mbar_init(&kbar[s], 1);
+        mbar_fence_init();
+        fence_proxy_async();
+        const int pre = min(NS, n_chunks);
+        for (int c = 0; c < pre; ++c) {
+            const uint32_t bytes = min(kChunkRows, nrows - c * kChunkRows) * kRowBytes;
+            mbar_expect_tx(&kbar[c], bytes);
+            tma_load_1d(kring + c * kChunkBytes, kc + (size_t)(row0 + c * kChunkRows) * D, bytes, &kbar[c]);
+        }
+        for (int c = 0; c < pre; ++c) {
+            const uint32_t bytes = min(kChunkRows, nrows - c * kChunkRows) * kRowBytes;
+            mbar_expect_tx(&vbar[c], bytes);
+            tma_load_1d(vring + c * kChunkBytes, vc + (size_t)(row0 + c * kChunkRows) * D, bytes, &vbar[c]);
+        }
+    }
+    // generation of the cross-cluster "shared reads done" barrier, read by the thread that may
+    // later have to wait on it (lane 0 of the last warp) BEFORE this cluster arrives
+    int32_t gen = 0;
+    if (needs_epoch && tid == kThreads - 32) gen = ld_acquire_gpu(&st.sync_words[1]);
+
+    const int ipos = p.a.input_pos[0];
+    const int pos_row = (st.pos_heads == 1) ? 0 : h;
+    const int32_t* posp = st.pos + (size_t)pos_row * L;
+    for (int i = tid; i < nrows; i += kThreads) maskb[i] = st.mask[(size_t)h * L + row0 + i];
+
+    // query rows of this KV group and the new key/value slices, in registers
+    float q[G][8];
+    uint4 vnew8 = make_uint4(0, 0, 0, 0);
+    if (do_attend) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const uint4 v = *reinterpret_cast<const uint4*>(
+                reinterpret_cast<const uint16_t*>(p.a.q) + (size_t)(h * G + g) * D + li * 8);
+            unpack8(v, q[g]);
+        }
+        if (do_evict)
+            vnew8 = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.a.v_new) + (size_t)h * D + li * 8);
+    }
+
+    // ---- 1. L2 only: key_norm.max() over every head and slot (cache.py:602) = X0 exchange
+    float l2_max = 0.f;
+    if (do_evict && policy == CC_POLICY_L2) {
+        const uint16_t* kn = reinterpret_cast<const uint16_t*>(st.key_norm);
+        float m = -CUDART_INF_F;
+        for (int hh = 0; hh < H; ++hh)
+            for (int i = tid; i < nrows; i += kThreads) m = fmaxf(m, bf16_bits_to_float(kn[(size_t)hh * L + row0 + i]));
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+        if (lane == 0) misc[kMiscWarpMax + warp] = m;
+        __syncthreads();
+        cluster_wait_acquire();
+        b0_waited = true;
+        if (tid < (int)C) {
+            float mm = misc[kMiscWarpMax];
+            for (int w = 1; w < kWarps; ++w) mm = fmaxf(mm, misc[kMiscWarpMax + w]);
+            st_cluster_f32(map_to_rank(smem_u32(&x0[rank]), tid), mm);
+        }
+        cluster_arrive_release();
+        cluster_wait_acquire();
+        l2_max = x0[0];
+        for (uint32_t r = 1; r < C; ++r) l2_max = fmaxf(l2_max, x0[r]);
+    }
+
+    // ---- 2. local arg-min candidate, key = (order(score) << 32) | slot  (first index wins ties)
+    uint64_t ckey = kNoKey;
+    if (do_evict) {
+        if (policy == CC_POLICY_HEAVY_HITTER) {
+            const double* num = reinterpret_cast<const double*>(st.attn_history_num) + (size_t)h * L;
+            const int32_t* den = st.attn_history_denom + (size_t)h * L;
+            for (int i = tid; i < nrows; i += kThreads) {
+                const int s = row0 + i;
+                const int ps = posp[s];
+                // cache.py:727-749: mean accumulated attention; globals & recent -> 1.0; unfilled -> 0.0
+                float avg = __fdiv_rn(__double2float_rn(num[s]), (float)max(den[s], 1));
+                if (ps < st.global_tokens || ps >= ipos - st.recent_window) avg = 1.0f;
+                if (ps == -1) avg = 0.0f;
+                const uint64_t k = ((uint64_t)float_order_key(avg) << 32) | (uint32_t)s;
+                ckey = k < ckey ? k : ckey;
+            }
+        } else if (policy == CC_POLICY_L2) {
+            const uint16_t* kn = reinterpret_cast<const uint16_t*>(st.key_norm) + (size_t)h * L;
+            for (int i = tid; i < nrows; i += kThreads) {
+                const int s = row0 + i;
+                const int ps = posp[s];
+                // cache.py:597-605 then 366-379: bf16(max - norm); recent -> +inf; first g slots -> +inf; unfilled -> -inf
+                float sc = bf16_round(__fsub_rn(l2_max, bf16_bits_to_float(kn[s])));
+                if (ps >= ipos - st.recent_window) sc = CUDART_INF_F;
+                if (s < st.global_tokens) sc = CUDART_INF_F;
+                if (ps == -1) sc = -CUDART_INF_F;
+                const uint64_t k = ((uint64_t)float_order_key(sc) << 32) | (uint32_t)s;
+                ckey = k < ckey ? k : ckey;
+            }
+        } else if (policy == CC_POLICY_RECENT_GLOBAL) {
+            // cache.py:552-556: oldest position among slots >= g (unfilled = -1 first)
+            for (int i = tid; i < nrows; i += kThreads) {
+                const int s = row0 + i;
+                if (s < st.global_tokens) continue;
+                const uint64_t k = ((uint64_t)((uint32_t)posp[s] ^ 0x80000000u) << 32) | (uint32_t)s;
+                ckey = k < ckey ? k : ckey;
+            }
+        } else {  // CC_POLICY_EXTERNAL: the caller chose the slot
+            const int64_t idx = p.a.fill_idx[st.pos_heads == 1 ? 0 : h];
+            if (tid == 0 && idx >= row0 && idx < row0 + nrows) ckey = (uint64_t)(uint32_t)idx;
+        }
+        ckey = warp_min_u64(ckey);
+        if (lane == 0) reinterpret_cast<unsigned long long*>(miscu + kMiscWarpKey)[warp] = ckey;
+        __syncthreads();
+        ckey = reinterpret_cast<unsigned long long*>(miscu + kMiscWarpKey)[0];
+        for (int w = 1; w < kWarps; ++w) {
+            const uint64_t o = reinterpret_cast<unsigned long long*>(miscu + kMiscWarpKey)[w];
+            ckey = o < ckey ? o : ckey;
+        }
+    }
+    const int cand_local = (ckey == kNoKey) ? -1 : (int)(uint32_t)(ckey & 0xffffffffu) - row0;
+
+    // ---- 3. logits over the K ring (canonical dot tree), new-token logits by warp 0
+    if (do_attend) {
+        if (do_evict && warp == 0) {
+            float kf[8];
+            const uint4 kv = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.a.k_new) + (size_t)h * D + li * 8);
+            unpack8(kv, kf);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc = __fmaf_rn(q[g][i], kf[i], acc);
+                acc = group_butterfly<LPR>(acc);
+                const float v = NAIVE ? bf16_round(__fmul_rn(bf16_round(acc), p.scale)) : __fmul_rn(acc, p.scale);
+                if (lane == 0) misc[kMiscNewLg + g] = v;
+            }
+        }
+        __syncthreads();  // maskb visible
+        for (int c = 0; c < n_chunks; ++c) {
+            const int stage = c % NS;
+            mbar_wait(&kbar[stage], (c / NS) & 1);
+            const int rows_c = min(kChunkRows, nrows - c * kChunkRows);
+            const uint8_t* kbase = kring + stage * kChunkBytes;
+            for (int r0 = warp * RPW; r0 < rows_c; r0 += kWarps * RPW) {
+                const int r = r0 + sub;
+                const bool valid = r < rows_c;
+                float kf[8];
+                uint4 kv = make_uint4(0, 0, 0, 0);
+                if (valid) kv = *reinterpret_cast<const uint4*>(kbase + r * kRowBytes + li * 16);
+                unpack8(kv, kf);
+                float dots[G];
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc = __fmaf_rn(q[g][i], kf[i], acc);
+                    dots[g] = group_butterfly<LPR>(acc);
+                }
+                if (valid && li == 0) {
+                    const int row = c * kChunkRows + r;
+                    const bool live = maskb[row];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        // naive path rounds q@k^T to bf16, then * scale to bf16 (attention_utils.py:37)
+                        const float v = NAIVE ? bf16_round(__fmul_rn(bf16_round(dots[g]), p.scale))
+                                              : __fmul_rn(dots[g], p.scale);
+                        lg[g * stride + row] = live ? v : -CUDART_INF_F;
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0 && c + NS < n_chunks) {
+                fence_proxy_async();
+                const int cn = c + NS;
+                const uint32_t bytes = min(kChunkRows, nrows - cn * kChunkRows) * kRowBytes;
+                mbar_expect_tx(&kbar[stage], bytes);
+                tma_load_1d(kring + stage * kChunkBytes, kc + (size_t)(row0 + cn * kChunkRows) * D, bytes, &kbar[stage]);
+            }
+        }
+        // ---- 4. row max without the local candidate, and the candidate's own logits
+        for (int g = warp; g < G; g += kWarps) {
+            float m = -CUDART_INF_F;
+            for (int i = lane; i < nrows; i += 32)
+                if (i != cand_local) m = fmaxf(m, lg[g * stride + i]);
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+            if (lane == 0) {
+                misc[kMiscLmax + g] = m;
+                misc[kMiscCandLg + g] = cand_local >= 0 ? lg[g * stride + cand_local] : -CUDART_INF_F;
+            }
+        }
+    }
+    // ---- 5. X1: every CTA learns every candidate and every partial max
+    if (tid == 0) {
+        miscu[kMiscMyRec + 0] = (uint32_t)(ckey & 0xffffffffu);
+        miscu[kMiscMyRec + 1] = (uint32_t)(ckey >> 32);
+    }
+    __syncthreads();
+    if (tid < G) {
+        miscu[kMiscMyRec + 2 + tid] = __float_as_uint(do_attend ? misc[kMiscLmax + tid] : -CUDART_INF_F);
+        miscu[kMiscMyRec + 2 + G + tid] = __float_as_uint(do_attend ? misc[kMiscCandLg + tid] : -CUDART_INF_F);
+    }
+    __syncthreads();
+    if (!b0_waited) cluster_wait_acquire();
+    constexpr int NW = 2 + 2 * G;
+    for (int idx = tid; idx < (int)C * NW; idx += kThreads) {
+        const int dest = idx / NW, w = idx % NW;
+        st_cluster_u32(map_to_rank(smem_u32(&rec[rank * kRecWords + w]), dest), miscu[kMiscMyRec + w]);
+    }
+    cluster_arrive_release();
+    cluster_wait_acquire();
+
+    // ---- 6. winner + global max per query head
+    uint64_t wkey = kNoKey;
+    for (uint32_t r = 0; r < C; ++r) {
+        const uint64_t k = (uint64_t)rec[r * kRecWords] | ((uint64_t)rec[r * kRecWords + 1] << 32);
+        wkey = k < wkey ? k : wkey;
+    }
+    const bool has_new = do_evict && wkey != kNoKey;
+    const int widx = has_new ? (int)(uint32_t)(wkey & 0xffffffffu) : -1;
+    const int owner = has_new ? widx / T : -1;
+    const bool i_own = has_new && owner == (int)rank;
+    if (needs_epoch && rank == 0 && tid == 0) red_release_gpu_add(&st.sync_words[0], 1);  // shared reads done
+    if (do_attend && tid < G) {
+        float m = has_new ? misc[kMiscNewLg + tid] : -CUDART_INF_F;
+        for (uint32_t r = 0; r < C; ++r) {
+            m = fmaxf(m, __uint_as_float(rec[r * kRecWords + 2 + tid]));
+            const bool has_cand = !(rec[r * kRecWords] == 0xffffffffu && rec[r * kRecWords + 1] == 0xffffffffu);
+            if ((int)r != owner && has_cand) m = fmaxf(m, __uint_as_float(rec[r * kRecWords + 2 + G + tid]));
+        }
+        misc[kMiscGmax + tid] = m;
+        if (i_own) lg[tid * stride + (widx - row0)] = misc[kMiscNewLg + tid];  // the new token attends to itself
+    }
+
+    // ---- 7. owner CTA: in-place slot overwrite (cache.py:390-401 / 460-490) + policy state
+    if (i_own && warp == kWarps - 1) {
+        if (lane < LPR) {
+            const uint16_t* ks = reinterpret_cast<const uint16_t*>(p.a.k_new) + (size_t)h * D + lane * 8;
+            const uint16_t* vs = reinterpret_cast<const uint16_t*>(p.a.v_new) + (size_t)h * D + lane * 8;
+            uint16_t* kd = reinterpret_cast<uint16_t*>(st.k_cache) + ((size_t)h * L + widx) * D + lane * 8;
+            uint16_t* vd = reinterpret_cast<uint16_t*>(st.v_cache) + ((size_t)h * L + widx) * D + lane * 8;
+            *reinterpret_cast<uint4*>(kd) = *reinterpret_cast<const uint4*>(ks);
+            *reinterpret_cast<uint4*>(vd) = *reinterpret_cast<const uint4*>(vs);
+        }
+        float knorm = 0.f;
+        if (policy == CC_POLICY_L2) {
+            // key_norm[idx] = ||k_new||_2 (cache.py:592-593), canonical tree, correctly rounded sqrt
+            float kf[8];
+            const uint4 kv = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.a.k_new) + (size_t)h * D + li * 8);
+            unpack8(kv, kf);
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc = __fmaf_rn(kf[i], kf[i], acc);
+            knorm = __fsqrt_rn(group_butterfly<LPR>(acc));
+        }
+        if (lane == 0) {
+            const int32_t pos_old = posp[widx];
+            st.mask[(size_t)h * L + widx] = 1;
+            if (p.a.fill_idx && policy != CC_POLICY_EXTERNAL) p.a.fill_idx[h] = widx;
+            if (policy == CC_POLICY_HEAVY_HITTER && !do_score) {
+                reinterpret_cast<double*>(st.attn_history_num)[(size_t)h * L + widx] = 0.0;  // cache.py:753-763
+                st.attn_history_denom[(size_t)h * L + widx] = 0;
+            }
+            if (needs_epoch) {  // pos (head-constant) and key_norm are read by every cluster: write after all have read
+                const int32_t target = (gen + 1) * H;
+                while (ld_acquire_gpu(&st.sync_words[0]) - target < 0) {}
+            }
+            if (policy == CC_POLICY_L2)
+                reinterpret_cast<__nv_bfloat16*>(st.key_norm)[(size_t)h * L + widx] = __float2bfloat16_rn(knorm);
+            if (st.pos_heads != 1 || h == 0) st.pos[(size_t)pos_row * L + widx] = ipos;
+            if (h == 0) st.cache_cts[0] += (pos_old == -1) ? 1 : 0;  // cache.py:330, 356-360
+        }
+    }
+    if (needs_epoch && h == 0 && rank == 0 && tid == 32) {
+        // generation bump: only after every cluster has arrived (each read `gen` before arriving)
+        const int32_t g0 = ld_acquire_gpu(&st.sync_words[1]);
+        const int32_t target = (g0 + 1) * H;
+        while (ld_acquire_gpu(&st.sync_words[0]) - target < 0) {}
+        st_release_gpu(&st.sync_words[1], g0 + 1);
+    }
+    __syncthreads();
+
+    if (do_attend) {
+        // ---- 8. exp and the exact fixed-point softmax denominator = X2
+        float gmax[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) gmax[g] = misc[kMiscGmax + g];
+        long long isum[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) isum[g] = 0;
+        for (int i = tid; i < nrows; i += kThreads) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const float e = det_expf(__fsub_rn(lg[g * stride + i], gmax[g]));
+                lg[g * stride + i] = e;
+                isum[g] += __float2ll_rz(__fmul_rn(e, 1099511627776.0f));
+            }
+        }
+        long long* wsum = reinterpret_cast<long long*>(red);  // [kWarps][G], red is free until the P.V phase
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            long long v = isum[g];
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if (lane == 0) wsum[warp * G + g] = v;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < (int)C * G; idx += kThreads) {
+            const int dest = idx / G, g = idx % G;
+            long long v = 0;
+            for (int w = 0; w < kWarps; ++w) v += wsum[w * G + g];
+            st_cluster_u64(map_to_rank(smem_u32(&sums[rank * kMaxG + g]), dest), (uint64_t)v);
+        }
+        cluster_arrive_release();
+        cluster_wait_acquire();
+        if (tid < G) {
+            long long tot = 0;
+            for (uint32_t r = 0; r < C; ++r) tot += (long long)sums[r * kMaxG + tid];
+            misc[kMiscSumF + tid] = __fmul_rn(__ll2float_rn(tot), 9.094947017729282e-13f);  // 2^-40
+        }
+        __syncthreads();
+    }
+
+    // ---- 9. probabilities, GQA pooling (model.py:413-418), score update (cache.py:716-723)
+    {
+        float sumf[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) sumf[g] = do_attend ? misc[kMiscSumF + g] : 1.f;
+        const bool hh_score = do_score && NAIVE && policy == CC_POLICY_HEAVY_HITTER;
+        __nv_bfloat16* probs = reinterpret_cast<__nv_bfloat16*>(p.a.probs);
+        for (int i = tid; i < nrows; i += kThreads) {
+            const int s = row0 + i;
+            float pooled = 0.f;
+            if (do_attend) {
+                float acc = 0.f;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    float pr = __fdiv_rn(lg[g * stride + i], sumf[g]);
+                    if (NAIVE) pr = bf16_round(pr);
+                    lg[g * stride + i] = pr;
+                    acc = g == 0 ? pr : __fadd_rn(acc, pr);
+                }
+                if (NAIVE) {
+                    pooled = bf16_round(__fdiv_rn(acc, (float)G));  // torch mean: fp32 sum / G, then bf16
+                    if (probs) probs[(size_t)h * L + s] = __float2bfloat16_rn(pooled);
+                }
+            } else if (hh_score) {
+                pooled = __bfloat162float(probs[(size_t)h * L + s]);
+            }
+            if (hh_score) {
+                double* num = reinterpret_cast<double*>(st.attn_history_num) + (size_t)h * L;
+                int32_t* den = st.attn_history_denom + (size_t)h * L;
+                const bool fresh = has_new && s == widx;  // evicted slot's history restarts (cache.py:753-763)
+                num[s] = (fresh ? 0.0 : num[s]) + (double)pooled;
+                den[s] = (fresh ? 0 : den[s]) + 1;
+            }
+        }
+        if (hh_score && h == 0 && rank == 0 && tid == 0) st.attn_counter[0] += 1;
+    }
+
+    if (do_attend) {
+        __syncthreads();
+        // ---- 10. y = P.V over the V ring, cluster-wide reduction = X3
+        float acc[G][8];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[g][i] = 0.f;
+        const int rg = tid / LPR;
+        const int patch_row = i_own ? widx - row0 : -1;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int stage = c % NS;
+            mbar_wait(&vbar[stage], (c / NS) & 1);
+            const int rows_c = min(kChunkRows, nrows - c * kChunkRows);
+            const uint8_t* vbase = vring + stage * kChunkBytes;
+            for (int r = rg; r < rows_c; r += NRG) {
+                const int row = c * kChunkRows + r;
+                uint4 vv = *reinterpret_cast<const uint4*>(vbase + r * kRowBytes + li * 16);
+                if (row == patch_row) vv = vnew8;
+                float vf[8];
+                unpack8(vv, vf);
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const float pr = lg[g * stride + row];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[g][i] = fmaf(pr, vf[i], acc[g][i]);
+                }
+            }
+            __syncthreads();
+            if (tid == 0 && c + NS < n_chunks) {
+                fence_proxy_async();
+                const int cn = c + NS;
+                const uint32_t bytes = min(kChunkRows, nrows - cn * kChunkRows) * kRowBytes;
+                mbar_expect_tx(&vbar[stage], bytes);
+                tma_load_1d(vring + stage * kChunkBytes, vc + (size_t)(row0 + cn * kChunkRows) * D, bytes, &vbar[stage]);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float v = acc[g][i];
+#pragma unroll
+                for (int d = 16; d >= LPR; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                acc[g][i] = v;
+            }
+        if (lane < LPR) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float4* dst = reinterpret_cast<float4*>(&red[warp * G * D + g * D + lane * 8]);
+                dst[0] = make_float4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]);
+                dst[1] = make_float4(acc[g][4], acc[g][5], acc[g][6], acc[g][7]);
+            }
+        }
+        __syncthreads();
+        const int SL = G * D / (int)C;  // outputs reduced by each CTA of the cluster
+        for (int o = tid; o < G * D; o += kThreads) {
+            float s = red[o];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) s += red[w * G * D + o];
+            const int dest = o / SL, off = o % SL;
+            st_cluster_f32(map_to_rank(smem_u32(&yx[rank * SL + off]), dest), s);
+        }
+        cluster_arrive_release();
+        cluster_wait_acquire();
+        __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.a.y) + (size_t)h * G * D;
+        for (int t = tid; t < SL; t += kThreads) {
+            float s = yx[t];
+            for (uint32_t r = 1; r < C; ++r) s += yx[r * SL + t];
+            y[rank * SL + t] = __float2bfloat16_rn(s);
+        }
+    }
+    (void)ypart;
+}
+
+// --------------------------------------------------------------------------- host side
+
+using KernelFn = void (*)(const DecodeParams);
+
+template <int D, int G>
+static KernelFn pick_mode(bool naive) {
+    return naive ? (KernelFn)cc_decode_kernel<D, G, true> : (KernelFn)cc_decode_kernel<D, G, false>;
+}
+template <int D>
+static KernelFn pick_group(int G, bool naive) {
+    switch (G) {
+    case 1: return pick_mode<D, 1>(naive);
+    case 2: return pick_mode<D, 2>(naive);
+    case 4: return pick_mode<D, 4>(naive);
+    case 6: return pick_mode<D, 6>(naive);
+    case 7: return pick_mode<D, 7>(naive);
+    case 8: return pick_mode<D, 8>(naive);
+    default: return nullptr;
+    }
+}
+static KernelFn pick_kernel(int D, int G, bool naive) {
+    if (D == 128) return pick_group<128>(G, naive);
+    if (D == 64) return pick_group<64>(G, naive);
+    return nullptr;
+}
+
+struct LaunchPlan {
+    KernelFn fn;
+    int cluster, rows_per_cta, n_stages, lg_stride;
+    uint32_t smem;
+};
+
+static int g_num_sms = 0;
+static int g_smem_optin = 0;
+
+static int device_limits() {
+    if (g_num_sms) return CC_OK;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return set_error(CC_ERR_NO_DEVICE, "no CUDA device");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return set_error(CC_ERR_NO_DEVICE, "cudaGetDeviceProperties failed");
+    if (prop.major != 10) return set_error(CC_ERR_NO_DEVICE, "this library is built for sm_100a (Blackwell B200) only");
+    g_num_sms = prop.multiProcessorCount;
+    g_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    return CC_OK;
+}
+
+// Plans are cached per (shape, policy class): the occupancy query is not free.
+struct PlanKey { int D, G, naive, H, L, epoch; };
+struct PlanEntry { PlanKey k; LaunchPlan p; };
+static PlanEntry g_plans[64];
+static int g_nplans = 0;
+
+static int make_plan(const CcCacheState* st, bool needs_epoch, LaunchPlan* out) {
+    const int D = st->head_dim, G = st->q_per_kv, H = st->n_kv_heads, L = st->max_cache_length;
+    const bool naive = st->attn_mode == CC_ATTN_NAIVE_BF16;
+    for (int i = 0; i < g_nplans; ++i) {
+        const PlanKey& k = g_plans[i].k;
+        if (k.D == D && k.G == G && k.naive == (int)naive && k.H == H && k.L == L && k.epoch == (int)needs_epoch) {
+            *out = g_plans[i].p;
+            return CC_OK;
+        }
+    }
+    int rc = device_limits();
+    if (rc) return rc;
+    KernelFn fn = pick_kernel(D, G, naive);
+    if (!fn) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "unsupported head_dim (64/128) or q_per_kv (1,2,4,6,7,8)");
+    cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    for (int C = kMaxCluster; C >= 1; C >>= 1) {
+        if (H * C > g_num_sms && C > 1) continue;
+        if (C > 1 && L / C < 16) continue;  // keep at least 16 slots per CTA
+        const int T = (L + C - 1) / C;
+        const int n_chunks = (T + kChunkRows - 1) / kChunkRows;
+        const int stride = (T + 31) / 32 * 32;
+        for (int ns = n_chunks < 4 ? n_chunks : 4; ns >= 1; --ns) {
+            const SmemLayout lay = make_layout(D, G, T, ns, stride);
+            if ((int)lay.total > g_smem_optin) continue;
+            if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total) != cudaSuccess) {
+                cudaGetLastError();
+                continue;
+            }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(H * C);
+            cfg.blockDim = dim3(kThreads);
+            cfg.dynamicSmemBytes = lay.total;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = C; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr; cfg.numAttrs = 1;
+            int max_clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
+            // with the cross-head epoch barrier every cluster must be co-resident
+            if (max_clusters < (needs_epoch ? H : 1)) continue;
+            LaunchPlan p = {fn, C, T, ns, stride, lay.total};
+            if (g_nplans < 64) g_plans[g_nplans++] = {{D, G, (int)naive, H, L, (int)needs_epoch}, p};
+            *out = p;
+            return CC_OK;
+        }
+    }
+    return set_error(CC_ERR_UNSUPPORTED_SHAPE, "no cluster size / shared-memory plan fits this cache shape");
+}
+
+static int validate(const CcCacheState* st, const CcDecodeArgs* a) {
+    if (!st || !a) return set_error(CC_ERR_INVALID_ARG, "null state or args");
+    if (st->n_kv_heads < 1 || st->q_per_kv < 1 || st->max_cache_length < 1) return set_error(CC_ERR_INVALID_ARG, "bad shape");
+    if (st->policy < CC_POLICY_EXTERNAL || st->policy > CC_POLICY_HYBRID) return set_error(CC_ERR_INVALID_ARG, "bad policy");
+    if (st->policy == CC_POLICY_HYBRID) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "hybrid policy: use cc_decode_step_hybrid build (not in this build)");
+    if (!st->k_cache || !st->v_cache || !st->pos || !st->mask || !st->cache_cts) return set_error(CC_ERR_INVALID_ARG, "null cache buffer");
+    if (st->pos_heads != 1 && st->pos_heads != st->n_kv_heads) return set_error(CC_ERR_INVALID_ARG, "pos_heads must be 1 or n_kv_heads");
+    const int phases = a->phases;
+    if (phases < 1 || phases > CC_PHASE_ALL) return set_error(CC_ERR_INVALID_ARG, "bad phases mask");
+    if (!a->input_pos) return set_error(CC_ERR_INVALID_ARG, "null input_pos");
+    if ((phases & CC_PHASE_EVICT_FILL) && (!a->k_new || !a->v_new)) return set_error(CC_ERR_INVALID_ARG, "evict/fill needs k_new and v_new");
+    if ((phases & CC_PHASE_ATTEND) && (!a->q || !a->y)) return set_error(CC_ERR_INVALID_ARG, "attend needs q and y");
+    if (st->policy == CC_POLICY_EXTERNAL && (phases & CC_PHASE_EVICT_FILL) && !a->fill_idx)
+        return set_error(CC_ERR_INVALID_ARG, "external policy needs fill_idx");
+    if (st->policy == CC_POLICY_HEAVY_HITTER) {
+        if (st->history_window != 1) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "heavy_hitter kernel needs history_window_size == 1");
+        if (!st->attn_history_num || !st->attn_history_denom || !st->attn_counter) return set_error(CC_ERR_INVALID_ARG, "null heavy_hitter state");
+        if (st->attn_mode != CC_ATTN_NAIVE_BF16) return set_error(CC_ERR_INVALID_ARG, "heavy_hitter needs the naive (probability-returning) attention mode");
+        if ((phases & CC_PHASE_SCORE) && !(phases & CC_PHASE_ATTEND) && !a->probs) return set_error(CC_ERR_INVALID_ARG, "score-only phase needs probs");
+    }
+    if (st->policy == CC_POLICY_L2 && !st->key_norm) return set_error(CC_ERR_INVALID_ARG, "null key_norm");
+    if ((st->policy == CC_POLICY_RECENT_GLOBAL || st->policy == CC_POLICY_L2) && !st->sync_words)
+        return set_error(CC_ERR_INVALID_ARG, "this policy needs sync_words");
+    if (st->policy == CC_POLICY_RECENT_GLOBAL && st->global_tokens >= st->max_cache_length)
+        return set_error(CC_ERR_INVALID_ARG, "global_tokens must be < max_cache_length");
+    return CC_OK;
+}
+
+int decode_step_impl(const CcCacheState* st, const CcDecodeArgs* a, cudaStream_t stream) {
+    int rc = validate(st, a);
+    if (rc) return rc;
+    const bool needs_epoch = (a->phases & CC_PHASE_EVICT_FILL) &&
+                             (st->policy == CC_POLICY_RECENT_GLOBAL || st->policy == CC_POLICY_L2);
+    LaunchPlan plan;
+    rc = make_plan(st, needs_epoch, &plan);
+    if (rc) return rc;
+    DecodeParams p;
+    p.st = *st;
+    p.a = *a;
+    p.rows_per_cta = plan.rows_per_cta;
+    p.n_stages = plan.n_stages;
+    p.lg_stride = plan.lg_stride;
+    p.scale = (float)(1.0 / sqrt((double)st->head_dim));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(st->n_kv_heads * plan.cluster);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = plan.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = plan.cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, plan.fn, p);
+    if (e != cudaSuccess) return set_cuda_error(e, "cc_decode_step launch");
+    return CC_OK;
+}
+
+int decode_cluster_size_impl(const CcCacheState* st) {
+    if (!st) return set_error(CC_ERR_INVALID_ARG, "null state");
+    LaunchPlan plan;
+    const bool needs_epoch = st->policy == CC_POLICY_RECENT_GLOBAL || st->policy == CC_POLICY_L2;
+    int rc = make_plan(st, needs_epoch, &plan);
+    return rc ? rc : plan.cluster;
+}
+
+}  // namespace cc

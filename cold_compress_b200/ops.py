@@ -1,0 +1,108 @@
+"""PyTorch custom ops over the C ABI (include/cc_b200.h).
+
+`torch.ops.cold_compress_b200.decode_step` is the fused per-layer decode step; it mutates the
+cache buffers in place and is registered with a schema that says so, so that functionalisation
+and CUDA-graph capture see the writes.  Ops exist for CUDA tensors only: calling them with CPU
+tensors raises (there is no CPU path in the product).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_LIB_NAME = "cold_compress_b200"
+_library = torch.library.Library(_LIB_NAME, "DEF")
+
+# order of the tensors in `state` (empty tensor = NULL); must match _lib._STATE_PTRS
+STATE_ORDER = _lib._STATE_PTRS
+META_ORDER = _lib._STATE_INTS
+
+_library.define(
+    "decode_step(Tensor q, Tensor k_new, Tensor v_new, Tensor input_pos, Tensor(a!)[] state, int[] meta, "
+    "Tensor(b!) y, Tensor(c!) fill_idx, Tensor(d!) probs, int phases, bool is_punc) -> ()")
+_library.define("key_norms(Tensor k, Tensor(a!) key_norm) -> ()")
+_library.define(
+    "prefill_gather(Tensor(a!)[] state, int[] meta, Tensor k_prompt, Tensor v_prompt, Tensor keep_idx) -> ()")
+
+
+def _ptr(t: torch.Tensor):
+    return t.data_ptr() if t.numel() else None
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+_state_cache: dict = {}
+
+
+def _c_state(state, meta) -> _lib.CcCacheState:
+    key = (tuple(t.data_ptr() for t in state), tuple(meta))
+    st = _state_cache.get(key)
+    if st is None:
+        st = _lib.CcCacheState()
+        for name, v in zip(META_ORDER, meta):
+            setattr(st, name, int(v))
+        for name, t in zip(STATE_ORDER, state):
+            setattr(st, name, _ptr(t))
+        if len(_state_cache) > 4096:
+            _state_cache.clear()
+        _state_cache[key] = st
+    return st
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t.numel() and not t.is_cuda:
+            raise _lib.CcError("cold_compress_b200 ops run on CUDA tensors only (no CPU fallback)")
+        if t.numel() and not t.is_contiguous():
+            raise _lib.CcError("cold_compress_b200 ops need contiguous tensors")
+
+
+def _decode_step(q, k_new, v_new, input_pos, state, meta, y, fill_idx, probs, phases, is_punc):
+    _require_cuda(q, k_new, v_new, input_pos, y, fill_idx, probs, *state)
+    lib = _lib.load()
+    st = _c_state(state, meta)
+    a = _lib.CcDecodeArgs()
+    a.q, a.k_new, a.v_new, a.input_pos = _ptr(q), _ptr(k_new), _ptr(v_new), _ptr(input_pos)
+    a.y, a.fill_idx, a.probs = _ptr(y), _ptr(fill_idx), _ptr(probs)
+    a.is_punc, a.phases = int(is_punc), int(phases)
+    _lib.check(lib.cc_decode_step(C.byref(st), C.byref(a), _stream()), "cc_decode_step")
+
+
+def _key_norms(k, key_norm):
+    _require_cuda(k, key_norm)
+    lib = _lib.load()
+    head_dim = k.shape[-1]
+    _lib.check(lib.cc_key_norms(_ptr(k), _ptr(key_norm), k.numel() // head_dim, head_dim, _stream()), "cc_key_norms")
+
+
+def _prefill_gather(state, meta, k_prompt, v_prompt, keep_idx):
+    _require_cuda(k_prompt, v_prompt, keep_idx, *state)
+    lib = _lib.load()
+    st = _c_state(state, meta)
+    keep_heads = 1 if keep_idx.dim() == 1 else keep_idx.shape[0]
+    n_keep = keep_idx.shape[-1]
+    prompt_len = k_prompt.shape[-2]
+    _lib.check(lib.cc_prefill_gather(C.byref(st), _ptr(k_prompt), _ptr(v_prompt), _ptr(keep_idx), keep_heads,
+                                     n_keep, prompt_len, _stream()), "cc_prefill_gather")
+
+
+_library.impl("decode_step", _decode_step, "CUDA")
+_library.impl("key_norms", _key_norms, "CUDA")
+_library.impl("prefill_gather", _prefill_gather, "CUDA")
+
+
+def _no_cpu(*_a, **_k):
+    raise _lib.CcError("cold_compress_b200 ops have no CPU implementation: the decode path is CUDA (sm_100a) only")
+
+
+for _name in ("decode_step", "key_norms", "prefill_gather"):
+    _library.impl(_name, _no_cpu, "CPU")
+
+decode_step = torch.ops.cold_compress_b200.decode_step
+key_norms = torch.ops.cold_compress_b200.key_norms
+prefill_gather = torch.ops.cold_compress_b200.prefill_gather
