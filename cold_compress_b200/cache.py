@@ -207,9 +207,9 @@ class KVCache(nn.Module):
             G = self._q_per_kv or 1
         out = self._outputs(G, dev, self.k_cache.dtype)
         e = self._empty
-        fill_idx = self._fill_idx
+        fill_idx = self._fill_idx  # static address: in for EXTERNAL, out (the eviction trace) otherwise
         if self.policy == _lib.POLICY_EXTERNAL and (phases & _lib.PHASE_EVICT_FILL):
-            fill_idx = self._external_fill_idx(input_pos).to(torch.int64).contiguous()
+            fill_idx.copy_(self._external_fill_idx(input_pos).to(torch.int64).reshape(-1).expand(self.n_heads))
         probs = out["probs"] if self.return_attn() else e
         if probs_in is not None:
             probs = probs_in.reshape(self.n_heads, -1).contiguous()
@@ -398,6 +398,9 @@ class KVCacheHybrid(KVCacheHeavyHitter):
             self.register_buffer("punc_mask", torch.zeros((max_batch_size, n_heads, L), dtype=torch.bool))
             self.register_buffer("num_punc", torch.zeros((1,), dtype=torch.int))
         self.register_buffer("cache_strategies", torch.zeros(n_heads, dtype=torch.int64))
+        # running fp64 sum of each slot's ring, maintained by the kernel (the reference re-sums the ring)
+        self.register_buffer("attn_history_sum", torch.zeros((max_batch_size, n_heads, L), dtype=torch.float64),
+                             persistent=False)
         self.register_buffer("_hyb_bits", torch.zeros(n_heads, dtype=torch.int32), persistent=False)
         self.register_buffer("_hyb_rw", torch.zeros(n_heads, dtype=torch.int32), persistent=False)
         self.register_buffer("_hyb_hh", torch.zeros(n_heads, dtype=torch.int32), persistent=False)
@@ -428,8 +431,13 @@ class KVCacheHybrid(KVCacheHeavyHitter):
         names = [self.hybrid_strategies[int(i)]["strategy"] for i in ids]
         self.requires_heavy_hitter = any("heavy_hitter" in n for n in names)
 
+    def resync_history(self):
+        """Recompute the running ring sums from the ring (after the ring was written from outside)."""
+        self.attn_history_sum.copy_(self.attn_history_num.to(torch.float64).sum(dim=-1))
+
     def reset(self):
         super().reset()
+        self.attn_history_sum.zero_()
         names = [s["strategy"] for s in self.hybrid_strategies]
         self.requires_heavy_hitter = any("heavy_hitter" in n for n in names)
         for n in ("special_mask", "num_special", "punc_mask", "num_punc"):

@@ -8,16 +8,18 @@
 // (cache.py:690-723), which run there as ~25 ATen ops and materialise 4x K/V copies.
 //
 // Shape of the launch (HBM-latency bound: 4 MiB of K/V per layer at L=1024):
-//   * one thread-block CLUSTER per KV head, C CTAs (<=16) per cluster, each CTA owns a
-//     contiguous range of ceil(L/C) cache slots -> Hkv*C CTAs (128 of 148 SMs for Llama-3-8B);
-//   * K and V rows of that range are streamed by the TMA engine (cp.async.bulk, UBLKCP) into
-//     a shared-memory ring, all chunks in flight from the first instruction;
+//   * one thread-block CLUSTER per KV head, C CTAs (<=16) per cluster; the cache rows of the head
+//     are cut into chunks of CH rows (16/32/64) dealt round-robin to the CTAs of the cluster, so
+//     a head whose live slots are a prefix (hybrid, caches still filling) stays balanced
+//     -> Hkv*C CTAs (128 of 148 SMs for Llama-3-8B);
+//   * the K and V rows of each chunk are streamed by the TMA engine (cp.async.bulk, UBLKCP) into
+//     a shared-memory ring, as many chunks in flight as the ring holds from the first instruction;
 //   * three DSMEM all-to-all exchanges per step: {arg-min candidate, row max}, {softmax sum},
 //     {P.V partials}; the first one carries both the eviction decision and the softmax max, so
 //     the evicted slot's old logit is excluded / the new token's logit included without a
-//     second pass;
+//     second pass over K;
 //   * arithmetic order is the bit-reproducible definition in common.cuh (canonical dot tree,
-//     det_expf, 2^-40 fixed-point sum), so the eviction indices do not depend on C or on the
+//     det_expf, 2^-40 fixed-point sum), so eviction indices do not depend on C, CH or the
 //     thread count.
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -32,7 +34,6 @@ namespace cc {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kChunkRows = 64;   // rows per TMA chunk (16 KiB at D=128)
 constexpr int kMaxCluster = 16;
 constexpr int kMaxG = 8;
 constexpr int kRecWords = 2 + 2 * kMaxG;  // X1 record: key64, lmax[G], candlogit[G]
@@ -41,50 +42,52 @@ constexpr uint64_t kNoKey = ~0ull;
 struct DecodeParams {
     CcCacheState st;
     CcDecodeArgs a;
-    int rows_per_cta;   // T
+    int ch_shift;       // log2(rows per chunk)
+    int max_local_chunks;  // chunks dealt to rank 0 (the most any CTA gets)
     int n_stages;       // ring depth for K and for V
-    int lg_stride;      // floats per query head in the logit/prob array (>= T)
+    int lg_stride;      // floats per query head in the logit/prob array
     float scale;        // (float)(1/sqrt(D))
 };
 
 struct SmemLayout {
-    uint32_t kring, vring, lg, red, ypart, yx, rec, sums, x0, maskb, bars, misc, total;
+    uint32_t kring, vring, lg, red, yx, rec, sums, x0, maskb, bars, misc, total;
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline SmemLayout make_layout(int D, int G, int T, int n_stages, int lg_stride) {
+__host__ __device__ inline SmemLayout make_layout(int D, int G, int chunk_rows, int local_rows, int n_stages, int lg_stride) {
     SmemLayout s;
     uint32_t off = 0;
-    const uint32_t chunk_bytes = kChunkRows * D * 2;
-    s.kring = off; off += n_stages * chunk_bytes;
-    s.vring = off; off += n_stages * chunk_bytes;
+    const uint32_t chunk_bytes = chunk_rows * D * 2;
+    s.kring = off; off += align_up(n_stages * chunk_bytes, 128);
+    s.vring = off; off += align_up(n_stages * chunk_bytes, 128);
     s.lg = off;    off += align_up(G * lg_stride * 4, 128);
     s.red = off;   off += kWarps * G * D * 4;
-    s.ypart = off; off += G * D * 4;
     s.yx = off;    off += G * D * 4;
     s.rec = off;   off += kMaxCluster * kRecWords * 4;
     s.sums = off;  off += kMaxCluster * kMaxG * 8;
-    s.x0 = off;    off += kMaxCluster * 4 + 64;
-    s.maskb = off; off += align_up(T, 128);
+    s.x0 = off;    off += 128;
+    s.maskb = off; off += align_up(local_rows, 128);
     s.bars = off;  off += align_up(2 * n_stages * 8, 128);
     s.misc = off;  off += 512;
     s.total = off;
     return s;
 }
 
-// misc area (floats / ints), indices in 4-byte words
+// misc area, indices in 4-byte words
 enum : int {
-    kMiscNewLg = 0,        // [kMaxG] logits of the new token
-    kMiscLmax = 8,         // [kMaxG]
-    kMiscCandLg = 16,      // [kMaxG]
-    kMiscGmax = 24,        // [kMaxG]
-    kMiscSumF = 32,        // [kMaxG]
-    kMiscMyRec = 40,       // [kRecWords]
-    kMiscWarpKey = 64,     // [kWarps] u64 -> 16 words
-    kMiscWarpSum = 80,     // [kWarps][kMaxG] i64 -> 128 words (ends at 208) -- placed in red instead
-    kMiscWarpMax = 96,     // [kWarps]
+    kMiscNewLg = 0,     // [kMaxG] logits of the new token
+    kMiscLmax = 8,      // [kMaxG]
+    kMiscCandLg = 16,   // [kMaxG]
+    kMiscGmax = 24,     // [kMaxG]
+    kMiscSumF = 32,     // [kMaxG]
+    kMiscMyRec = 40,    // [kRecWords]
+    kMiscWarpKey = 64,  // [kWarps] u64
+    kMiscWarpMax = 96,  // [kWarps]
 };
+
+// hybrid per-head decision (reference cache.py:896-950)
+enum : int { kHybAppend = 0, kHybEvict = 1, kHybDrop = 2 };
 
 template <int LPR>
 __device__ __forceinline__ float group_butterfly(float v) {
@@ -105,34 +108,41 @@ __device__ __forceinline__ uint64_t warp_min_u64(uint64_t k) {
 template <int D, int G, bool NAIVE>
 __global__ void __launch_bounds__(kThreads, 1)
 cc_decode_kernel(const __grid_constant__ DecodeParams p) {
-    constexpr int LPR = D / 8;        // lanes per cache row (16-byte slice each)
-    constexpr int RPW = 32 / LPR;     // rows per warp iteration
+    constexpr int LPR = D / 8;           // lanes per cache row (16-byte slice each)
+    constexpr int RPW = 32 / LPR;        // rows per warp iteration
     constexpr int NRG = kThreads / LPR;  // row groups in the P.V phase
     constexpr uint32_t kRowBytes = D * 2;
-    constexpr uint32_t kChunkBytes = kChunkRows * kRowBytes;
 
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int li = lane % LPR, sub = lane / LPR;
-    const uint32_t C = cluster_nctarank(), rank = cluster_ctarank();
+    const int C = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
     const int h = blockIdx.x / C;
     const CcCacheState& st = p.st;
-    const int L = st.max_cache_length, T = p.rows_per_cta, H = st.n_kv_heads;
-    const int row0 = rank * T;
-    const int nrows = max(0, min(T, L - row0));
+    const int L = st.max_cache_length, H = st.n_kv_heads;
+    const int chs = p.ch_shift, CH = 1 << chs;
+    const uint32_t chunk_bytes = CH * kRowBytes;
     const int phases = p.a.phases;
     const bool do_evict = phases & CC_PHASE_EVICT_FILL, do_attend = phases & CC_PHASE_ATTEND,
                do_score = phases & CC_PHASE_SCORE;
     const int policy = st.policy;
+    const bool hybrid = policy == CC_POLICY_HYBRID;
     const int NS = p.n_stages, stride = p.lg_stride;
-    const bool needs_epoch = do_evict && (policy == CC_POLICY_RECENT_GLOBAL || policy == CC_POLICY_L2);
+    // shared (cross-head) state is read by every cluster and written by one: order with an epoch barrier
+    const bool needs_epoch = (do_evict && (policy == CC_POLICY_RECENT_GLOBAL || policy == CC_POLICY_L2)) ||
+                             (hybrid && (do_evict || do_score));
 
-    const SmemLayout lay = make_layout(D, G, T, NS, stride);
+    // chunk-cyclic ownership: local chunk j <-> global chunk rank + j*C; local row lr = j*CH + r
+    const int n_chunks_total = (L + CH - 1) >> chs;
+    const int nlc = n_chunks_total > rank ? (n_chunks_total - rank + C - 1) / C : 0;
+    const int local_rows = nlc << chs;
+    auto slot_of = [&](int lr) { return (((lr >> chs) * C + rank) << chs) + (lr & (CH - 1)); };
+
+    const SmemLayout lay = make_layout(D, G, CH, p.max_local_chunks << chs, NS, stride);
     uint8_t* kring = smem + lay.kring;
     uint8_t* vring = smem + lay.vring;
     float* lg = reinterpret_cast<float*>(smem + lay.lg);
     float* red = reinterpret_cast<float*>(smem + lay.red);
-    float* ypart = reinterpret_cast<float*>(smem + lay.ypart);
     float* yx = reinterpret_cast<float*>(smem + lay.yx);
     uint32_t* rec = reinterpret_cast<uint32_t*>(smem + lay.rec);
     unsigned long long* sums = reinterpret_cast<unsigned long long*>(smem + lay.sums);
@@ -146,25 +156,57 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     cluster_arrive_relaxed();  // B0: this CTA has started (its shared memory may be written by peers)
     bool b0_waited = false;
 
+    const int ipos = p.a.input_pos[0];
+    const int pos_row = (st.pos_heads == 1) ? 0 : h;
+    const int32_t* posp = st.pos + (size_t)pos_row * L;
+
+    // ---- hybrid: per-head decision from scalars (every CTA of the cluster computes the same)
+    int hyb_mode = kHybAppend, hyb_bits = 0, hyb_cts = 0, hyb_rw = 0;
+    int64_t hyb_counter = 0;
+    int live_limit = L;  // slots >= live_limit cannot be live: their chunks are never loaded
+    if (hybrid) {
+        hyb_bits = st.hyb_strategy_bits[h];
+        hyb_cts = st.cache_cts[h];
+        hyb_rw = (hyb_bits & CC_HYB_WINDOW) ? st.hyb_recent_window[h] : 0;
+        if (st.attn_counter) hyb_counter = st.attn_counter[0];
+        if (do_evict) {
+            if (((hyb_bits & CC_HYB_PUNC) && p.a.is_punc) || (hyb_bits & CC_HYB_FULL)) {
+                hyb_mode = kHybAppend;
+            } else {
+                int budget = st.global_tokens;
+                if ((hyb_bits & CC_HYB_SPECIAL) && st.num_special) budget += st.num_special[0];
+                if ((hyb_bits & CC_HYB_PUNC) && st.num_punc) budget += st.num_punc[0];
+                if (hyb_bits & CC_HYB_WINDOW) budget += st.hyb_recent_window[h];
+                if (hyb_bits & CC_HYB_HEAVY_HITTER) budget += st.hyb_heavy_budget[h];
+                hyb_mode = hyb_cts < budget ? kHybAppend
+                         : (hyb_bits & (CC_HYB_HEAVY_HITTER | CC_HYB_WINDOW)) ? kHybEvict : kHybDrop;
+            }
+        }
+        live_limit = min(L, hyb_cts + ((do_evict && hyb_mode == kHybAppend) ? 1 : 0));
+    }
+    const int live_chunks_total = (live_limit + CH - 1) >> chs;
+    const int nlc_live = do_attend ? (live_chunks_total > rank ? (live_chunks_total - rank + C - 1) / C : 0) : 0;
+    const int live_rows = nlc_live << chs;
+
     const uint16_t* kc = reinterpret_cast<const uint16_t*>(st.k_cache) + (size_t)h * L * D;
     const uint16_t* vc = reinterpret_cast<const uint16_t*>(st.v_cache) + (size_t)h * L * D;
-    const int n_chunks = do_attend ? (nrows + kChunkRows - 1) / kChunkRows : 0;
+    auto chunk_rows_valid = [&](int j) { return min(CH, L - (((j * C + rank)) << chs)); };
 
-    // ---- 0. barriers + all K/V chunks that fit the ring in flight
+    // ---- 0. barriers + as many K/V chunks in flight as the ring holds
     if (tid == 0) {
         for (int s = 0; s < 2 * NS; ++s) mbar_init(&kbar[s], 1);
         mbar_fence_init();
         fence_proxy_async();
-        const int pre = min(NS, n_chunks);
-        for (int c = 0; c < pre; ++c) {
-            const uint32_t bytes = min(kChunkRows, nrows - c * kChunkRows) * kRowBytes;
-            mbar_expect_tx(&kbar[c], bytes);
-            tma_load_1d(kring + c * kChunkBytes, kc + (size_t)(row0 + c * kChunkRows) * D, bytes, &kbar[c]);
+        const int pre = min(NS, nlc_live);
+        for (int j = 0; j < pre; ++j) {
+            const uint32_t bytes = chunk_rows_valid(j) * kRowBytes;
+            mbar_expect_tx(&kbar[j], bytes);
+            tma_load_1d(kring + j * chunk_bytes, kc + ((size_t)(j * C + rank) << chs) * D, bytes, &kbar[j]);
         }
-        for (int c = 0; c < pre; ++c) {
-            const uint32_t bytes = min(kChunkRows, nrows - c * kChunkRows) * kRowBytes;
-            mbar_expect_tx(&vbar[c], bytes);
-            tma_load_1d(vring + c * kChunkBytes, vc + (size_t)(row0 + c * kChunkRows) * D, bytes, &vbar[c]);
+        for (int j = 0; j < pre; ++j) {
+            const uint32_t bytes = chunk_rows_valid(j) * kRowBytes;
+            mbar_expect_tx(&vbar[j], bytes);
+            tma_load_1d(vring + j * chunk_bytes, vc + ((size_t)(j * C + rank) << chs) * D, bytes, &vbar[j]);
         }
     }
     // generation of the cross-cluster "shared reads done" barrier, read by the thread that may
@@ -172,12 +214,12 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     int32_t gen = 0;
     if (needs_epoch && tid == kThreads - 32) gen = ld_acquire_gpu(&st.sync_words[1]);
 
-    const int ipos = p.a.input_pos[0];
-    const int pos_row = (st.pos_heads == 1) ? 0 : h;
-    const int32_t* posp = st.pos + (size_t)pos_row * L;
-    for (int i = tid; i < nrows; i += kThreads) maskb[i] = st.mask[(size_t)h * L + row0 + i];
+    for (int lr = tid; lr < local_rows; lr += kThreads) {
+        const int s = slot_of(lr);
+        maskb[lr] = (s < L) ? st.mask[(size_t)h * L + s] : 0;
+    }
 
-    // query rows of this KV group and the new key/value slices, in registers
+    // query rows of this KV group and the new value slice, in registers
     float q[G][8];
     uint4 vnew8 = make_uint4(0, 0, 0, 0);
     if (do_attend) {
@@ -197,14 +239,17 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         const uint16_t* kn = reinterpret_cast<const uint16_t*>(st.key_norm);
         float m = -CUDART_INF_F;
         for (int hh = 0; hh < H; ++hh)
-            for (int i = tid; i < nrows; i += kThreads) m = fmaxf(m, bf16_bits_to_float(kn[(size_t)hh * L + row0 + i]));
+            for (int lr = tid; lr < local_rows; lr += kThreads) {
+                const int s = slot_of(lr);
+                if (s < L) m = fmaxf(m, bf16_bits_to_float(kn[(size_t)hh * L + s]));
+            }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
         if (lane == 0) misc[kMiscWarpMax + warp] = m;
         __syncthreads();
         cluster_wait_acquire();
         b0_waited = true;
-        if (tid < (int)C) {
+        if (tid < C) {
             float mm = misc[kMiscWarpMax];
             for (int w = 1; w < kWarps; ++w) mm = fmaxf(mm, misc[kMiscWarpMax + w]);
             st_cluster_f32(map_to_rank(smem_u32(&x0[rank]), tid), mm);
@@ -212,7 +257,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         cluster_arrive_release();
         cluster_wait_acquire();
         l2_max = x0[0];
-        for (uint32_t r = 1; r < C; ++r) l2_max = fmaxf(l2_max, x0[r]);
+        for (int r = 1; r < C; ++r) l2_max = fmaxf(l2_max, x0[r]);
     }
 
     // ---- 2. local arg-min candidate, key = (order(score) << 32) | slot  (first index wins ties)
@@ -221,8 +266,9 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         if (policy == CC_POLICY_HEAVY_HITTER) {
             const double* num = reinterpret_cast<const double*>(st.attn_history_num) + (size_t)h * L;
             const int32_t* den = st.attn_history_denom + (size_t)h * L;
-            for (int i = tid; i < nrows; i += kThreads) {
-                const int s = row0 + i;
+            for (int lr = tid; lr < local_rows; lr += kThreads) {
+                const int s = slot_of(lr);
+                if (s >= L) continue;
                 const int ps = posp[s];
                 // cache.py:727-749: mean accumulated attention; globals & recent -> 1.0; unfilled -> 0.0
                 float avg = __fdiv_rn(__double2float_rn(num[s]), (float)max(den[s], 1));
@@ -233,8 +279,9 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             }
         } else if (policy == CC_POLICY_L2) {
             const uint16_t* kn = reinterpret_cast<const uint16_t*>(st.key_norm) + (size_t)h * L;
-            for (int i = tid; i < nrows; i += kThreads) {
-                const int s = row0 + i;
+            for (int lr = tid; lr < local_rows; lr += kThreads) {
+                const int s = slot_of(lr);
+                if (s >= L) continue;
                 const int ps = posp[s];
                 // cache.py:597-605 then 366-379: bf16(max - norm); recent -> +inf; first g slots -> +inf; unfilled -> -inf
                 float sc = bf16_round(__fsub_rn(l2_max, bf16_bits_to_float(kn[s])));
@@ -246,15 +293,48 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             }
         } else if (policy == CC_POLICY_RECENT_GLOBAL) {
             // cache.py:552-556: oldest position among slots >= g (unfilled = -1 first)
-            for (int i = tid; i < nrows; i += kThreads) {
-                const int s = row0 + i;
-                if (s < st.global_tokens) continue;
+            for (int lr = tid; lr < local_rows; lr += kThreads) {
+                const int s = slot_of(lr);
+                if (s >= L || s < st.global_tokens) continue;
                 const uint64_t k = ((uint64_t)((uint32_t)posp[s] ^ 0x80000000u) << 32) | (uint32_t)s;
                 ckey = k < ckey ? k : ckey;
             }
+        } else if (hybrid) {
+            if (hyb_mode == kHybEvict) {
+                // cache.py:844-894 over the live prefix [0, cts): mean ring attention (or position for
+                // window-only heads); first g slots, special, punctuation and the recent window are saved
+                const int W = st.history_window;
+                const int32_t* den = st.attn_history_denom + (size_t)h * L;
+                const double* hsum = st.attn_history_sum + (size_t)h * L;
+                for (int lr = tid; lr < local_rows; lr += kThreads) {
+                    const int s = slot_of(lr);
+                    if (s >= hyb_cts) continue;
+                    const int ps = posp[s];
+                    float sc;
+                    if (hyb_bits & CC_HYB_HEAVY_HITTER) {
+                        const float d = (float)min(den[s], W);
+                        sc = __fdiv_rn(bf16_round(__double2float_rn(hsum[s])), d);
+                    } else {
+                        sc = (float)ps;
+                    }
+                    bool save = s < st.global_tokens;
+                    if ((hyb_bits & CC_HYB_SPECIAL) && st.special_mask) save |= st.special_mask[(size_t)h * L + s] != 0;
+                    if ((hyb_bits & CC_HYB_PUNC) && st.punc_mask) save |= st.punc_mask[(size_t)h * L + s] != 0;
+                    if ((hyb_bits & CC_HYB_WINDOW) && ps > ipos - hyb_rw) save = true;  // strict >
+                    if (save) sc = CUDART_INF_F;
+                    // torch.argmin treats NaN (0/0) as the minimum
+                    const uint32_t hi = (sc != sc) ? 0u : float_order_key(sc);
+                    const uint64_t k = ((uint64_t)hi << 32) | (uint32_t)s;
+                    ckey = k < ckey ? k : ckey;
+                }
+            } else {
+                // append at min(L-1, cts); a dropped token is parked in slot L-1 (cache.py:973-979)
+                const int idx = hyb_mode == kHybAppend ? min(L - 1, hyb_cts) : L - 1;
+                if (tid == 0 && ((idx >> chs) % C) == rank) ckey = (uint64_t)(uint32_t)idx;
+            }
         } else {  // CC_POLICY_EXTERNAL: the caller chose the slot
             const int64_t idx = p.a.fill_idx[st.pos_heads == 1 ? 0 : h];
-            if (tid == 0 && idx >= row0 && idx < row0 + nrows) ckey = (uint64_t)(uint32_t)idx;
+            if (tid == 0 && idx >= 0 && idx < L && (((int)idx >> chs) % C) == rank) ckey = (uint64_t)(uint32_t)idx;
         }
         ckey = warp_min_u64(ckey);
         if (lane == 0) reinterpret_cast<unsigned long long*>(miscu + kMiscWarpKey)[warp] = ckey;
@@ -265,11 +345,18 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             ckey = o < ckey ? o : ckey;
         }
     }
-    const int cand_local = (ckey == kNoKey) ? -1 : (int)(uint32_t)(ckey & 0xffffffffu) - row0;
+    // local row of this CTA's candidate (it owns the slot by construction)
+    int cand_local = -1;
+    if (ckey != kNoKey) {
+        const int s = (int)(uint32_t)(ckey & 0xffffffffu);
+        cand_local = (((s >> chs) / C) << chs) + (s & (CH - 1));
+    }
+    // a dropped token does not take part in attention (its slot's mask stays as it was)
+    const bool attend_new = do_evict && !(hybrid && hyb_mode == kHybDrop);
 
     // ---- 3. logits over the K ring (canonical dot tree), new-token logits by warp 0
     if (do_attend) {
-        if (do_evict && warp == 0) {
+        if (attend_new && warp == 0) {
             float kf[8];
             const uint4 kv = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.a.k_new) + (size_t)h * D + li * 8);
             unpack8(kv, kf);
@@ -283,13 +370,17 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
                 if (lane == 0) misc[kMiscNewLg + g] = v;
             }
         }
+        // rows of chunks that cannot be live
+        for (int lr = live_rows + tid; lr < local_rows; lr += kThreads)
+#pragma unroll
+            for (int g = 0; g < G; ++g) lg[g * stride + lr] = -CUDART_INF_F;
         __syncthreads();  // maskb visible
-        for (int c = 0; c < n_chunks; ++c) {
-            const int stage = c % NS;
-            mbar_wait(&kbar[stage], (c / NS) & 1);
-            const int rows_c = min(kChunkRows, nrows - c * kChunkRows);
-            const uint8_t* kbase = kring + stage * kChunkBytes;
-            for (int r0 = warp * RPW; r0 < rows_c; r0 += kWarps * RPW) {
+        for (int j = 0; j < nlc_live; ++j) {
+            const int stage = j % NS;
+            mbar_wait(&kbar[stage], (j / NS) & 1);
+            const int rows_c = chunk_rows_valid(j);
+            const uint8_t* kbase = kring + stage * chunk_bytes;
+            for (int r0 = warp * RPW; r0 < CH; r0 += kWarps * RPW) {
                 const int r = r0 + sub;
                 const bool valid = r < rows_c;
                 float kf[8];
@@ -304,32 +395,32 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
                     for (int i = 0; i < 8; ++i) acc = __fmaf_rn(q[g][i], kf[i], acc);
                     dots[g] = group_butterfly<LPR>(acc);
                 }
-                if (valid && li == 0) {
-                    const int row = c * kChunkRows + r;
-                    const bool live = maskb[row];
+                if (li == 0) {
+                    const int lr = (j << chs) + r;
+                    const bool live = valid && maskb[lr];
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
                         // naive path rounds q@k^T to bf16, then * scale to bf16 (attention_utils.py:37)
                         const float v = NAIVE ? bf16_round(__fmul_rn(bf16_round(dots[g]), p.scale))
                                               : __fmul_rn(dots[g], p.scale);
-                        lg[g * stride + row] = live ? v : -CUDART_INF_F;
+                        lg[g * stride + lr] = live ? v : -CUDART_INF_F;
                     }
                 }
             }
             __syncthreads();
-            if (tid == 0 && c + NS < n_chunks) {
+            if (tid == 0 && j + NS < nlc_live) {
                 fence_proxy_async();
-                const int cn = c + NS;
-                const uint32_t bytes = min(kChunkRows, nrows - cn * kChunkRows) * kRowBytes;
+                const int jn = j + NS;
+                const uint32_t bytes = chunk_rows_valid(jn) * kRowBytes;
                 mbar_expect_tx(&kbar[stage], bytes);
-                tma_load_1d(kring + stage * kChunkBytes, kc + (size_t)(row0 + cn * kChunkRows) * D, bytes, &kbar[stage]);
+                tma_load_1d(kring + stage * chunk_bytes, kc + ((size_t)(jn * C + rank) << chs) * D, bytes, &kbar[stage]);
             }
         }
         // ---- 4. row max without the local candidate, and the candidate's own logits
         for (int g = warp; g < G; g += kWarps) {
             float m = -CUDART_INF_F;
-            for (int i = lane; i < nrows; i += 32)
-                if (i != cand_local) m = fmaxf(m, lg[g * stride + i]);
+            for (int lr = lane; lr < live_rows; lr += 32)
+                if (lr != cand_local) m = fmaxf(m, lg[g * stride + lr]);
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
             if (lane == 0) {
@@ -351,7 +442,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     __syncthreads();
     if (!b0_waited) cluster_wait_acquire();
     constexpr int NW = 2 + 2 * G;
-    for (int idx = tid; idx < (int)C * NW; idx += kThreads) {
+    for (int idx = tid; idx < C * NW; idx += kThreads) {
         const int dest = idx / NW, w = idx % NW;
         st_cluster_u32(map_to_rank(smem_u32(&rec[rank * kRecWords + w]), dest), miscu[kMiscMyRec + w]);
     }
@@ -360,24 +451,28 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
 
     // ---- 6. winner + global max per query head
     uint64_t wkey = kNoKey;
-    for (uint32_t r = 0; r < C; ++r) {
+    for (int r = 0; r < C; ++r) {
         const uint64_t k = (uint64_t)rec[r * kRecWords] | ((uint64_t)rec[r * kRecWords + 1] << 32);
         wkey = k < wkey ? k : wkey;
     }
-    const bool has_new = do_evict && wkey != kNoKey;
-    const int widx = has_new ? (int)(uint32_t)(wkey & 0xffffffffu) : -1;
-    const int owner = has_new ? widx / T : -1;
-    const bool i_own = has_new && owner == (int)rank;
+    const bool has_slot = do_evict && wkey != kNoKey;  // a slot is overwritten this step
+    const int widx = has_slot ? (int)(uint32_t)(wkey & 0xffffffffu) : -1;
+    const int owner = has_slot ? (widx >> chs) % C : -1;
+    const bool i_own = has_slot && owner == rank;
+    const int widx_local = has_slot ? (((widx >> chs) / C) << chs) + (widx & (CH - 1)) : -1;
+    const bool has_new = has_slot && attend_new;  // ... and the new token attends to itself there
     if (needs_epoch && rank == 0 && tid == 0) red_release_gpu_add(&st.sync_words[0], 1);  // shared reads done
     if (do_attend && tid < G) {
         float m = has_new ? misc[kMiscNewLg + tid] : -CUDART_INF_F;
-        for (uint32_t r = 0; r < C; ++r) {
+        for (int r = 0; r < C; ++r) {
             m = fmaxf(m, __uint_as_float(rec[r * kRecWords + 2 + tid]));
             const bool has_cand = !(rec[r * kRecWords] == 0xffffffffu && rec[r * kRecWords + 1] == 0xffffffffu);
-            if ((int)r != owner && has_cand) m = fmaxf(m, __uint_as_float(rec[r * kRecWords + 2 + G + tid]));
+            // a candidate that is not overwritten keeps its logit; the overwritten one only if the
+            // new token does not replace it in attention (hybrid drop: slot L-1 stays as it was)
+            if (has_cand && (r != owner || !has_new)) m = fmaxf(m, __uint_as_float(rec[r * kRecWords + 2 + G + tid]));
         }
         misc[kMiscGmax + tid] = m;
-        if (i_own) lg[tid * stride + (widx - row0)] = misc[kMiscNewLg + tid];  // the new token attends to itself
+        if (i_own && has_new) lg[tid * stride + widx_local] = misc[kMiscNewLg + tid];
     }
 
     // ---- 7. owner CTA: in-place slot overwrite (cache.py:390-401 / 460-490) + policy state
@@ -403,27 +498,34 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         }
         if (lane == 0) {
             const int32_t pos_old = posp[widx];
-            st.mask[(size_t)h * L + widx] = 1;
+            if (!hybrid || hyb_mode == kHybAppend) st.mask[(size_t)h * L + widx] = 1;
             if (p.a.fill_idx && policy != CC_POLICY_EXTERNAL) p.a.fill_idx[h] = widx;
             if (policy == CC_POLICY_HEAVY_HITTER && !do_score) {
                 reinterpret_cast<double*>(st.attn_history_num)[(size_t)h * L + widx] = 0.0;  // cache.py:753-763
                 st.attn_history_denom[(size_t)h * L + widx] = 0;
             }
-            if (needs_epoch) {  // pos (head-constant) and key_norm are read by every cluster: write after all have read
+            if (hybrid && p.a.is_punc && st.punc_mask) st.punc_mask[(size_t)h * L + widx] = 1;  // cache.py:1011-1016
+            if (needs_epoch) {  // head-constant pos, key_norm, counters are read by every cluster: write after all have read
                 const int32_t target = (gen + 1) * H;
                 while (ld_acquire_gpu(&st.sync_words[0]) - target < 0) {}
             }
             if (policy == CC_POLICY_L2)
                 reinterpret_cast<__nv_bfloat16*>(st.key_norm)[(size_t)h * L + widx] = __float2bfloat16_rn(knorm);
             if (st.pos_heads != 1 || h == 0) st.pos[(size_t)pos_row * L + widx] = ipos;
-            if (h == 0) st.cache_cts[0] += (pos_old == -1) ? 1 : 0;  // cache.py:330, 356-360
+            if (hybrid) {
+                if (hyb_mode == kHybAppend) st.cache_cts[h] = hyb_cts + 1;
+                if (h == 0 && p.a.is_punc && st.num_punc) st.num_punc[0] += 1;
+            } else if (h == 0) {
+                st.cache_cts[0] += (pos_old == -1) ? 1 : 0;  // cache.py:330, 356-360
+            }
         }
     }
     if (needs_epoch && h == 0 && rank == 0 && tid == 32) {
-        // generation bump: only after every cluster has arrived (each read `gen` before arriving)
+        // generation bump (and the shared step counter): only after every cluster has arrived
         const int32_t g0 = ld_acquire_gpu(&st.sync_words[1]);
         const int32_t target = (g0 + 1) * H;
         while (ld_acquire_gpu(&st.sync_words[0]) - target < 0) {}
+        if (hybrid && do_score && NAIVE) st.attn_counter[0] = hyb_counter + 1;
         st_release_gpu(&st.sync_words[1], g0 + 1);
     }
     __syncthreads();
@@ -436,15 +538,15 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         long long isum[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) isum[g] = 0;
-        for (int i = tid; i < nrows; i += kThreads) {
+        for (int lr = tid; lr < live_rows; lr += kThreads) {
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                const float e = det_expf(__fsub_rn(lg[g * stride + i], gmax[g]));
-                lg[g * stride + i] = e;
+                const float e = det_expf(__fsub_rn(lg[g * stride + lr], gmax[g]));
+                lg[g * stride + lr] = e;
                 isum[g] += __float2ll_rz(__fmul_rn(e, 1099511627776.0f));
             }
         }
-        long long* wsum = reinterpret_cast<long long*>(red);  // [kWarps][G], red is free until the P.V phase
+        long long* wsum = reinterpret_cast<long long*>(red);  // [kWarps][G]; red is free until the P.V phase
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             long long v = isum[g];
@@ -453,7 +555,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             if (lane == 0) wsum[warp * G + g] = v;
         }
         __syncthreads();
-        for (int idx = tid; idx < (int)C * G; idx += kThreads) {
+        for (int idx = tid; idx < C * G; idx += kThreads) {
             const int dest = idx / G, g = idx % G;
             long long v = 0;
             for (int w = 0; w < kWarps; ++w) v += wsum[w * G + g];
@@ -463,7 +565,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         cluster_wait_acquire();
         if (tid < G) {
             long long tot = 0;
-            for (uint32_t r = 0; r < C; ++r) tot += (long long)sums[r * kMaxG + tid];
+            for (int r = 0; r < C; ++r) tot += (long long)sums[r * kMaxG + tid];
             misc[kMiscSumF + tid] = __fmul_rn(__ll2float_rn(tot), 9.094947017729282e-13f);  // 2^-40
         }
         __syncthreads();
@@ -475,32 +577,50 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
 #pragma unroll
         for (int g = 0; g < G; ++g) sumf[g] = do_attend ? misc[kMiscSumF + g] : 1.f;
         const bool hh_score = do_score && NAIVE && policy == CC_POLICY_HEAVY_HITTER;
+        const bool ring_score = do_score && NAIVE && hybrid;
+        const int W = st.history_window;
+        const int wslot = ring_score ? (int)(hyb_counter % W) : 0;
         __nv_bfloat16* probs = reinterpret_cast<__nv_bfloat16*>(p.a.probs);
-        for (int i = tid; i < nrows; i += kThreads) {
-            const int s = row0 + i;
+        for (int lr = tid; lr < local_rows; lr += kThreads) {
+            const int s = slot_of(lr);
+            if (s >= L) continue;
             float pooled = 0.f;
             if (do_attend) {
-                float acc = 0.f;
+                if (lr < live_rows) {
+                    float acc = 0.f;
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    float pr = __fdiv_rn(lg[g * stride + i], sumf[g]);
-                    if (NAIVE) pr = bf16_round(pr);
-                    lg[g * stride + i] = pr;
-                    acc = g == 0 ? pr : __fadd_rn(acc, pr);
+                    for (int g = 0; g < G; ++g) {
+                        float pr = __fdiv_rn(lg[g * stride + lr], sumf[g]);
+                        if (NAIVE) pr = bf16_round(pr);
+                        lg[g * stride + lr] = pr;
+                        acc = g == 0 ? pr : __fadd_rn(acc, pr);
+                    }
+                    if (NAIVE) pooled = bf16_round(__fdiv_rn(acc, (float)G));  // torch mean: fp32 sum / G, then bf16
                 }
-                if (NAIVE) {
-                    pooled = bf16_round(__fdiv_rn(acc, (float)G));  // torch mean: fp32 sum / G, then bf16
-                    if (probs) probs[(size_t)h * L + s] = __float2bfloat16_rn(pooled);
-                }
-            } else if (hh_score) {
+                if (NAIVE && probs) probs[(size_t)h * L + s] = __float2bfloat16_rn(pooled);
+            } else if (hh_score || ring_score) {
                 pooled = __bfloat162float(probs[(size_t)h * L + s]);
             }
             if (hh_score) {
                 double* num = reinterpret_cast<double*>(st.attn_history_num) + (size_t)h * L;
                 int32_t* den = st.attn_history_denom + (size_t)h * L;
-                const bool fresh = has_new && s == widx;  // evicted slot's history restarts (cache.py:753-763)
+                const bool fresh = has_slot && s == widx;  // evicted slot's history restarts (cache.py:753-763)
                 num[s] = (fresh ? 0.0 : num[s]) + (double)pooled;
                 den[s] = (fresh ? 0 : den[s]) + 1;
+            } else if (ring_score) {
+                // ring[s][counter % W] = pooled; the evicted slot keeps its ring (the reference's reset is a
+                // silent no-op, cache.py:993-996).  Only live slots can hold non-zero history.
+                int32_t* den = st.attn_history_denom + (size_t)h * L;
+                den[s] += 1;
+                if (s < live_limit || pooled != 0.f) {
+                    __nv_bfloat16* cell = reinterpret_cast<__nv_bfloat16*>(st.attn_history_num) + ((size_t)h * L + s) * W + wslot;
+                    const float old = __bfloat162float(*cell);
+                    if (old != pooled) {
+                        double* hs = st.attn_history_sum + (size_t)h * L + s;
+                        *hs = (*hs - (double)old) + (double)pooled;
+                        *cell = __float2bfloat16_rn(pooled);
+                    }
+                }
             }
         }
         if (hh_score && h == 0 && rank == 0 && tid == 0) st.attn_counter[0] += 1;
@@ -515,32 +635,32 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[g][i] = 0.f;
         const int rg = tid / LPR;
-        const int patch_row = i_own ? widx - row0 : -1;
-        for (int c = 0; c < n_chunks; ++c) {
-            const int stage = c % NS;
-            mbar_wait(&vbar[stage], (c / NS) & 1);
-            const int rows_c = min(kChunkRows, nrows - c * kChunkRows);
-            const uint8_t* vbase = vring + stage * kChunkBytes;
+        const int patch_row = (i_own && has_new) ? widx_local : -1;
+        for (int j = 0; j < nlc_live; ++j) {
+            const int stage = j % NS;
+            mbar_wait(&vbar[stage], (j / NS) & 1);
+            const int rows_c = chunk_rows_valid(j);
+            const uint8_t* vbase = vring + stage * chunk_bytes;
             for (int r = rg; r < rows_c; r += NRG) {
-                const int row = c * kChunkRows + r;
+                const int lr = (j << chs) + r;
                 uint4 vv = *reinterpret_cast<const uint4*>(vbase + r * kRowBytes + li * 16);
-                if (row == patch_row) vv = vnew8;
+                if (lr == patch_row) vv = vnew8;
                 float vf[8];
                 unpack8(vv, vf);
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    const float pr = lg[g * stride + row];
+                    const float pr = lg[g * stride + lr];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) acc[g][i] = fmaf(pr, vf[i], acc[g][i]);
                 }
             }
             __syncthreads();
-            if (tid == 0 && c + NS < n_chunks) {
+            if (tid == 0 && j + NS < nlc_live) {
                 fence_proxy_async();
-                const int cn = c + NS;
-                const uint32_t bytes = min(kChunkRows, nrows - cn * kChunkRows) * kRowBytes;
+                const int jn = j + NS;
+                const uint32_t bytes = chunk_rows_valid(jn) * kRowBytes;
                 mbar_expect_tx(&vbar[stage], bytes);
-                tma_load_1d(vring + stage * kChunkBytes, vc + (size_t)(row0 + cn * kChunkRows) * D, bytes, &vbar[stage]);
+                tma_load_1d(vring + stage * chunk_bytes, vc + ((size_t)(jn * C + rank) << chs) * D, bytes, &vbar[stage]);
             }
         }
 #pragma unroll
@@ -561,7 +681,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             }
         }
         __syncthreads();
-        const int SL = G * D / (int)C;  // outputs reduced by each CTA of the cluster
+        const int SL = G * D / C;  // outputs reduced by each CTA of the cluster
         for (int o = tid; o < G * D; o += kThreads) {
             float s = red[o];
 #pragma unroll
@@ -574,11 +694,10 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.a.y) + (size_t)h * G * D;
         for (int t = tid; t < SL; t += kThreads) {
             float s = yx[t];
-            for (uint32_t r = 1; r < C; ++r) s += yx[r * SL + t];
+            for (int r = 1; r < C; ++r) s += yx[r * SL + t];
             y[rank * SL + t] = __float2bfloat16_rn(s);
         }
     }
-    (void)ypart;
 }
 
 // --------------------------------------------------------------------------- host side
@@ -609,7 +728,7 @@ static KernelFn pick_kernel(int D, int G, bool naive) {
 
 struct LaunchPlan {
     KernelFn fn;
-    int cluster, rows_per_cta, n_stages, lg_stride;
+    int cluster, ch_shift, max_local_chunks, n_stages, lg_stride;
     uint32_t smem;
 };
 
@@ -631,7 +750,7 @@ static int device_limits() {
 // Plans are cached per (shape, policy class): the occupancy query is not free.
 struct PlanKey { int D, G, naive, H, L, epoch; };
 struct PlanEntry { PlanKey k; LaunchPlan p; };
-static PlanEntry g_plans[64];
+static PlanEntry g_plans[128];
 static int g_nplans = 0;
 
 static int make_plan(const CcCacheState* st, bool needs_epoch, LaunchPlan* out) {
@@ -649,14 +768,16 @@ static int make_plan(const CcCacheState* st, bool needs_epoch, LaunchPlan* out) 
     KernelFn fn = pick_kernel(D, G, naive);
     if (!fn) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "unsupported head_dim (64/128) or q_per_kv (1,2,4,6,7,8)");
     cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    // chunk size: the largest of 64/32/16 rows that still gives every CTA of a 16-cluster a chunk
+    int chs = 6;
+    while (chs > 4 && ((L + (1 << chs) - 1) >> chs) < kMaxCluster) --chs;
+    const int n_chunks = (L + (1 << chs) - 1) >> chs;
     for (int C = kMaxCluster; C >= 1; C >>= 1) {
-        if (H * C > g_num_sms && C > 1) continue;
-        if (C > 1 && L / C < 16) continue;  // keep at least 16 slots per CTA
-        const int T = (L + C - 1) / C;
-        const int n_chunks = (T + kChunkRows - 1) / kChunkRows;
-        const int stride = (T + 31) / 32 * 32;
-        for (int ns = n_chunks < 4 ? n_chunks : 4; ns >= 1; --ns) {
-            const SmemLayout lay = make_layout(D, G, T, ns, stride);
+        if (C > 1 && (H * C > g_num_sms || C > n_chunks)) continue;
+        const int mlc = (n_chunks + C - 1) / C;
+        const int stride = ((mlc << chs) + 31) / 32 * 32;
+        for (int ns = mlc < 4 ? mlc : 4; ns >= 1; --ns) {
+            const SmemLayout lay = make_layout(D, G, 1 << chs, mlc << chs, ns, stride);
             if ((int)lay.total > g_smem_optin) continue;
             if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total) != cudaSuccess) {
                 cudaGetLastError();
@@ -674,8 +795,8 @@ static int make_plan(const CcCacheState* st, bool needs_epoch, LaunchPlan* out) 
             if (cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
             // with the cross-head epoch barrier every cluster must be co-resident
             if (max_clusters < (needs_epoch ? H : 1)) continue;
-            LaunchPlan p = {fn, C, T, ns, stride, lay.total};
-            if (g_nplans < 64) g_plans[g_nplans++] = {{D, G, (int)naive, H, L, (int)needs_epoch}, p};
+            LaunchPlan p = {fn, C, chs, mlc, ns, stride, lay.total};
+            if (g_nplans < 128) g_plans[g_nplans++] = {{D, G, (int)naive, H, L, (int)needs_epoch}, p};
             *out = p;
             return CC_OK;
         }
@@ -687,7 +808,6 @@ static int validate(const CcCacheState* st, const CcDecodeArgs* a) {
     if (!st || !a) return set_error(CC_ERR_INVALID_ARG, "null state or args");
     if (st->n_kv_heads < 1 || st->q_per_kv < 1 || st->max_cache_length < 1) return set_error(CC_ERR_INVALID_ARG, "bad shape");
     if (st->policy < CC_POLICY_EXTERNAL || st->policy > CC_POLICY_HYBRID) return set_error(CC_ERR_INVALID_ARG, "bad policy");
-    if (st->policy == CC_POLICY_HYBRID) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "hybrid policy: use cc_decode_step_hybrid build (not in this build)");
     if (!st->k_cache || !st->v_cache || !st->pos || !st->mask || !st->cache_cts) return set_error(CC_ERR_INVALID_ARG, "null cache buffer");
     if (st->pos_heads != 1 && st->pos_heads != st->n_kv_heads) return set_error(CC_ERR_INVALID_ARG, "pos_heads must be 1 or n_kv_heads");
     const int phases = a->phases;
@@ -697,11 +817,21 @@ static int validate(const CcCacheState* st, const CcDecodeArgs* a) {
     if ((phases & CC_PHASE_ATTEND) && (!a->q || !a->y)) return set_error(CC_ERR_INVALID_ARG, "attend needs q and y");
     if (st->policy == CC_POLICY_EXTERNAL && (phases & CC_PHASE_EVICT_FILL) && !a->fill_idx)
         return set_error(CC_ERR_INVALID_ARG, "external policy needs fill_idx");
+    const bool naive = st->attn_mode == CC_ATTN_NAIVE_BF16;
+    if (naive && (phases & CC_PHASE_SCORE) && !(phases & CC_PHASE_ATTEND) && !a->probs)
+        return set_error(CC_ERR_INVALID_ARG, "score-only phase needs probs");
     if (st->policy == CC_POLICY_HEAVY_HITTER) {
         if (st->history_window != 1) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "heavy_hitter kernel needs history_window_size == 1");
         if (!st->attn_history_num || !st->attn_history_denom || !st->attn_counter) return set_error(CC_ERR_INVALID_ARG, "null heavy_hitter state");
-        if (st->attn_mode != CC_ATTN_NAIVE_BF16) return set_error(CC_ERR_INVALID_ARG, "heavy_hitter needs the naive (probability-returning) attention mode");
-        if ((phases & CC_PHASE_SCORE) && !(phases & CC_PHASE_ATTEND) && !a->probs) return set_error(CC_ERR_INVALID_ARG, "score-only phase needs probs");
+        if (!naive) return set_error(CC_ERR_INVALID_ARG, "heavy_hitter needs the naive (probability-returning) attention mode");
+    }
+    if (st->policy == CC_POLICY_HYBRID) {
+        if (st->cts_heads != st->n_kv_heads) return set_error(CC_ERR_INVALID_ARG, "hybrid needs per-head cache_cts");
+        if (st->pos_heads != st->n_kv_heads) return set_error(CC_ERR_INVALID_ARG, "hybrid needs per-head pos");
+        if (!st->hyb_strategy_bits || !st->hyb_recent_window || !st->hyb_heavy_budget) return set_error(CC_ERR_INVALID_ARG, "null hybrid strategy tables");
+        if (naive && (st->history_window < 2 || !st->attn_history_num || !st->attn_history_denom || !st->attn_counter || !st->attn_history_sum))
+            return set_error(CC_ERR_INVALID_ARG, "hybrid with heavy hitters needs the ring history, its denominators, counter and running sums");
+        if (!st->sync_words) return set_error(CC_ERR_INVALID_ARG, "hybrid needs sync_words");
     }
     if (st->policy == CC_POLICY_L2 && !st->key_norm) return set_error(CC_ERR_INVALID_ARG, "null key_norm");
     if ((st->policy == CC_POLICY_RECENT_GLOBAL || st->policy == CC_POLICY_L2) && !st->sync_words)
@@ -711,18 +841,21 @@ static int validate(const CcCacheState* st, const CcDecodeArgs* a) {
     return CC_OK;
 }
 
+static bool plan_needs_epoch(const CcCacheState* st) {
+    return st->policy == CC_POLICY_RECENT_GLOBAL || st->policy == CC_POLICY_L2 || st->policy == CC_POLICY_HYBRID;
+}
+
 int decode_step_impl(const CcCacheState* st, const CcDecodeArgs* a, cudaStream_t stream) {
     int rc = validate(st, a);
     if (rc) return rc;
-    const bool needs_epoch = (a->phases & CC_PHASE_EVICT_FILL) &&
-                             (st->policy == CC_POLICY_RECENT_GLOBAL || st->policy == CC_POLICY_L2);
     LaunchPlan plan;
-    rc = make_plan(st, needs_epoch, &plan);
+    rc = make_plan(st, plan_needs_epoch(st), &plan);
     if (rc) return rc;
     DecodeParams p;
     p.st = *st;
     p.a = *a;
-    p.rows_per_cta = plan.rows_per_cta;
+    p.ch_shift = plan.ch_shift;
+    p.max_local_chunks = plan.max_local_chunks;
     p.n_stages = plan.n_stages;
     p.lg_stride = plan.lg_stride;
     p.scale = (float)(1.0 / sqrt((double)st->head_dim));
@@ -743,8 +876,7 @@ int decode_step_impl(const CcCacheState* st, const CcDecodeArgs* a, cudaStream_t
 int decode_cluster_size_impl(const CcCacheState* st) {
     if (!st) return set_error(CC_ERR_INVALID_ARG, "null state");
     LaunchPlan plan;
-    const bool needs_epoch = st->policy == CC_POLICY_RECENT_GLOBAL || st->policy == CC_POLICY_L2;
-    int rc = make_plan(st, needs_epoch, &plan);
+    int rc = make_plan(st, plan_needs_epoch(st), &plan);
     return rc ? rc : plan.cluster;
 }
 

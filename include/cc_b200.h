@@ -90,6 +90,9 @@ typedef struct CcCacheState {
     void*    attn_history_num;   /* f64 [Hkv, L] when W == 1; bf16 [Hkv, L, W] otherwise */
     int32_t* attn_history_denom; /* i32 [Hkv, L]                                          */
     int64_t* attn_counter;       /* i64 [1]                                               */
+    double*  attn_history_sum;   /* hybrid (W > 1) only: f64 [Hkv, L] running sum of each slot's ring,
+                                    kept by the kernel so the ring is not re-summed every step (the
+                                    reference re-sums it, cache.py:855-859); NULL otherwise            */
 
     /* l2 (cache.py:573-574) */
     void*    key_norm;           /* bf16 [Hkv, L]                                         */

@@ -165,12 +165,15 @@ static void evict_heavy_hitter(const CcCacheState* st, int32_t input_pos, int64_
     }
 }
 
-/* bf16 ring sum: torch sums bf16 in fp32 and rounds once (cache.py:855-859).
- * Order: plain ascending; the reference's vectorised order is unspecified. */
+/* bf16 ring sum (cache.py:855-859): torch accumulates the W bf16 values in fp32 in an
+ * unspecified vectorised order and rounds the result to bf16.  Here the sum is taken in fp64
+ * (exact for any realistic dynamic range, hence order independent), rounded to fp32, then to
+ * bf16.  The CUDA kernel keeps the same fp64 value as a running sum instead of re-reading the
+ * ring. */
 static float ring_sum_bf16(const uint16_t* ring, int W) {
-    float acc = 0.0f;
-    for (int w = 0; w < W; ++w) acc += bf2f(ring[w]);
-    return bfround(acc);
+    double acc = 0.0;
+    for (int w = 0; w < W; ++w) acc += (double)bf2f(ring[w]);
+    return bfround((float)acc);
 }
 
 /* KVCacheHybrid._select_fill_idx / _eviction_idx_for_head (cache.py:844-950).

@@ -29,7 +29,7 @@ class CacheState(C.Structure):
         "global_tokens", "recent_window", "history_window", "pos_heads", "cts_heads", "reserved0")] + [
         (n, C.c_void_p) for n in (
             "k_cache", "v_cache", "pos", "mask", "cache_cts", "attn_history_num",
-            "attn_history_denom", "attn_counter", "key_norm", "hyb_strategy_bits",
+            "attn_history_denom", "attn_counter", "attn_history_sum", "key_norm", "hyb_strategy_bits",
             "hyb_recent_window", "hyb_heavy_budget", "special_mask", "punc_mask",
             "num_special", "num_punc", "sync_words")]
 

@@ -33,6 +33,8 @@ def load_state(cache, tensors: dict):
             continue
         src = tensors[name]
         dst.copy_(src.reshape(dst.shape).to(dst.dtype))
+    if hasattr(cache, "resync_history"):
+        cache.resync_history()
 
 
 def device_cache_from_golden(g: Golden, device="cuda"):

