@@ -768,6 +768,12 @@ static int make_plan(const CcCacheState* st, bool needs_epoch, LaunchPlan* out) 
     KernelFn fn = pick_kernel(D, G, naive);
     if (!fn) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "unsupported head_dim (64/128) or q_per_kv (1,2,4,6,7,8)");
     cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    // the cap is per function and plans for other shapes share it: raise it once to the device
+    // limit instead of to this plan's size (a later, smaller plan must not lower it)
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(CC_ERR_CUDA, "cannot raise the dynamic shared memory limit");
+    }
     // chunk size: the largest of 64/32/16 rows that still gives every CTA of a 16-cluster a chunk
     int chs = 6;
     while (chs > 4 && ((L + (1 << chs) - 1) >> chs) < kMaxCluster) --chs;
@@ -779,10 +785,6 @@ static int make_plan(const CcCacheState* st, bool needs_epoch, LaunchPlan* out) 
         for (int ns = mlc < 4 ? mlc : 4; ns >= 1; --ns) {
             const SmemLayout lay = make_layout(D, G, 1 << chs, mlc << chs, ns, stride);
             if ((int)lay.total > g_smem_optin) continue;
-            if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total) != cudaSuccess) {
-                cudaGetLastError();
-                continue;
-            }
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(H * C);
             cfg.blockDim = dim3(kThreads);
