@@ -247,8 +247,7 @@ def run_ours(args):
             dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dev_s, e2e_s = times.tolist()
         roof = k1_roofline(model, min(args.steps, 32), device) if rank == 0 else None
-    n_layer = model.config.n_layer
-    ours_per_step = n_layer + getattr(model, "custom_kernels_per_token", 0)
+    ours_per_step = model.kernels_per_token() if model.fused_decode else model.config.n_layer
     out = {
         "metric": METRIC, "value": round(args.steps / dev_s, 2), "unit": "tokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(dev_s / args.steps * 1e3, 4),

@@ -43,9 +43,17 @@ EXPORTS = {
     "cc_sync_words": (C.c_int, []),
     "cc_decode_step": (C.c_int, [C.POINTER(CcCacheState), C.POINTER(CcDecodeArgs), C.c_void_p]),
     "cc_decode_cluster_size": (C.c_int, [C.POINTER(CcCacheState)]),
+    "cc_debug_set_trace": (None, [C.c_void_p]),
     "cc_key_norms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "cc_prefill_gather": (C.c_int, [C.POINTER(CcCacheState), C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "cc_rmsnorm_qkv_rope": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_void_p]),
+    "cc_gemv_residual": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int32, C.c_int32, C.c_void_p]),
+    "cc_rmsnorm_ffn_gate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int32, C.c_int32, C.c_void_p]),
 }
 
 _lib = None

@@ -39,6 +39,8 @@ int cc_decode_step(const CcCacheState* state, const CcDecodeArgs* args, void* st
 
 int cc_decode_cluster_size(const CcCacheState* state) { return cc::decode_cluster_size_impl(state); }
 
+void cc_debug_set_trace(void* device_buffer) { cc::set_trace_buffer((unsigned long long*)device_buffer); }
+
 int cc_key_norms(const void* k, void* key_norm, int32_t n_rows, int32_t head_dim, void* stream) {
     return cc::key_norms_impl(k, key_norm, n_rows, head_dim, (cudaStream_t)stream);
 }
@@ -48,6 +50,23 @@ int cc_prefill_gather(const CcCacheState* state, const void* k_prompt, const voi
                       void* stream) {
     return cc::prefill_gather_impl(state, k_prompt, v_prompt, keep_idx, keep_heads, n_keep, prompt_len,
                                    (cudaStream_t)stream);
+}
+
+int cc_rmsnorm_qkv_rope(const void* x, const void* norm_w, float eps, const void* wqkv, const void* bias,
+                        const void* freqs_cis, const int32_t* input_pos, void* q, void* k, void* v,
+                        int32_t dim, int32_t n_q_heads, int32_t n_kv_heads, int32_t head_dim, void* stream) {
+    return cc::rmsnorm_qkv_rope_impl(x, norm_w, eps, wqkv, bias, freqs_cis, input_pos, q, k, v, dim, n_q_heads,
+                                     n_kv_heads, head_dim, (cudaStream_t)stream);
+}
+
+int cc_gemv_residual(const void* x, const void* norm_w, float eps, const void* w, const void* residual,
+                     void* out, int32_t K, int32_t N, void* stream) {
+    return cc::gemv_residual_impl(x, norm_w, eps, w, residual, out, K, N, (cudaStream_t)stream);
+}
+
+int cc_rmsnorm_ffn_gate(const void* x, const void* norm_w, float eps, const void* w1, const void* w3,
+                        void* out, int32_t K, int32_t N, void* stream) {
+    return cc::rmsnorm_ffn_gate_impl(x, norm_w, eps, w1, w3, out, K, N, (cudaStream_t)stream);
 }
 
 }  // extern "C"

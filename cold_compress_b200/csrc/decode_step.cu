@@ -47,6 +47,7 @@ struct DecodeParams {
     int n_stages;       // ring depth for K and for V
     int lg_stride;      // floats per query head in the logit/prob array
     float scale;        // (float)(1/sqrt(D))
+    unsigned long long* trace;  // diagnostics: [gridDim.x][16] globaltimer stamps (NULL = off)
 };
 
 struct SmemLayout {
@@ -88,6 +89,14 @@ enum : int {
 
 // hybrid per-head decision (reference cache.py:896-950)
 enum : int { kHybAppend = 0, kHybEvict = 1, kHybDrop = 2 };
+
+__device__ __forceinline__ void stamp(const DecodeParams& p, int k) {
+    if (p.trace && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[(size_t)blockIdx.x * 16 + k] = t;
+    }
+}
 
 template <int LPR>
 __device__ __forceinline__ float group_butterfly(float v) {
@@ -153,6 +162,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     float* misc = reinterpret_cast<float*>(smem + lay.misc);
     uint32_t* miscu = reinterpret_cast<uint32_t*>(misc);
 
+    stamp(p, 0);
     cluster_arrive_relaxed();  // B0: this CTA has started (its shared memory may be written by peers)
     bool b0_waited = false;
 
@@ -209,6 +219,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             tma_load_1d(vring + j * chunk_bytes, vc + ((size_t)(j * C + rank) << chs) * D, bytes, &vbar[j]);
         }
     }
+    stamp(p, 1);
     // generation of the cross-cluster "shared reads done" barrier, read by the thread that may
     // later have to wait on it (lane 0 of the last warp) BEFORE this cluster arrives
     int32_t gen = 0;
@@ -345,6 +356,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             ckey = o < ckey ? o : ckey;
         }
     }
+    stamp(p, 2);
     // local row of this CTA's candidate (it owns the slot by construction)
     int cand_local = -1;
     if (ckey != kNoKey) {
@@ -378,6 +390,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         for (int j = 0; j < nlc_live; ++j) {
             const int stage = j % NS;
             mbar_wait(&kbar[stage], (j / NS) & 1);
+            if (j == 0) stamp(p, 3);
             const int rows_c = chunk_rows_valid(j);
             const uint8_t* kbase = kring + stage * chunk_bytes;
             for (int r0 = warp * RPW; r0 < CH; r0 += kWarps * RPW) {
@@ -429,6 +442,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             }
         }
     }
+    stamp(p, 4);
     // ---- 5. X1: every CTA learns every candidate and every partial max
     if (tid == 0) {
         miscu[kMiscMyRec + 0] = (uint32_t)(ckey & 0xffffffffu);
@@ -449,6 +463,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     cluster_arrive_release();
     cluster_wait_acquire();
 
+    stamp(p, 5);
     // ---- 6. winner + global max per query head
     uint64_t wkey = kNoKey;
     for (int r = 0; r < C; ++r) {
@@ -529,6 +544,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         st_release_gpu(&st.sync_words[1], g0 + 1);
     }
     __syncthreads();
+    stamp(p, 6);
 
     if (do_attend) {
         // ---- 8. exp and the exact fixed-point softmax denominator = X2
@@ -561,8 +577,10 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             for (int w = 0; w < kWarps; ++w) v += wsum[w * G + g];
             st_cluster_u64(map_to_rank(smem_u32(&sums[rank * kMaxG + g]), dest), (uint64_t)v);
         }
+        stamp(p, 7);
         cluster_arrive_release();
         cluster_wait_acquire();
+        stamp(p, 8);
         if (tid < G) {
             long long tot = 0;
             for (int r = 0; r < C; ++r) tot += (long long)sums[r * kMaxG + tid];
@@ -626,6 +644,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         if (hh_score && h == 0 && rank == 0 && tid == 0) st.attn_counter[0] += 1;
     }
 
+    stamp(p, 9);
     if (do_attend) {
         __syncthreads();
         // ---- 10. y = P.V over the V ring, cluster-wide reduction = X3
@@ -663,6 +682,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
                 tma_load_1d(vring + stage * chunk_bytes, vc + ((size_t)(jn * C + rank) << chs) * D, bytes, &vbar[stage]);
             }
         }
+        stamp(p, 10);
 #pragma unroll
         for (int g = 0; g < G; ++g)
 #pragma unroll
@@ -689,8 +709,10 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             const int dest = o / SL, off = o % SL;
             st_cluster_f32(map_to_rank(smem_u32(&yx[rank * SL + off]), dest), s);
         }
+        stamp(p, 11);
         cluster_arrive_release();
         cluster_wait_acquire();
+        stamp(p, 12);
         __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.a.y) + (size_t)h * G * D;
         for (int t = tid; t < SL; t += kThreads) {
             float s = yx[t];
@@ -698,6 +720,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             y[rank * SL + t] = __float2bfloat16_rn(s);
         }
     }
+    stamp(p, 13);
 }
 
 // --------------------------------------------------------------------------- host side
@@ -734,6 +757,8 @@ struct LaunchPlan {
 
 static int g_num_sms = 0;
 static int g_smem_optin = 0;
+static unsigned long long* g_trace = nullptr;  // diagnostics only (cc_debug_set_trace)
+void set_trace_buffer(unsigned long long* buf) { g_trace = buf; }
 
 static int device_limits() {
     if (g_num_sms) return CC_OK;
@@ -861,6 +886,7 @@ int decode_step_impl(const CcCacheState* st, const CcDecodeArgs* a, cudaStream_t
     p.n_stages = plan.n_stages;
     p.lg_stride = plan.lg_stride;
     p.scale = (float)(1.0 / sqrt((double)st->head_dim));
+    p.trace = g_trace;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(st->n_kv_heads * plan.cluster);
     cfg.blockDim = dim3(kThreads);

@@ -9,8 +9,16 @@ int set_error(int code, const char* msg);                 // records msg for cc_
 int set_cuda_error(cudaError_t e, const char* where);     // CC_ERR_CUDA with the runtime's message
 int decode_step_impl(const CcCacheState* st, const CcDecodeArgs* a, cudaStream_t stream);
 int decode_cluster_size_impl(const CcCacheState* st);
+void set_trace_buffer(unsigned long long* buf);
 int key_norms_impl(const void* k, void* key_norm, int n_rows, int head_dim, cudaStream_t stream);
 int prefill_gather_impl(const CcCacheState* st, const void* k_prompt, const void* v_prompt,
                         const int64_t* keep_idx, int keep_heads, int n_keep, int prompt_len,
                         cudaStream_t stream);
+int rmsnorm_qkv_rope_impl(const void* x, const void* norm_w, float eps, const void* wqkv, const void* bias,
+                          const void* freqs, const int32_t* input_pos, void* q, void* k, void* v, int dim,
+                          int n_q_heads, int n_kv_heads, int head_dim, cudaStream_t stream);
+int gemv_residual_impl(const void* x, const void* norm_w, float eps, const void* w, const void* residual, void* out,
+                       int K, int N, cudaStream_t stream);
+int rmsnorm_ffn_gate_impl(const void* x, const void* norm_w, float eps, const void* w1, const void* w3, void* out,
+                          int K, int N, cudaStream_t stream);
 }  // namespace cc

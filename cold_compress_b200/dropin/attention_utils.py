@@ -1,0 +1,6 @@
+"""Top-level alias of cold_compress_b200.attention_utils, so that the reference's own scripts (`from attention_utils import ...`)
+resolve against this package when this directory comes first on sys.path."""
+from cold_compress_b200.attention_utils import *  # noqa: F401,F403
+from cold_compress_b200 import attention_utils as _impl
+
+globals().update({k: v for k, v in vars(_impl).items() if not k.startswith("__")})

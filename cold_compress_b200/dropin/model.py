@@ -1,0 +1,6 @@
+"""Top-level alias of cold_compress_b200.model, so that the reference's own scripts (`from model import ...`)
+resolve against this package when this directory comes first on sys.path."""
+from cold_compress_b200.model import *  # noqa: F401,F403
+from cold_compress_b200 import model as _impl
+
+globals().update({k: v for k, v in vars(_impl).items() if not k.startswith("__")})

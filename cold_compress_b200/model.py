@@ -22,6 +22,7 @@ import torch.nn as nn
 from torch import Tensor
 from torch.nn import functional as F
 
+from . import ops
 from .attention_utils import prefill_attention_stats, scaled_dot_product_attention
 from .cache import get_cache_constructor
 from .prompt_compression import PrefillAttnStats, get_prompt_compressor_constructor
@@ -107,6 +108,10 @@ class Transformer(nn.Module):
         self.output = nn.Linear(config.dim, config.vocab_size, bias=False)
         self.freqs_cis: Optional[Tensor] = None
         self.max_batch_size = 1
+        # decode through the fused one-token kernels (5 launches per layer); False = plain tensor ops
+        # around the cache kernel (used by the A/B tests)
+        self.fused_decode = True
+        self._bufs = None
 
     def setup_caches(self, **kwargs):
         """Per layer: cache + prompt compressor from the strategy names (reference model.py:191-233)."""
@@ -149,9 +154,66 @@ class Transformer(nn.Module):
     def min_cache_length(self):
         return min(layer.attention.kv_cache.max_cache_length for layer in self.layers)
 
+    # ---- one-token decode through the fused kernels ------------------------------------------
+    def _fused_ready(self, idx) -> bool:
+        w = self.output.weight
+        return (self.fused_decode and idx.is_cuda and w.dtype == torch.bfloat16 and idx.numel() == 1
+                and self.output.in_features % 256 == 0
+                and all(l.feed_forward.w2.in_features % 256 == 0 and l.attention.wo.in_features % 256 == 0
+                        for l in self.layers[:1]))
+
+    def _buffers(self, device):
+        if self._bufs is None or self._bufs["x"].device != device:
+            att, ffn = self.layers[0].attention, self.layers[0].feed_forward
+            mk = lambda n: torch.empty(n, dtype=torch.bfloat16, device=device)  # noqa: E731
+            dim = self.output.in_features
+            self._bufs = {"x": mk(dim), "h": mk(dim), "part": mk(dim), "q": mk(att.n_head * att.head_dim),
+                          "k": mk(att.n_local_heads * att.head_dim), "v": mk(att.n_local_heads * att.head_dim),
+                          "gate": mk(ffn.w1.out_features), "logits": mk(self.output.out_features)}
+        return self._bufs
+
+    def _decode_fused(self, idx: Tensor, input_pos: Tensor) -> Tensor:
+        """embedding -> per layer [norm+wqkv+RoPE | cache step | wo+residual | norm+gate | w2+residual] -> head.
+        Same bf16 rounding points as the tensor-op path; every kernel takes `input_pos` from device
+        memory, so the whole step is capturable in one CUDA graph."""
+        b = self._buffers(idx.device)
+        ip = input_pos if input_pos.dtype == torch.int32 else input_pos.int()
+        eps = self.norm.eps
+        b["x"].copy_(self.tok_embeddings(idx).view(-1))
+        x, h = b["x"], b["h"]
+        for layer in self.layers:
+            att, ffn = layer.attention, layer.feed_forward
+            ops.rmsnorm_qkv_rope(x, layer.attention_norm.weight, layer.attention_norm.eps, att.wqkv.weight,
+                                 att.wqkv.bias, self.freqs_cis, ip, b["q"], b["k"], b["v"], att.n_head,
+                                 att.n_local_heads, att.head_dim)
+            y = att.kv_cache.decode_step(b["q"].view(1, att.n_head, 1, att.head_dim),
+                                         b["k"].view(1, att.n_local_heads, 1, att.head_dim),
+                                         b["v"].view(1, att.n_local_heads, 1, att.head_dim), ip, input_ids=idx)
+            if att.tp_group is None:
+                ops.gemv_residual(y.view(-1), None, 0.0, att.wo.weight, x, h)
+            else:  # row-parallel wo: partial sums, one all-reduce, then the residual (tp.py:156-160)
+                ops.gemv_residual(y.view(-1), None, 0.0, att.wo.weight, None, b["part"])
+                torch.distributed.all_reduce(b["part"], group=att.tp_group)
+                torch.add(x, b["part"], out=h)
+            ops.rmsnorm_ffn_gate(h, layer.ffn_norm.weight, layer.ffn_norm.eps, ffn.w1.weight, ffn.w3.weight, b["gate"])
+            if ffn.tp_group is None:
+                ops.gemv_residual(b["gate"], None, 0.0, ffn.w2.weight, h, x)
+            else:
+                ops.gemv_residual(b["gate"], None, 0.0, ffn.w2.weight, None, b["part"])
+                torch.distributed.all_reduce(b["part"], group=ffn.tp_group)
+                torch.add(h, b["part"], out=x)
+        ops.gemv_residual(x, self.norm.weight, eps, self.output.weight, None, b["logits"])
+        return b["logits"].view(1, 1, -1)
+
+    def kernels_per_token(self) -> int:
+        """Launches of this repo's kernels in one fused decode step (bench.py: gpu_launches)."""
+        return 5 * len(self.layers) + 1
+
     def forward(self, idx: Tensor, input_pos: Tensor, is_prefill, mask: Optional[Tensor] = None,
                 attn_top_k: Optional[float] = 1.0) -> Tensor:
         assert self.freqs_cis is not None, "Caches must be initialized first"
+        if not is_prefill and self._fused_ready(idx):
+            return self._decode_fused(idx, input_pos)
         freqs_cis = self.freqs_cis[input_pos]
         x = self.tok_embeddings(idx)
         for layer in self.layers:

@@ -26,6 +26,11 @@ _library.define(
 _library.define("key_norms(Tensor k, Tensor(a!) key_norm) -> ()")
 _library.define(
     "prefill_gather(Tensor(a!)[] state, int[] meta, Tensor k_prompt, Tensor v_prompt, Tensor keep_idx) -> ()")
+_library.define(
+    "rmsnorm_qkv_rope(Tensor x, Tensor norm_w, float eps, Tensor wqkv, Tensor? bias, Tensor freqs_cis, "
+    "Tensor input_pos, Tensor(a!) q, Tensor(b!) k, Tensor(c!) v, int n_q_heads, int n_kv_heads, int head_dim) -> ()")
+_library.define("gemv_residual(Tensor x, Tensor? norm_w, float eps, Tensor w, Tensor? residual, Tensor(a!) out) -> ()")
+_library.define("rmsnorm_ffn_gate(Tensor x, Tensor norm_w, float eps, Tensor w1, Tensor w3, Tensor(a!) out) -> ()")
 
 
 def _ptr(t: torch.Tensor):
@@ -91,7 +96,34 @@ def _prefill_gather(state, meta, k_prompt, v_prompt, keep_idx):
                                      n_keep, prompt_len, _stream()), "cc_prefill_gather")
 
 
+def _optr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _rmsnorm_qkv_rope(x, norm_w, eps, wqkv, bias, freqs_cis, input_pos, q, k, v, n_q_heads, n_kv_heads, head_dim):
+    _require_cuda(x, norm_w, wqkv, freqs_cis, input_pos, q, k, v)
+    _lib.check(_lib.load().cc_rmsnorm_qkv_rope(
+        x.data_ptr(), norm_w.data_ptr(), eps, wqkv.data_ptr(), _optr(bias), freqs_cis.data_ptr(), input_pos.data_ptr(),
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), wqkv.shape[1], n_q_heads, n_kv_heads, head_dim, _stream()),
+        "cc_rmsnorm_qkv_rope")
+
+
+def _gemv_residual(x, norm_w, eps, w, residual, out):
+    _require_cuda(x, w, out)
+    _lib.check(_lib.load().cc_gemv_residual(x.data_ptr(), _optr(norm_w), eps, w.data_ptr(), _optr(residual),
+                                            out.data_ptr(), w.shape[1], w.shape[0], _stream()), "cc_gemv_residual")
+
+
+def _rmsnorm_ffn_gate(x, norm_w, eps, w1, w3, out):
+    _require_cuda(x, norm_w, w1, w3, out)
+    _lib.check(_lib.load().cc_rmsnorm_ffn_gate(x.data_ptr(), norm_w.data_ptr(), eps, w1.data_ptr(), w3.data_ptr(),
+                                               out.data_ptr(), w1.shape[1], w1.shape[0], _stream()), "cc_rmsnorm_ffn_gate")
+
+
 _library.impl("decode_step", _decode_step, "CUDA")
+_library.impl("rmsnorm_qkv_rope", _rmsnorm_qkv_rope, "CUDA")
+_library.impl("gemv_residual", _gemv_residual, "CUDA")
+_library.impl("rmsnorm_ffn_gate", _rmsnorm_ffn_gate, "CUDA")
 _library.impl("key_norms", _key_norms, "CUDA")
 _library.impl("prefill_gather", _prefill_gather, "CUDA")
 
@@ -100,9 +132,12 @@ def _no_cpu(*_a, **_k):
     raise _lib.CcError("cold_compress_b200 ops have no CPU implementation: the decode path is CUDA (sm_100a) only")
 
 
-for _name in ("decode_step", "key_norms", "prefill_gather"):
+for _name in ("decode_step", "key_norms", "prefill_gather", "rmsnorm_qkv_rope", "gemv_residual", "rmsnorm_ffn_gate"):
     _library.impl(_name, _no_cpu, "CPU")
 
 decode_step = torch.ops.cold_compress_b200.decode_step
 key_norms = torch.ops.cold_compress_b200.key_norms
 prefill_gather = torch.ops.cold_compress_b200.prefill_gather
+rmsnorm_qkv_rope = torch.ops.cold_compress_b200.rmsnorm_qkv_rope
+gemv_residual = torch.ops.cold_compress_b200.gemv_residual
+rmsnorm_ffn_gate = torch.ops.cold_compress_b200.rmsnorm_ffn_gate

@@ -146,6 +146,10 @@ int cc_decode_step(const CcCacheState* state, const CcDecodeArgs* args, void* st
 /* Launch-shape query for tests / the bench: cluster size the step would use. */
 int cc_decode_cluster_size(const CcCacheState* state);
 
+/* Diagnostics: device buffer of [n_CTAs][16] u64 that later cc_decode_step launches fill with
+   %globaltimer stamps at their phase boundaries (profiles/trace_k1.py); NULL turns it off. */
+void cc_debug_set_trace(void* device_buffer);
+
 /*
  * Key L2 norms of cached keys: key_norm[h, s] = bf16(||k_cache[h, s, :]||_2).
  * Replaces KVCacheL2.update_state prefill branch (cache.py:607-612).
@@ -160,6 +164,24 @@ int cc_key_norms(const void* k, void* key_norm, int32_t n_rows, int32_t head_dim
 int cc_prefill_gather(const CcCacheState* state, const void* k_prompt, const void* v_prompt,
                       const int64_t* keep_idx, int32_t keep_heads, int32_t n_keep,
                       int32_t prompt_len, void* stream);
+
+/*
+ * The rest of the decode layer (one token): bf16 matrix-vector products with the elementwise
+ * work of the layer fused in.  x/out are device vectors, weights are nn.Linear weights [N, K]
+ * row-major.  norm_w != NULL applies the reference's RMSNorm (model.py:446-457) to x first.
+ *
+ * cc_rmsnorm_qkv_rope: attention_norm -> wqkv (+bias) -> rotary embedding at input_pos
+ *   (model.py:376-387, 507-519).  freqs_cis = the precompute_freqs_cis table [max_pos, D/2, 2].
+ * cc_gemv_residual:   out = [residual +] W x      (wo: model.py:431,317; w2: 443,326; output head: 290-291)
+ * cc_rmsnorm_ffn_gate: out = silu(w1 xn) * (w3 xn), xn = ffn_norm(x)   (model.py:442-443)
+ */
+int cc_rmsnorm_qkv_rope(const void* x, const void* norm_w, float eps, const void* wqkv, const void* bias,
+                        const void* freqs_cis, const int32_t* input_pos, void* q, void* k, void* v,
+                        int32_t dim, int32_t n_q_heads, int32_t n_kv_heads, int32_t head_dim, void* stream);
+int cc_gemv_residual(const void* x, const void* norm_w, float eps, const void* w, const void* residual,
+                     void* out, int32_t K, int32_t N, void* stream);
+int cc_rmsnorm_ffn_gate(const void* x, const void* norm_w, float eps, const void* w1, const void* w3,
+                        void* out, int32_t K, int32_t N, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,84 @@
+"""The reference's generate.py must find every name it imports in the drop-in aliases (CPU test).
+The names are listed here (taken from reference generate.py:16-51) so the test does not need the
+reference checkout; when /root/reference exists the list is re-derived from the file itself."""
+import ast
+import importlib
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+NEEDED = {
+    "cache": ["add_cache_arguments", "cache_compatibility", "get_cache_constructor"],
+    "generation_utils": ["add_generation_arguments", "compile_funcs", "compute_max_seq_length", "device_sync",
+                         "print_stats", "generate", "get_model_size", "load_model", "merge_cache_config",
+                         "setup_caches", "decode_n_tokens", "prefill", "decode_one_token", "reset_caches",
+                         "get_cache_stats", "normalize_cache_length", "apply_pattern"],
+    "tokenizer": ["get_tokenizer", "encode", "TokenizerInterface"],
+    "tp": ["maybe_init_dist", "apply_tp"],
+    "model": ["Transformer", "Attention", "FeedForward", "TransformerBlock", "ModelArgs", "find_multiple",
+              "transformer_configs", "precompute_freqs_cis", "apply_rotary_emb", "RMSNorm"],
+    "prompt_compression": ["get_prompt_compressor_constructor"],
+    "attention_utils": ["scaled_dot_product_attention"],
+}
+
+
+def _from_reference():
+    ref = Path("/root/reference/generate.py")
+    if not ref.exists():
+        return {}
+    found = {}
+    for node in ast.walk(ast.parse(ref.read_text())):
+        if isinstance(node, ast.ImportFrom) and node.module in NEEDED:
+            found.setdefault(node.module, []).extend(a.name for a in node.names)
+    return found
+
+
+def test_dropin_modules_export_what_generate_py_imports():
+    sys.path.insert(0, str(ROOT / "cold_compress_b200" / "dropin"))
+    try:
+        wanted = {m: list(v) for m, v in NEEDED.items()}
+        for m, names in _from_reference().items():
+            wanted[m] = sorted(set(wanted[m]) | set(names))
+        for mod, names in wanted.items():
+            sys.modules.pop(mod, None)
+            module = importlib.import_module(mod)
+            assert "cold_compress_b200" in (module.__doc__ or ""), f"{mod} resolved to a foreign module"
+            for n in names:
+                assert hasattr(module, n), f"{mod}.{n} missing"
+    finally:
+        sys.path.pop(0)
+        for mod in NEEDED:
+            sys.modules.pop(mod, None)
+
+
+def test_cli_arguments_match_reference_defaults():
+    import argparse
+    from cold_compress_b200.cache import add_cache_arguments, cache_compatibility
+    from cold_compress_b200.generation_utils import add_generation_arguments, merge_cache_config
+    p = argparse.ArgumentParser()
+    p.add_argument("--cache_config", default=None)
+    add_generation_arguments(p)
+    add_cache_arguments(p)
+    a = p.parse_args(["--cache_config", "heavy_hitter", "--max_cache_length", "1024"])
+    a = merge_cache_config(a)
+    assert a.cache_strategy == ["heavy_hitter"] and a.prompt_compression_strategy == ["heavy_hitter"]
+    assert a.global_tokens == 4 and a.recent_window == 10 and a.history_window_size == 1
+    assert a.max_cache_length == [1024.0] and a.cache_length_pattern == "tile"
+    cache_compatibility(a)
+    d = p.parse_args([])
+    assert d.cache_strategy == ["full"] and d.global_tokens == 1 and d.recent_window == 10 and d.min_recovery_frac == 0.9
+
+
+def test_abi_exports_every_declared_symbol():
+    """libcc_b200.so loads on a CPU-only box and exports everything include/cc_b200.h declares."""
+    import re
+    from cold_compress_b200 import _lib
+    lib = _lib.load()
+    header = (ROOT / "include" / "cc_b200.h").read_text()
+    declared = set(re.findall(r"\b(cc_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.cc_abi_version() == _lib.ABI_VERSION and b"sm_100a" in lib.cc_build_info()
+    import ctypes as C
+    assert C.sizeof(_lib.CcCacheState) == 12 * 4 + 18 * 8 and C.sizeof(_lib.CcDecodeArgs) == 7 * 8 + 8
