@@ -162,7 +162,7 @@ class Transformer(nn.Module):
                 and all(l.feed_forward.w2.in_features % 256 == 0 and l.attention.wo.in_features % 256 == 0
                         for l in self.layers[:1]))
 
-    def _buffers(self, device):
+    def _decode_buffers(self, device):
         if self._bufs is None or self._bufs["x"].device != device:
             att, ffn = self.layers[0].attention, self.layers[0].feed_forward
             mk = lambda n: torch.empty(n, dtype=torch.bfloat16, device=device)  # noqa: E731
@@ -176,7 +176,7 @@ class Transformer(nn.Module):
         """embedding -> per layer [norm+wqkv+RoPE | cache step | wo+residual | norm+gate | w2+residual] -> head.
         Same bf16 rounding points as the tensor-op path; every kernel takes `input_pos` from device
         memory, so the whole step is capturable in one CUDA graph."""
-        b = self._buffers(idx.device)
+        b = self._decode_buffers(idx.device)
         ip = input_pos if input_pos.dtype == torch.int32 else input_pos.int()
         eps = self.norm.eps
         b["x"].copy_(self.tok_embeddings(idx).view(-1))
