@@ -363,7 +363,9 @@ def cpu_decode_token(tok, pos):
 def cpu_reference(sample_seconds=20.0, warmup=1, steps=None):
     """tokens/s of the reference's CPU path (port): whole-model decode on the host cores."""
     from oracle import oracle
-    cores = os.cpu_count() or 1
+    # usable cores = the affinity mask (a container may see 128 logical CPUs but own 32; oversubscribing
+    # torch's intra-op pool beyond that collapses its GEMV throughput by 60x)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     torch.set_num_threads(cores)
     cpu_model()
     tok, pos = 17, PROMPT_LEN

@@ -32,7 +32,7 @@
 
 namespace cc {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxCluster = 16;
 constexpr int kMaxG = 8;
@@ -51,7 +51,7 @@ struct DecodeParams {
 };
 
 struct SmemLayout {
-    uint32_t kring, vring, lg, red, yx, rec, sums, x0, maskb, bars, misc, total;
+    uint32_t kring, vring, lg, red, yx, rec, sums, ssum, x0, maskb, bars, misc, total;
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
@@ -67,6 +67,7 @@ __host__ __device__ inline SmemLayout make_layout(int D, int G, int chunk_rows, 
     s.yx = off;    off += G * D * 4;
     s.rec = off;   off += kMaxCluster * kRecWords * 4;
     s.sums = off;  off += kMaxCluster * kMaxG * 8;
+    s.ssum = off;  off += kMaxG * 8;
     s.x0 = off;    off += 128;
     s.maskb = off; off += align_up(local_rows, 128);
     s.bars = off;  off += align_up(2 * n_stages * 8, 128);
@@ -83,8 +84,9 @@ enum : int {
     kMiscGmax = 24,     // [kMaxG]
     kMiscSumF = 32,     // [kMaxG]
     kMiscMyRec = 40,    // [kRecWords]
-    kMiscWarpKey = 64,  // [kWarps] u64
+    kMiscWarpKey = 64,  // [kWarps] u64 (32 words)
     kMiscWarpMax = 96,  // [kWarps]
+    kMiscWords = 128,
 };
 
 // hybrid per-head decision (reference cache.py:896-950)
@@ -105,6 +107,43 @@ __device__ __forceinline__ float group_butterfly(float v) {
     return v;
 }
 
+// Reduce G per-lane partial sums over the LPR lanes of a row group with the SAME addition tree as
+// group_butterfly (pairs at lane distance LPR/2, ..., 1) but exchanging halves of the value set while
+// more than one value is held: 5 shuffles instead of 16 for G = 4.  On return lane `li` holds the
+// full sum of query head `*g_out` (replicated over the lanes that share it); fp add is commutative,
+// so the bits equal the plain butterfly's.
+template <int LPR, int G>
+__device__ __forceinline__ float group_reduce_multi(const float (&v)[G], int li, int* g_out) {
+    constexpr int P0 = G <= 1 ? 1 : G <= 2 ? 2 : G <= 4 ? 4 : 8;
+    static_assert(P0 <= LPR, "more query heads than lanes per row");
+    float w[P0];
+#pragma unroll
+    for (int i = 0; i < P0; ++i) w[i] = i < G ? v[i] : 0.f;
+    int g = 0;
+    int held = P0;
+#pragma unroll
+    for (int d = LPR / 2; d >= 1; d >>= 1) {
+        if (held > 1) {
+            const int half = held / 2;
+            const bool upper = (li & d) != 0;  // upper lanes keep the upper half of the values
+#pragma unroll
+            for (int i = 0; i < P0 / 2; ++i) {
+                if (i < half) {
+                    const float send = upper ? w[i] : w[i + half];
+                    const float keep = upper ? w[i + half] : w[i];
+                    w[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, d));
+                }
+            }
+            if (upper) g += half;
+            held = half;
+        } else {
+            w[0] = __fadd_rn(w[0], __shfl_xor_sync(0xffffffffu, w[0], d));
+        }
+    }
+    *g_out = g;
+    return w[0];
+}
+
 __device__ __forceinline__ uint64_t warp_min_u64(uint64_t k) {
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
@@ -114,13 +153,14 @@ __device__ __forceinline__ uint64_t warp_min_u64(uint64_t k) {
     return k;
 }
 
-template <int D, int G, bool NAIVE>
+template <int D, int G, int POLICY, bool NAIVE>
 __global__ void __launch_bounds__(kThreads, 1)
 cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     constexpr int LPR = D / 8;           // lanes per cache row (16-byte slice each)
     constexpr int RPW = 32 / LPR;        // rows per warp iteration
     constexpr int NRG = kThreads / LPR;  // row groups in the P.V phase
     constexpr uint32_t kRowBytes = D * 2;
+    constexpr bool hybrid = POLICY == CC_POLICY_HYBRID;
 
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -134,11 +174,9 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     const int phases = p.a.phases;
     const bool do_evict = phases & CC_PHASE_EVICT_FILL, do_attend = phases & CC_PHASE_ATTEND,
                do_score = phases & CC_PHASE_SCORE;
-    const int policy = st.policy;
-    const bool hybrid = policy == CC_POLICY_HYBRID;
     const int NS = p.n_stages, stride = p.lg_stride;
     // shared (cross-head) state is read by every cluster and written by one: order with an epoch barrier
-    const bool needs_epoch = (do_evict && (policy == CC_POLICY_RECENT_GLOBAL || policy == CC_POLICY_L2)) ||
+    const bool needs_epoch = (do_evict && (POLICY == CC_POLICY_RECENT_GLOBAL || POLICY == CC_POLICY_L2)) ||
                              (hybrid && (do_evict || do_score));
 
     // chunk-cyclic ownership: local chunk j <-> global chunk rank + j*C; local row lr = j*CH + r
@@ -161,20 +199,17 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     uint64_t* vbar = kbar + NS;
     float* misc = reinterpret_cast<float*>(smem + lay.misc);
     uint32_t* miscu = reinterpret_cast<uint32_t*>(misc);
+    unsigned long long* ssum = reinterpret_cast<unsigned long long*>(smem + lay.ssum);  // [kMaxG] local fixed-point sums
 
     stamp(p, 0);
     cluster_arrive_relaxed();  // B0: this CTA has started (its shared memory may be written by peers)
     bool b0_waited = false;
 
-    const int ipos = p.a.input_pos[0];
-    const int pos_row = (st.pos_heads == 1) ? 0 : h;
-    const int32_t* posp = st.pos + (size_t)pos_row * L;
-
     // ---- hybrid: per-head decision from scalars (every CTA of the cluster computes the same)
     int hyb_mode = kHybAppend, hyb_bits = 0, hyb_cts = 0, hyb_rw = 0;
     int64_t hyb_counter = 0;
     int live_limit = L;  // slots >= live_limit cannot be live: their chunks are never loaded
-    if (hybrid) {
+    if constexpr (hybrid) {
         hyb_bits = st.hyb_strategy_bits[h];
         hyb_cts = st.cache_cts[h];
         hyb_rw = (hyb_bits & CC_HYB_WINDOW) ? st.hyb_recent_window[h] : 0;
@@ -219,12 +254,16 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             tma_load_1d(vring + j * chunk_bytes, vc + ((size_t)(j * C + rank) << chs) * D, bytes, &vbar[j]);
         }
     }
+    if (tid < kMaxG) ssum[tid] = 0ull;
     stamp(p, 1);
     // generation of the cross-cluster "shared reads done" barrier, read by the thread that may
     // later have to wait on it (lane 0 of the last warp) BEFORE this cluster arrives
     int32_t gen = 0;
     if (needs_epoch && tid == kThreads - 32) gen = ld_acquire_gpu(&st.sync_words[1]);
 
+    const int ipos = p.a.input_pos[0];
+    const int pos_row = (st.pos_heads == 1) ? 0 : h;
+    const int32_t* posp = st.pos + (size_t)pos_row * L;
     for (int lr = tid; lr < local_rows; lr += kThreads) {
         const int s = slot_of(lr);
         maskb[lr] = (s < L) ? st.mask[(size_t)h * L + s] : 0;
@@ -246,35 +285,37 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
 
     // ---- 1. L2 only: key_norm.max() over every head and slot (cache.py:602) = X0 exchange
     float l2_max = 0.f;
-    if (do_evict && policy == CC_POLICY_L2) {
-        const uint16_t* kn = reinterpret_cast<const uint16_t*>(st.key_norm);
-        float m = -CUDART_INF_F;
-        for (int hh = 0; hh < H; ++hh)
-            for (int lr = tid; lr < local_rows; lr += kThreads) {
-                const int s = slot_of(lr);
-                if (s < L) m = fmaxf(m, bf16_bits_to_float(kn[(size_t)hh * L + s]));
-            }
+    if constexpr (POLICY == CC_POLICY_L2) {
+        if (do_evict) {
+            const uint16_t* kn = reinterpret_cast<const uint16_t*>(st.key_norm);
+            float m = -CUDART_INF_F;
+            for (int hh = 0; hh < H; ++hh)
+                for (int lr = tid; lr < local_rows; lr += kThreads) {
+                    const int s = slot_of(lr);
+                    if (s < L) m = fmaxf(m, bf16_bits_to_float(kn[(size_t)hh * L + s]));
+                }
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
-        if (lane == 0) misc[kMiscWarpMax + warp] = m;
-        __syncthreads();
-        cluster_wait_acquire();
-        b0_waited = true;
-        if (tid < C) {
-            float mm = misc[kMiscWarpMax];
-            for (int w = 1; w < kWarps; ++w) mm = fmaxf(mm, misc[kMiscWarpMax + w]);
-            st_cluster_f32(map_to_rank(smem_u32(&x0[rank]), tid), mm);
+            for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+            if (lane == 0) misc[kMiscWarpMax + warp] = m;
+            __syncthreads();
+            cluster_wait_acquire();
+            b0_waited = true;
+            if (tid < C) {
+                float mm = misc[kMiscWarpMax];
+                for (int w = 1; w < kWarps; ++w) mm = fmaxf(mm, misc[kMiscWarpMax + w]);
+                st_cluster_f32(map_to_rank(smem_u32(&x0[rank]), tid), mm);
+            }
+            cluster_arrive_release();
+            cluster_wait_acquire();
+            l2_max = x0[0];
+            for (int r = 1; r < C; ++r) l2_max = fmaxf(l2_max, x0[r]);
         }
-        cluster_arrive_release();
-        cluster_wait_acquire();
-        l2_max = x0[0];
-        for (int r = 1; r < C; ++r) l2_max = fmaxf(l2_max, x0[r]);
     }
 
     // ---- 2. local arg-min candidate, key = (order(score) << 32) | slot  (first index wins ties)
     uint64_t ckey = kNoKey;
     if (do_evict) {
-        if (policy == CC_POLICY_HEAVY_HITTER) {
+        if constexpr (POLICY == CC_POLICY_HEAVY_HITTER) {
             const double* num = reinterpret_cast<const double*>(st.attn_history_num) + (size_t)h * L;
             const int32_t* den = st.attn_history_denom + (size_t)h * L;
             for (int lr = tid; lr < local_rows; lr += kThreads) {
@@ -288,7 +329,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
                 const uint64_t k = ((uint64_t)float_order_key(avg) << 32) | (uint32_t)s;
                 ckey = k < ckey ? k : ckey;
             }
-        } else if (policy == CC_POLICY_L2) {
+        } else if constexpr (POLICY == CC_POLICY_L2) {
             const uint16_t* kn = reinterpret_cast<const uint16_t*>(st.key_norm) + (size_t)h * L;
             for (int lr = tid; lr < local_rows; lr += kThreads) {
                 const int s = slot_of(lr);
@@ -302,7 +343,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
                 const uint64_t k = ((uint64_t)float_order_key(sc) << 32) | (uint32_t)s;
                 ckey = k < ckey ? k : ckey;
             }
-        } else if (policy == CC_POLICY_RECENT_GLOBAL) {
+        } else if constexpr (POLICY == CC_POLICY_RECENT_GLOBAL) {
             // cache.py:552-556: oldest position among slots >= g (unfilled = -1 first)
             for (int lr = tid; lr < local_rows; lr += kThreads) {
                 const int s = slot_of(lr);
@@ -310,7 +351,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
                 const uint64_t k = ((uint64_t)((uint32_t)posp[s] ^ 0x80000000u) << 32) | (uint32_t)s;
                 ckey = k < ckey ? k : ckey;
             }
-        } else if (hybrid) {
+        } else if constexpr (hybrid) {
             if (hyb_mode == kHybEvict) {
                 // cache.py:844-894 over the live prefix [0, cts): mean ring attention (or position for
                 // window-only heads); first g slots, special, punctuation and the recent window are saved
@@ -350,11 +391,8 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         ckey = warp_min_u64(ckey);
         if (lane == 0) reinterpret_cast<unsigned long long*>(miscu + kMiscWarpKey)[warp] = ckey;
         __syncthreads();
-        ckey = reinterpret_cast<unsigned long long*>(miscu + kMiscWarpKey)[0];
-        for (int w = 1; w < kWarps; ++w) {
-            const uint64_t o = reinterpret_cast<unsigned long long*>(miscu + kMiscWarpKey)[w];
-            ckey = o < ckey ? o : ckey;
-        }
+        ckey = lane < kWarps ? reinterpret_cast<unsigned long long*>(miscu + kMiscWarpKey)[lane] : kNoKey;
+        ckey = warp_min_u64(ckey);
     }
     stamp(p, 2);
     // local row of this CTA's candidate (it owns the slot by construction)
@@ -366,21 +404,24 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     // a dropped token does not take part in attention (its slot's mask stays as it was)
     const bool attend_new = do_evict && !(hybrid && hyb_mode == kHybDrop);
 
-    // ---- 3. logits over the K ring (canonical dot tree), new-token logits by warp 0
+    // ---- 3. logits over the K ring (canonical dot tree), new-token logits by the last warp
     if (do_attend) {
-        if (attend_new && warp == 0) {
+        if (attend_new && warp == kWarps - 1) {
             float kf[8];
             const uint4 kv = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.a.k_new) + (size_t)h * D + li * 8);
             unpack8(kv, kf);
+            float part[G];
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 float acc = 0.f;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc = __fmaf_rn(q[g][i], kf[i], acc);
-                acc = group_butterfly<LPR>(acc);
-                const float v = NAIVE ? bf16_round(__fmul_rn(bf16_round(acc), p.scale)) : __fmul_rn(acc, p.scale);
-                if (lane == 0) misc[kMiscNewLg + g] = v;
+                part[g] = acc;
             }
+            int gsel;
+            const float dot = group_reduce_multi<LPR, G>(part, li, &gsel);
+            const float v = NAIVE ? bf16_round(__fmul_rn(bf16_round(dot), p.scale)) : __fmul_rn(dot, p.scale);
+            if (sub == 0 && gsel < G) misc[kMiscNewLg + gsel] = v;  // replicated lanes write the same value
         }
         // rows of chunks that cannot be live
         for (int lr = live_rows + tid; lr < local_rows; lr += kThreads)
@@ -400,25 +441,20 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
                 uint4 kv = make_uint4(0, 0, 0, 0);
                 if (valid) kv = *reinterpret_cast<const uint4*>(kbase + r * kRowBytes + li * 16);
                 unpack8(kv, kf);
-                float dots[G];
+                float part[G];
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     float acc = 0.f;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) acc = __fmaf_rn(q[g][i], kf[i], acc);
-                    dots[g] = group_butterfly<LPR>(acc);
+                    part[g] = acc;
                 }
-                if (li == 0) {
-                    const int lr = (j << chs) + r;
-                    const bool live = valid && maskb[lr];
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        // naive path rounds q@k^T to bf16, then * scale to bf16 (attention_utils.py:37)
-                        const float v = NAIVE ? bf16_round(__fmul_rn(bf16_round(dots[g]), p.scale))
-                                              : __fmul_rn(dots[g], p.scale);
-                        lg[g * stride + lr] = live ? v : -CUDART_INF_F;
-                    }
-                }
+                int gsel;
+                const float dot = group_reduce_multi<LPR, G>(part, li, &gsel);
+                // naive path rounds q@k^T to bf16, then * scale to bf16 (attention_utils.py:37)
+                const float v = NAIVE ? bf16_round(__fmul_rn(bf16_round(dot), p.scale)) : __fmul_rn(dot, p.scale);
+                const int lr = (j << chs) + r;
+                if (gsel < G && r < CH) lg[gsel * stride + lr] = (valid && maskb[lr]) ? v : -CUDART_INF_F;
             }
             __syncthreads();
             if (tid == 0 && j + NS < nlc_live) {
@@ -429,7 +465,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
                 tma_load_1d(kring + stage * chunk_bytes, kc + ((size_t)(jn * C + rank) << chs) * D, bytes, &kbar[stage]);
             }
         }
-        // ---- 4. row max without the local candidate, and the candidate's own logits
+        // ---- 4. row max without the local candidate, and the candidate's own logits -> my X1 record
         for (int g = warp; g < G; g += kWarps) {
             float m = -CUDART_INF_F;
             for (int lr = lane; lr < live_rows; lr += 32)
@@ -437,21 +473,18 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
             if (lane == 0) {
-                misc[kMiscLmax + g] = m;
-                misc[kMiscCandLg + g] = cand_local >= 0 ? lg[g * stride + cand_local] : -CUDART_INF_F;
+                misc[kMiscMyRec + 2 + g] = m;
+                misc[kMiscMyRec + 2 + G + g] = cand_local >= 0 ? lg[g * stride + cand_local] : -CUDART_INF_F;
             }
         }
+    } else if (tid < 2 * G) {
+        misc[kMiscMyRec + 2 + tid] = -CUDART_INF_F;
     }
     stamp(p, 4);
     // ---- 5. X1: every CTA learns every candidate and every partial max
     if (tid == 0) {
         miscu[kMiscMyRec + 0] = (uint32_t)(ckey & 0xffffffffu);
         miscu[kMiscMyRec + 1] = (uint32_t)(ckey >> 32);
-    }
-    __syncthreads();
-    if (tid < G) {
-        miscu[kMiscMyRec + 2 + tid] = __float_as_uint(do_attend ? misc[kMiscLmax + tid] : -CUDART_INF_F);
-        miscu[kMiscMyRec + 2 + G + tid] = __float_as_uint(do_attend ? misc[kMiscCandLg + tid] : -CUDART_INF_F);
     }
     __syncthreads();
     if (!b0_waited) cluster_wait_acquire();
@@ -462,14 +495,13 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     }
     cluster_arrive_release();
     cluster_wait_acquire();
-
     stamp(p, 5);
-    // ---- 6. winner + global max per query head
+
+    // ---- 6. winner + global max per query head (every warp redundantly: no block barrier needed)
     uint64_t wkey = kNoKey;
-    for (int r = 0; r < C; ++r) {
-        const uint64_t k = (uint64_t)rec[r * kRecWords] | ((uint64_t)rec[r * kRecWords + 1] << 32);
-        wkey = k < wkey ? k : wkey;
-    }
+    if (lane < C) wkey = (uint64_t)rec[lane * kRecWords] | ((uint64_t)rec[lane * kRecWords + 1] << 32);
+    const bool lane_has_cand = wkey != kNoKey;
+    wkey = warp_min_u64(wkey);
     const bool has_slot = do_evict && wkey != kNoKey;  // a slot is overwritten this step
     const int widx = has_slot ? (int)(uint32_t)(wkey & 0xffffffffu) : -1;
     const int owner = has_slot ? (widx >> chs) % C : -1;
@@ -477,176 +509,77 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     const int widx_local = has_slot ? (((widx >> chs) / C) << chs) + (widx & (CH - 1)) : -1;
     const bool has_new = has_slot && attend_new;  // ... and the new token attends to itself there
     if (needs_epoch && rank == 0 && tid == 0) red_release_gpu_add(&st.sync_words[0], 1);  // shared reads done
-    if (do_attend && tid < G) {
-        float m = has_new ? misc[kMiscNewLg + tid] : -CUDART_INF_F;
-        for (int r = 0; r < C; ++r) {
-            m = fmaxf(m, __uint_as_float(rec[r * kRecWords + 2 + tid]));
-            const bool has_cand = !(rec[r * kRecWords] == 0xffffffffu && rec[r * kRecWords + 1] == 0xffffffffu);
-            // a candidate that is not overwritten keeps its logit; the overwritten one only if the
-            // new token does not replace it in attention (hybrid drop: slot L-1 stays as it was)
-            if (has_cand && (r != owner || !has_new)) m = fmaxf(m, __uint_as_float(rec[r * kRecWords + 2 + G + tid]));
-        }
-        misc[kMiscGmax + tid] = m;
-        if (i_own && has_new) lg[tid * stride + widx_local] = misc[kMiscNewLg + tid];
-    }
-
-    // ---- 7. owner CTA: in-place slot overwrite (cache.py:390-401 / 460-490) + policy state
-    if (i_own && warp == kWarps - 1) {
-        if (lane < LPR) {
-            const uint16_t* ks = reinterpret_cast<const uint16_t*>(p.a.k_new) + (size_t)h * D + lane * 8;
-            const uint16_t* vs = reinterpret_cast<const uint16_t*>(p.a.v_new) + (size_t)h * D + lane * 8;
-            uint16_t* kd = reinterpret_cast<uint16_t*>(st.k_cache) + ((size_t)h * L + widx) * D + lane * 8;
-            uint16_t* vd = reinterpret_cast<uint16_t*>(st.v_cache) + ((size_t)h * L + widx) * D + lane * 8;
-            *reinterpret_cast<uint4*>(kd) = *reinterpret_cast<const uint4*>(ks);
-            *reinterpret_cast<uint4*>(vd) = *reinterpret_cast<const uint4*>(vs);
-        }
-        float knorm = 0.f;
-        if (policy == CC_POLICY_L2) {
-            // key_norm[idx] = ||k_new||_2 (cache.py:592-593), canonical tree, correctly rounded sqrt
-            float kf[8];
-            const uint4 kv = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.a.k_new) + (size_t)h * D + li * 8);
-            unpack8(kv, kf);
-            float acc = 0.f;
+    float gmax[G], newlg[G];
+    if (do_attend) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc = __fmaf_rn(kf[i], kf[i], acc);
-            knorm = __fsqrt_rn(group_butterfly<LPR>(acc));
-        }
-        if (lane == 0) {
-            const int32_t pos_old = posp[widx];
-            if (!hybrid || hyb_mode == kHybAppend) st.mask[(size_t)h * L + widx] = 1;
-            if (p.a.fill_idx && policy != CC_POLICY_EXTERNAL) p.a.fill_idx[h] = widx;
-            if (policy == CC_POLICY_HEAVY_HITTER && !do_score) {
-                reinterpret_cast<double*>(st.attn_history_num)[(size_t)h * L + widx] = 0.0;  // cache.py:753-763
-                st.attn_history_denom[(size_t)h * L + widx] = 0;
+        for (int g = 0; g < G; ++g) {
+            newlg[g] = has_new ? misc[kMiscNewLg + g] : -CUDART_INF_F;
+            float m = -CUDART_INF_F;
+            if (lane < C) {
+                m = __uint_as_float(rec[lane * kRecWords + 2 + g]);
+                // a candidate that is not overwritten keeps its logit; the overwritten one only if the new
+                // token does not replace it in attention (hybrid drop: slot L-1 stays as it was)
+                if (lane_has_cand && (lane != owner || !has_new))
+                    m = fmaxf(m, __uint_as_float(rec[lane * kRecWords + 2 + G + g]));
             }
-            if (hybrid && p.a.is_punc && st.punc_mask) st.punc_mask[(size_t)h * L + widx] = 1;  // cache.py:1011-1016
-            if (needs_epoch) {  // head-constant pos, key_norm, counters are read by every cluster: write after all have read
-                const int32_t target = (gen + 1) * H;
-                while (ld_acquire_gpu(&st.sync_words[0]) - target < 0) {}
-            }
-            if (policy == CC_POLICY_L2)
-                reinterpret_cast<__nv_bfloat16*>(st.key_norm)[(size_t)h * L + widx] = __float2bfloat16_rn(knorm);
-            if (st.pos_heads != 1 || h == 0) st.pos[(size_t)pos_row * L + widx] = ipos;
-            if (hybrid) {
-                if (hyb_mode == kHybAppend) st.cache_cts[h] = hyb_cts + 1;
-                if (h == 0 && p.a.is_punc && st.num_punc) st.num_punc[0] += 1;
-            } else if (h == 0) {
-                st.cache_cts[0] += (pos_old == -1) ? 1 : 0;  // cache.py:330, 356-360
-            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+            gmax[g] = fmaxf(m, newlg[g]);
         }
     }
-    if (needs_epoch && h == 0 && rank == 0 && tid == 32) {
-        // generation bump (and the shared step counter): only after every cluster has arrived
-        const int32_t g0 = ld_acquire_gpu(&st.sync_words[1]);
-        const int32_t target = (g0 + 1) * H;
-        while (ld_acquire_gpu(&st.sync_words[0]) - target < 0) {}
-        if (hybrid && do_score && NAIVE) st.attn_counter[0] = hyb_counter + 1;
-        st_release_gpu(&st.sync_words[1], g0 + 1);
-    }
-    __syncthreads();
+    const int patch_row = (i_own && has_new) ? widx_local : -1;  // this row now holds the new token
     stamp(p, 6);
 
     if (do_attend) {
-        // ---- 8. exp and the exact fixed-point softmax denominator = X2
-        float gmax[G];
+        // ---- 8. exp and the exact fixed-point softmax denominator = X2.  Items are (g, row) pairs laid
+        // out g-major with the row count padded to a warp multiple, so a warp never straddles two g.
+        const int rows_pad = (live_rows + 31) & ~31;
+        for (int it = tid; it < G * rows_pad; it += kThreads) {
+            const int g = it / rows_pad, lr = it - g * rows_pad;
+            long long part = 0;
+            if (lr < live_rows) {
+                float gm = gmax[0], nl = newlg[0];
 #pragma unroll
-        for (int g = 0; g < G; ++g) gmax[g] = misc[kMiscGmax + g];
-        long long isum[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) isum[g] = 0;
-        for (int lr = tid; lr < live_rows; lr += kThreads) {
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const float e = det_expf(__fsub_rn(lg[g * stride + lr], gmax[g]));
+                for (int gg = 1; gg < G; ++gg) if (g == gg) { gm = gmax[gg]; nl = newlg[gg]; }
+                const float l = lr == patch_row ? nl : lg[g * stride + lr];
+                const float e = det_expf(__fsub_rn(l, gm));
                 lg[g * stride + lr] = e;
-                isum[g] += __float2ll_rz(__fmul_rn(e, 1099511627776.0f));
+                part = __float2ll_rz(__fmul_rn(e, 1099511627776.0f));
             }
-        }
-        long long* wsum = reinterpret_cast<long long*>(red);  // [kWarps][G]; red is free until the P.V phase
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            long long v = isum[g];
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-            if (lane == 0) wsum[warp * G + g] = v;
+            for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+            if (lane == 0 && part) atomicAdd(&ssum[g], (unsigned long long)part);  // integers: order independent
         }
         __syncthreads();
+        stamp(p, 7);
         for (int idx = tid; idx < C * G; idx += kThreads) {
             const int dest = idx / G, g = idx % G;
-            long long v = 0;
-            for (int w = 0; w < kWarps; ++w) v += wsum[w * G + g];
-            st_cluster_u64(map_to_rank(smem_u32(&sums[rank * kMaxG + g]), dest), (uint64_t)v);
+            st_cluster_u64(map_to_rank(smem_u32(&sums[rank * kMaxG + g]), dest), ssum[g]);
         }
-        stamp(p, 7);
         cluster_arrive_release();
         cluster_wait_acquire();
         stamp(p, 8);
-        if (tid < G) {
-            long long tot = 0;
-            for (int r = 0; r < C; ++r) tot += (long long)sums[r * kMaxG + tid];
-            misc[kMiscSumF + tid] = __fmul_rn(__ll2float_rn(tot), 9.094947017729282e-13f);  // 2^-40
-        }
-        __syncthreads();
-    }
-
-    // ---- 9. probabilities, GQA pooling (model.py:413-418), score update (cache.py:716-723)
-    {
+        // ---- 9a. probabilities (every warp sums the C partial denominators itself)
         float sumf[G];
 #pragma unroll
-        for (int g = 0; g < G; ++g) sumf[g] = do_attend ? misc[kMiscSumF + g] : 1.f;
-        const bool hh_score = do_score && NAIVE && policy == CC_POLICY_HEAVY_HITTER;
-        const bool ring_score = do_score && NAIVE && hybrid;
-        const int W = st.history_window;
-        const int wslot = ring_score ? (int)(hyb_counter % W) : 0;
-        __nv_bfloat16* probs = reinterpret_cast<__nv_bfloat16*>(p.a.probs);
-        for (int lr = tid; lr < local_rows; lr += kThreads) {
-            const int s = slot_of(lr);
-            if (s >= L) continue;
-            float pooled = 0.f;
-            if (do_attend) {
-                if (lr < live_rows) {
-                    float acc = 0.f;
+        for (int g = 0; g < G; ++g) {
+            long long t = lane < C ? (long long)sums[lane * kMaxG + g] : 0ll;
 #pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        float pr = __fdiv_rn(lg[g * stride + lr], sumf[g]);
-                        if (NAIVE) pr = bf16_round(pr);
-                        lg[g * stride + lr] = pr;
-                        acc = g == 0 ? pr : __fadd_rn(acc, pr);
-                    }
-                    if (NAIVE) pooled = bf16_round(__fdiv_rn(acc, (float)G));  // torch mean: fp32 sum / G, then bf16
-                }
-                if (NAIVE && probs) probs[(size_t)h * L + s] = __float2bfloat16_rn(pooled);
-            } else if (hh_score || ring_score) {
-                pooled = __bfloat162float(probs[(size_t)h * L + s]);
-            }
-            if (hh_score) {
-                double* num = reinterpret_cast<double*>(st.attn_history_num) + (size_t)h * L;
-                int32_t* den = st.attn_history_denom + (size_t)h * L;
-                const bool fresh = has_slot && s == widx;  // evicted slot's history restarts (cache.py:753-763)
-                num[s] = (fresh ? 0.0 : num[s]) + (double)pooled;
-                den[s] = (fresh ? 0 : den[s]) + 1;
-            } else if (ring_score) {
-                // ring[s][counter % W] = pooled; the evicted slot keeps its ring (the reference's reset is a
-                // silent no-op, cache.py:993-996).  Only live slots can hold non-zero history.
-                int32_t* den = st.attn_history_denom + (size_t)h * L;
-                den[s] += 1;
-                if (s < live_limit || pooled != 0.f) {
-                    __nv_bfloat16* cell = reinterpret_cast<__nv_bfloat16*>(st.attn_history_num) + ((size_t)h * L + s) * W + wslot;
-                    const float old = __bfloat162float(*cell);
-                    if (old != pooled) {
-                        double* hs = st.attn_history_sum + (size_t)h * L + s;
-                        *hs = (*hs - (double)old) + (double)pooled;
-                        *cell = __float2bfloat16_rn(pooled);
-                    }
-                }
-            }
+            for (int d = 16; d >= 1; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+            sumf[g] = __fmul_rn(__ll2float_rn(t), 9.094947017729282e-13f);  // 2^-40
         }
-        if (hh_score && h == 0 && rank == 0 && tid == 0) st.attn_counter[0] += 1;
-    }
-
-    stamp(p, 9);
-    if (do_attend) {
+        for (int it = tid; it < G * live_rows; it += kThreads) {
+            const int g = it / live_rows, lr = it - g * live_rows;
+            float sf = sumf[0];
+#pragma unroll
+            for (int gg = 1; gg < G; ++gg) if (g == gg) sf = sumf[gg];
+            float pr = __fdiv_rn(lg[g * stride + lr], sf);
+            if (NAIVE) pr = bf16_round(pr);
+            lg[g * stride + lr] = pr;
+        }
         __syncthreads();
+        stamp(p, 9);
+
         // ---- 10. y = P.V over the V ring, cluster-wide reduction = X3
         float acc[G][8];
 #pragma unroll
@@ -654,7 +587,6 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[g][i] = 0.f;
         const int rg = tid / LPR;
-        const int patch_row = (i_own && has_new) ? widx_local : -1;
         for (int j = 0; j < nlc_live; ++j) {
             const int stage = j % NS;
             mbar_wait(&vbar[stage], (j / NS) & 1);
@@ -673,13 +605,15 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
                     for (int i = 0; i < 8; ++i) acc[g][i] = fmaf(pr, vf[i], acc[g][i]);
                 }
             }
-            __syncthreads();
-            if (tid == 0 && j + NS < nlc_live) {
-                fence_proxy_async();
-                const int jn = j + NS;
-                const uint32_t bytes = chunk_rows_valid(jn) * kRowBytes;
-                mbar_expect_tx(&vbar[stage], bytes);
-                tma_load_1d(vring + stage * chunk_bytes, vc + ((size_t)(jn * C + rank) << chs) * D, bytes, &vbar[stage]);
+            if (j + NS < nlc_live) {  // ring slot is refilled: everyone must be done with it
+                __syncthreads();
+                if (tid == 0) {
+                    fence_proxy_async();
+                    const int jn = j + NS;
+                    const uint32_t bytes = chunk_rows_valid(jn) * kRowBytes;
+                    mbar_expect_tx(&vbar[stage], bytes);
+                    tma_load_1d(vring + stage * chunk_bytes, vc + ((size_t)(jn * C + rank) << chs) * D, bytes, &vbar[stage]);
+                }
             }
         }
         stamp(p, 10);
@@ -711,8 +645,116 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         }
         stamp(p, 11);
         cluster_arrive_release();
+    }
+
+    // ======== off the critical path: global state writes, overlapped with the X3 barrier ========
+    // ---- 7. owner CTA: in-place slot overwrite (cache.py:390-401 / 460-490) + policy state
+    if (i_own && warp == kWarps - 1) {
+        if (lane < LPR) {
+            const uint16_t* ks = reinterpret_cast<const uint16_t*>(p.a.k_new) + (size_t)h * D + lane * 8;
+            const uint16_t* vs = reinterpret_cast<const uint16_t*>(p.a.v_new) + (size_t)h * D + lane * 8;
+            uint16_t* kd = reinterpret_cast<uint16_t*>(st.k_cache) + ((size_t)h * L + widx) * D + lane * 8;
+            uint16_t* vd = reinterpret_cast<uint16_t*>(st.v_cache) + ((size_t)h * L + widx) * D + lane * 8;
+            *reinterpret_cast<uint4*>(kd) = *reinterpret_cast<const uint4*>(ks);
+            *reinterpret_cast<uint4*>(vd) = *reinterpret_cast<const uint4*>(vs);
+        }
+        float knorm = 0.f;
+        if constexpr (POLICY == CC_POLICY_L2) {
+            // key_norm[idx] = ||k_new||_2 (cache.py:592-593), canonical tree, correctly rounded sqrt
+            float kf[8];
+            const uint4 kv = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.a.k_new) + (size_t)h * D + li * 8);
+            unpack8(kv, kf);
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc = __fmaf_rn(kf[i], kf[i], acc);
+            knorm = __fsqrt_rn(group_butterfly<LPR>(acc));
+        }
+        if (lane == 0) {
+            const int32_t pos_old = posp[widx];
+            if (!hybrid || hyb_mode == kHybAppend) st.mask[(size_t)h * L + widx] = 1;
+            if (p.a.fill_idx && POLICY != CC_POLICY_EXTERNAL) p.a.fill_idx[h] = widx;
+            if (POLICY == CC_POLICY_HEAVY_HITTER && !do_score) {
+                reinterpret_cast<double*>(st.attn_history_num)[(size_t)h * L + widx] = 0.0;  // cache.py:753-763
+                st.attn_history_denom[(size_t)h * L + widx] = 0;
+            }
+            if (hybrid && p.a.is_punc && st.punc_mask) st.punc_mask[(size_t)h * L + widx] = 1;  // cache.py:1011-1016
+            if (needs_epoch) {  // head-constant pos, key_norm, counters are read by every cluster: write after all have read
+                const int32_t target = (gen + 1) * H;
+                while (ld_acquire_gpu(&st.sync_words[0]) - target < 0) {}
+            }
+            if constexpr (POLICY == CC_POLICY_L2)
+                reinterpret_cast<__nv_bfloat16*>(st.key_norm)[(size_t)h * L + widx] = __float2bfloat16_rn(knorm);
+            if (st.pos_heads != 1 || h == 0) st.pos[(size_t)pos_row * L + widx] = ipos;
+            if constexpr (hybrid) {
+                if (hyb_mode == kHybAppend) st.cache_cts[h] = hyb_cts + 1;
+                if (h == 0 && p.a.is_punc && st.num_punc) st.num_punc[0] += 1;
+            } else if (h == 0) {
+                st.cache_cts[0] += (pos_old == -1) ? 1 : 0;  // cache.py:330, 356-360
+            }
+        }
+    }
+    if (needs_epoch && h == 0 && rank == 0 && tid == 32) {
+        // generation bump (and the shared step counter): only after every cluster has arrived
+        const int32_t g0 = ld_acquire_gpu(&st.sync_words[1]);
+        const int32_t target = (g0 + 1) * H;
+        while (ld_acquire_gpu(&st.sync_words[0]) - target < 0) {}
+        if (hybrid && do_score && NAIVE) st.attn_counter[0] = hyb_counter + 1;
+        st_release_gpu(&st.sync_words[1], g0 + 1);
+    }
+
+    // ---- 9b. GQA pooling (model.py:413-418) and the score update (cache.py:716-723)
+    {
+        const bool hh_score = do_score && NAIVE && POLICY == CC_POLICY_HEAVY_HITTER;
+        const bool ring_score = do_score && NAIVE && hybrid;
+        const int W = st.history_window;
+        const int wslot = ring_score ? (int)(hyb_counter % W) : 0;
+        __nv_bfloat16* probs = reinterpret_cast<__nv_bfloat16*>(p.a.probs);
+        if (NAIVE && (hh_score || ring_score || (do_attend && probs))) {
+            for (int lr = tid; lr < local_rows; lr += kThreads) {
+                const int s = slot_of(lr);
+                if (s >= L) continue;
+                float pooled = 0.f;
+                if (do_attend) {
+                    if (lr < live_rows) {
+                        float acc = lg[lr];
+#pragma unroll
+                        for (int g = 1; g < G; ++g) acc = __fadd_rn(acc, lg[g * stride + lr]);
+                        pooled = bf16_round(__fdiv_rn(acc, (float)G));  // torch mean: fp32 sum / G, then bf16
+                    }
+                    if (probs) probs[(size_t)h * L + s] = __float2bfloat16_rn(pooled);
+                } else {
+                    pooled = __bfloat162float(probs[(size_t)h * L + s]);
+                }
+                if (hh_score) {
+                    double* num = reinterpret_cast<double*>(st.attn_history_num) + (size_t)h * L;
+                    int32_t* den = st.attn_history_denom + (size_t)h * L;
+                    const bool fresh = has_slot && s == widx;  // evicted slot's history restarts (cache.py:753-763)
+                    num[s] = (fresh ? 0.0 : num[s]) + (double)pooled;
+                    den[s] = (fresh ? 0 : den[s]) + 1;
+                } else if (ring_score) {
+                    // ring[s][counter % W] = pooled; the evicted slot keeps its ring (the reference's reset is a
+                    // silent no-op, cache.py:993-996).  Only live slots can hold non-zero history.
+                    int32_t* den = st.attn_history_denom + (size_t)h * L;
+                    den[s] += 1;
+                    if (s < live_limit || pooled != 0.f) {
+                        __nv_bfloat16* cell = reinterpret_cast<__nv_bfloat16*>(st.attn_history_num) + ((size_t)h * L + s) * W + wslot;
+                        const float old = __bfloat162float(*cell);
+                        if (old != pooled) {
+                            double* hs = st.attn_history_sum + (size_t)h * L + s;
+                            *hs = (*hs - (double)old) + (double)pooled;
+                            *cell = __float2bfloat16_rn(pooled);
+                        }
+                    }
+                }
+            }
+        }
+        if (hh_score && h == 0 && rank == 0 && tid == 0) st.attn_counter[0] += 1;
+    }
+
+    if (do_attend) {
         cluster_wait_acquire();
         stamp(p, 12);
+        const int SL = G * D / C;
         __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.a.y) + (size_t)h * G * D;
         for (int t = tid; t < SL; t += kThreads) {
             float s = yx[t];
@@ -728,24 +770,32 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
 using KernelFn = void (*)(const DecodeParams);
 
 template <int D, int G>
-static KernelFn pick_mode(bool naive) {
-    return naive ? (KernelFn)cc_decode_kernel<D, G, true> : (KernelFn)cc_decode_kernel<D, G, false>;
-}
-template <int D>
-static KernelFn pick_group(int G, bool naive) {
-    switch (G) {
-    case 1: return pick_mode<D, 1>(naive);
-    case 2: return pick_mode<D, 2>(naive);
-    case 4: return pick_mode<D, 4>(naive);
-    case 6: return pick_mode<D, 6>(naive);
-    case 7: return pick_mode<D, 7>(naive);
-    case 8: return pick_mode<D, 8>(naive);
+static KernelFn pick_policy(int policy, bool naive) {
+    switch (policy) {
+    case CC_POLICY_EXTERNAL: return naive ? nullptr : (KernelFn)cc_decode_kernel<D, G, CC_POLICY_EXTERNAL, false>;
+    case CC_POLICY_RECENT_GLOBAL: return naive ? nullptr : (KernelFn)cc_decode_kernel<D, G, CC_POLICY_RECENT_GLOBAL, false>;
+    case CC_POLICY_L2: return naive ? nullptr : (KernelFn)cc_decode_kernel<D, G, CC_POLICY_L2, false>;
+    case CC_POLICY_HEAVY_HITTER: return naive ? (KernelFn)cc_decode_kernel<D, G, CC_POLICY_HEAVY_HITTER, true> : nullptr;
+    case CC_POLICY_HYBRID: return naive ? (KernelFn)cc_decode_kernel<D, G, CC_POLICY_HYBRID, true>
+                                        : (KernelFn)cc_decode_kernel<D, G, CC_POLICY_HYBRID, false>;
     default: return nullptr;
     }
 }
-static KernelFn pick_kernel(int D, int G, bool naive) {
-    if (D == 128) return pick_group<128>(G, naive);
-    if (D == 64) return pick_group<64>(G, naive);
+template <int D>
+static KernelFn pick_group(int G, int policy, bool naive) {
+    switch (G) {
+    case 1: return pick_policy<D, 1>(policy, naive);
+    case 2: return pick_policy<D, 2>(policy, naive);
+    case 4: return pick_policy<D, 4>(policy, naive);
+    case 6: return pick_policy<D, 6>(policy, naive);
+    case 7: return pick_policy<D, 7>(policy, naive);
+    case 8: return pick_policy<D, 8>(policy, naive);
+    default: return nullptr;
+    }
+}
+static KernelFn pick_kernel(int D, int G, int policy, bool naive) {
+    if (D == 128) return pick_group<128>(G, policy, naive);
+    if (D == 64) return pick_group<64>(G, policy, naive);
     return nullptr;
 }
 
@@ -773,7 +823,7 @@ static int device_limits() {
 }
 
 // Plans are cached per (shape, policy class): the occupancy query is not free.
-struct PlanKey { int D, G, naive, H, L, epoch; };
+struct PlanKey { int D, G, naive, H, L, policy; };
 struct PlanEntry { PlanKey k; LaunchPlan p; };
 static PlanEntry g_plans[128];
 static int g_nplans = 0;
@@ -783,15 +833,15 @@ static int make_plan(const CcCacheState* st, bool needs_epoch, LaunchPlan* out) 
     const bool naive = st->attn_mode == CC_ATTN_NAIVE_BF16;
     for (int i = 0; i < g_nplans; ++i) {
         const PlanKey& k = g_plans[i].k;
-        if (k.D == D && k.G == G && k.naive == (int)naive && k.H == H && k.L == L && k.epoch == (int)needs_epoch) {
+        if (k.D == D && k.G == G && k.naive == (int)naive && k.H == H && k.L == L && k.policy == st->policy) {
             *out = g_plans[i].p;
             return CC_OK;
         }
     }
     int rc = device_limits();
     if (rc) return rc;
-    KernelFn fn = pick_kernel(D, G, naive);
-    if (!fn) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "unsupported head_dim (64/128) or q_per_kv (1,2,4,6,7,8)");
+    KernelFn fn = pick_kernel(D, G, st->policy, naive);
+    if (!fn) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "unsupported head_dim (64/128), q_per_kv (1,2,4,6,7,8) or policy/attention-mode pair");
     cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     // the cap is per function and plans for other shapes share it: raise it once to the device
     // limit instead of to this plan's size (a later, smaller plan must not lower it)
@@ -823,7 +873,7 @@ static int make_plan(const CcCacheState* st, bool needs_epoch, LaunchPlan* out) 
             // with the cross-head epoch barrier every cluster must be co-resident
             if (max_clusters < (needs_epoch ? H : 1)) continue;
             LaunchPlan p = {fn, C, chs, mlc, ns, stride, lay.total};
-            if (g_nplans < 128) g_plans[g_nplans++] = {{D, G, (int)naive, H, L, (int)needs_epoch}, p};
+            if (g_nplans < 128) g_plans[g_nplans++] = {{D, G, (int)naive, H, L, st->policy}, p};
             *out = p;
             return CC_OK;
         }

@@ -25,9 +25,9 @@ pos = torch.tensor([L], dtype=torch.int32, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for c in caches:
     c.decode_step(q, k, v, pos)
-trace = torch.zeros(256, 16, dtype=torch.int64, device="cuda")
-names = ["start", "tma issued", "candidate", "K chunk0 landed", "logits+lmax", "X1 done", "owner writes+sync",
-         "exp+push sums", "X2 done", "probs+score", "PV loop", "reduce+push y", "X3 done", "end"]
+trace = torch.zeros(512, 16, dtype=torch.int64, device="cuda")
+names = ["start", "tma issued", "candidate", "K chunk0 landed", "logits+lmax", "X1 done", "winner+gmax",
+         "exp+local sums", "X2 done", "probs", "PV loop", "reduce+push y", "state writes+X3 done", "end"]
 lib = _lib.load()
 for rep in range(3):
     flush.fill_(rep)
