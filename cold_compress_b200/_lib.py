@@ -10,13 +10,16 @@ import ctypes as C
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-SO_PATH = PKG / "libcc_b200.so"
+import os
+
+SO_PATH = Path(os.environ.get("CC_B200_LIB", PKG / "libcc_b200.so"))  # override: A/B builds in profiles/
 
 ABI_VERSION = 1
 CC_OK = 0
 POLICY_EXTERNAL, POLICY_RECENT_GLOBAL, POLICY_L2, POLICY_HEAVY_HITTER, POLICY_HYBRID = range(5)
 ATTN_MATH_FP32, ATTN_NAIVE_BF16 = 0, 1
 PHASE_EVICT_FILL, PHASE_ATTEND, PHASE_SCORE, PHASE_ALL = 1, 2, 4, 7
+FLAG_OVERLAP_PREDECESSOR = 1
 HYB_FULL, HYB_WINDOW, HYB_HEAVY_HITTER, HYB_SPECIAL, HYB_PUNC = 1, 2, 4, 8, 16
 
 _STATE_INTS = ("policy", "attn_mode", "n_kv_heads", "q_per_kv", "head_dim", "max_cache_length",
@@ -32,7 +35,7 @@ class CcCacheState(C.Structure):
 
 class CcDecodeArgs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("q", "k_new", "v_new", "input_pos", "y", "fill_idx", "probs")] + [
-        ("is_punc", C.c_int32), ("phases", C.c_int32)]
+        ("is_punc", C.c_int32), ("phases", C.c_int32), ("flags", C.c_int32), ("reserved1", C.c_int32)]
 
 
 # every symbol include/cc_b200.h declares: name -> (restype, argtypes)

@@ -159,7 +159,9 @@ class KVCache(nn.Module):
         return _lib.ATTN_NAIVE_BF16 if self.return_attn() else _lib.ATTN_MATH_FP32
 
     def decode_step(self, q, k_val, v_val, input_pos, **kwargs):
-        """ONE kernel: evict -> overwrite -> attend -> pool -> score.  q [1,Hq,1,D]; returns y [1,Hq,1,D]."""
+        """ONE kernel: evict -> overwrite -> attend -> pool -> score.  q [1,Hq,1,D]; returns y [1,Hq,1,D].
+        overlap_predecessor=True promises that the kernel launched just before on this stream does not
+        write this cache (CC_FLAG_OVERLAP_PREDECESSOR): the step then starts fetching early."""
         return self._launch(_lib.PHASE_ALL, q, k_val, v_val, input_pos, **kwargs)
 
     def attend(self, q, input_pos):
@@ -219,7 +221,8 @@ class KVCache(nn.Module):
             k_val.reshape(-1, self.head_dim) if k_val is not None else e,
             v_val.reshape(-1, self.head_dim) if v_val is not None else e,
             ip, self._state_list(), self._meta(G), out["y"], fill_idx, probs, phases,
-            bool(kwargs.get("is_punc", False)))
+            bool(kwargs.get("is_punc", False)),
+            _lib.FLAG_OVERLAP_PREDECESSOR if kwargs.get("overlap_predecessor") else 0)
         return out["y"].view(1, self.n_heads * G, 1, self.head_dim) if q is not None else None
 
     # ---- prefill fill ---------------------------------------------------------------------

@@ -8,7 +8,17 @@
 #define CC_STR2(x) #x
 #define CC_STR(x) CC_STR2(x)
 
+#include <stdlib.h>
+
 namespace cc {
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("CC_B200_PDL");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
 static thread_local char g_err[512] = "";
 int set_error(int code, const char* msg) {
     strncpy(g_err, msg, sizeof(g_err) - 1);

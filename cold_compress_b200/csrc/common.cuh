@@ -127,6 +127,19 @@ __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its
+// predecessor in the stream is still running.  Everything before pdl_wait() must only touch memory
+// no in-flight predecessor writes (weights, the K/V cache, policy state of this layer);
+// pdl_wait() returns when the predecessor grid has completed and its writes are visible.
+// Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ global memory, gpu scope
 __device__ __forceinline__ int32_t ld_acquire_gpu(const int32_t* p) {
     int32_t v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;

@@ -25,6 +25,7 @@
 #include <math_constants.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/cc_b200.h"
 #include "common.cuh"
@@ -32,7 +33,10 @@
 
 namespace cc {
 
-constexpr int kThreads = 512;
+#ifndef CC_DECODE_THREADS
+#define CC_DECODE_THREADS 256
+#endif
+constexpr int kThreads = CC_DECODE_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxCluster = 16;
 constexpr int kMaxG = 8;
@@ -269,6 +273,10 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         maskb[lr] = (s < L) ? st.mask[(size_t)h * L + s] : 0;
     }
 
+    // Everything above reads only this layer's cache and policy state, which no kernel in flight
+    // writes; q / k_new / v_new come from the projection kernel launched just before this one.
+    pdl_launch_dependents();
+    pdl_wait();
     // query rows of this KV group and the new value slice, in registers
     float q[G][8];
     uint4 vnew8 = make_uint4(0, 0, 0, 0);
@@ -853,7 +861,9 @@ static int make_plan(const CcCacheState* st, bool needs_epoch, LaunchPlan* out) 
     int chs = 6;
     while (chs > 4 && ((L + (1 << chs) - 1) >> chs) < kMaxCluster) --chs;
     const int n_chunks = (L + (1 << chs) - 1) >> chs;
-    for (int C = kMaxCluster; C >= 1; C >>= 1) {
+    int c_max = kMaxCluster;
+    if (const char* e = getenv("CC_B200_MAX_CLUSTER")) c_max = atoi(e) > 0 ? atoi(e) : c_max;  // experiments only
+    for (int C = c_max; C >= 1; C >>= 1) {
         if (C > 1 && (H * C > g_num_sms || C > n_chunks)) continue;
         const int mlc = (n_chunks + C - 1) / C;
         const int stride = ((mlc << chs) + 31) / 32 * 32;
@@ -870,8 +880,10 @@ static int make_plan(const CcCacheState* st, bool needs_epoch, LaunchPlan* out) 
             cfg.attrs = &attr; cfg.numAttrs = 1;
             int max_clusters = 0;
             if (cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
-            // with the cross-head epoch barrier every cluster must be co-resident
-            if (max_clusters < (needs_epoch ? H : 1)) continue;
+            // every cluster of the layer must be co-resident: the epoch barrier needs it for correctness,
+            // and a second wave of clusters would double the step time in any case
+            if (max_clusters < H && C > 1) continue;
+            (void)needs_epoch;
             LaunchPlan p = {fn, C, chs, mlc, ns, stride, lay.total};
             if (g_nplans < 128) g_plans[g_nplans++] = {{D, G, (int)naive, H, L, st->policy}, p};
             *out = p;
@@ -942,10 +954,13 @@ int decode_step_impl(const CcCacheState* st, const CcDecodeArgs* a, cudaStream_t
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = plan.smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = plan.cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr; cfg.numAttrs = 1;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = plan.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl_enabled() && (a->flags & CC_FLAG_OVERLAP_PREDECESSOR)) ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, plan.fn, p);
     if (e != cudaSuccess) return set_cuda_error(e, "cc_decode_step launch");
     return CC_OK;

@@ -73,48 +73,98 @@ __device__ void stage_input(const __nv_bfloat16* __restrict__ x, const __nv_bflo
     __syncthreads();
 }
 
-// dot products of R weight rows (row pointers) with the staged input; all lanes get the sums
-template <int R>
-__device__ __forceinline__ void warp_dots(const __nv_bfloat16* const (&rows)[R], const __nv_bfloat16* xs, int K,
-                                          float (&out)[R]) {
-    const int lane = threadIdx.x & 31;
-    float acc[R];
+// A warp's share of R weight rows over the K-range [k0, k1) (a multiple of 256 long), in two steps so
+// that the weight stream starts before anything else the kernel has to do:
+//   prefetch(): issues the first NV K-steps of every row (NV*R independent 16-byte loads per lane);
+//   finish():   consumes them against the staged input and streams the rest.
+template <int R, int NV>
+struct WarpDots {
+    uint4 w[NV][R];
+    int k, k1;
+    __device__ __forceinline__ void prefetch(const __nv_bfloat16* const (&rows)[R], int k0, int k1_) {
+        const int lane = threadIdx.x & 31;
+        k = k0 + lane * 8;
+        k1 = k1_;
 #pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = 0.f;
-    int k = lane * 8;
-    // two K-steps per iteration: 2*R independent 16-byte loads in flight per lane
-    for (; k + 256 < K; k += 512) {
-        uint4 w0[R], w1[R];
+        for (int u = 0; u < NV; ++u)
 #pragma unroll
-        for (int r = 0; r < R; ++r) { w0[r] = ldg_stream(rows[r] + k); w1[r] = ldg_stream(rows[r] + k + 256); }
-        float x0[8], x1[8];
-        unpack8(*reinterpret_cast<const uint4*>(xs + k), x0);
-        unpack8(*reinterpret_cast<const uint4*>(xs + k + 256), x1);
+            for (int r = 0; r < R; ++r)
+                w[u][r] = (k + u * 256 < k1) ? ldg_stream(rows[r] + k + u * 256) : make_uint4(0, 0, 0, 0);
+    }
+    __device__ __forceinline__ void finish(const __nv_bfloat16* const (&rows)[R], const __nv_bfloat16* xs, float (&out)[R]) {
+        float acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.f;
+        while (true) {
+#pragma unroll
+            for (int u = 0; u < NV; ++u) {
+                if (k + u * 256 < k1) {
+                    float x[8];
+                    unpack8(*reinterpret_cast<const uint4*>(xs + k + u * 256), x);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        float f[8];
+                        unpack8(w[u][r], f);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[r] = fmaf(f[j], x[j], acc[r]);
+                    }
+                }
+            }
+            k += NV * 256;
+            if (k >= k1) break;
+#pragma unroll
+            for (int u = 0; u < NV; ++u)
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (k + u * 256 < k1) w[u][r] = ldg_stream(rows[r] + k + u * 256);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) out[r] = warp_sum(acc[r]);
+    }
+};
+
+// KS warps of a CTA share a row group and split K between them; their partial sums are combined in
+// shared memory in a fixed order (deterministic).  Returns true in the lane that owns the epilogue,
+// with the complete sums in out[].
+template <int R, int KS>
+__device__ __forceinline__ bool combine_split(float (*part)[R], float (&out)[R]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if constexpr (KS == 1) return lane == 0;
+    const int ks = warp % KS;
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) part[warp][r] = out[r];
+    }
+    __syncthreads();
+    if (ks == 0 && lane == 0) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            float f[8];
-            unpack8(w0[r], f);
+            float s = part[warp][r];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[r] = fmaf(f[j], x0[j], acc[r]);
-            unpack8(w1[r], f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[r] = fmaf(f[j], x1[j], acc[r]);
+            for (int j = 1; j < KS; ++j) s += part[warp + j][r];
+            out[r] = s;
         }
     }
-    for (; k < K; k += 256) {
-        float x0[8];
-        unpack8(*reinterpret_cast<const uint4*>(xs + k), x0);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            float f[8];
-            unpack8(ldg_stream(rows[r] + k), f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[r] = fmaf(f[j], x0[j], acc[r]);
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) out[r] = warp_sum(acc[r]);
+    return ks == 0 && lane == 0;
 }
+
+// Skeleton shared by the three kernels: every warp owns row group `base + warp / KS` and the K-slice
+// `warp % KS`.  First pass: weights are requested BEFORE the dependency wait and the input staging.
+#define CC_GEMV_PROLOGUE(R_, NV_, ROWS_OF)                                                          \
+    constexpr int GPB = kGemvWarps / KS;                                                            \
+    const int warp = threadIdx.x >> 5;                                                              \
+    const int klen = p.K / KS, k0 = (warp % KS) * klen;                                             \
+    WarpDots<R_, NV_> wd;                                                                           \
+    int base = blockIdx.x * GPB;                                                                    \
+    {                                                                                               \
+        const int pr = min(base + warp / KS, n_pairs - 1);                                          \
+        const int r0 = 2 * pr;                                                                      \
+        const __nv_bfloat16* rows[R_] = ROWS_OF;                                                    \
+        wd.prefetch(rows, k0, k0 + klen);                                                           \
+    }                                                                                               \
+    pdl_launch_dependents();                                                                        \
+    pdl_wait();                                                                                     \
+    stage_input(p.x, p.norm_w, p.eps, p.K, xs, scratch);
 
 // ---------------------------------------------------------------- attention_norm -> wqkv -> RoPE
 struct QkvParams {
@@ -125,22 +175,28 @@ struct QkvParams {
     int K, n_q_rows, n_kv_rows, head_dim;
 };
 
+template <int KS>
 __global__ void __launch_bounds__(kGemvThreads) rmsnorm_qkv_rope_kernel(const __grid_constant__ QkvParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem_raw);
     __shared__ float scratch[kGemvWarps];
-    stage_input(p.x, p.norm_w, p.eps, p.K, xs, scratch);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_rows = p.n_q_rows + 2 * p.n_kv_rows;
+    __shared__ float part[kGemvWarps][2];
+    const int n_pairs = (p.n_q_rows + 2 * p.n_kv_rows) / 2;
+#define CC_ROWS {p.w + (size_t)r0 * p.K, p.w + (size_t)(r0 + 1) * p.K}
+    CC_GEMV_PROLOGUE(2, 4, CC_ROWS)
     const int pos = p.input_pos[0];
     const int half = p.head_dim / 2;
-    // a warp owns the two rows of a rotary pair
-    for (int pr = blockIdx.x * kGemvWarps + warp; pr < n_rows / 2; pr += gridDim.x * kGemvWarps) {
+    // a row group = the two rows of a rotary pair; loop bound is CTA-uniform (barriers inside)
+    for (; base < n_pairs; base += gridDim.x * GPB) {
+        const int pr = min(base + warp / KS, n_pairs - 1);
+        const bool active = base + warp / KS < n_pairs;
         const int r0 = 2 * pr;
-        const __nv_bfloat16* rows[2] = {p.w + (size_t)r0 * p.K, p.w + (size_t)(r0 + 1) * p.K};
+        const __nv_bfloat16* rows[2] = CC_ROWS;
+        if (base != (int)blockIdx.x * GPB) wd.prefetch(rows, k0, k0 + klen);
         float d[2];
-        warp_dots<2>(rows, xs, p.K, d);
-        if (lane == 0) {
+        wd.finish(rows, xs, d);
+        const bool owner = combine_split<2, KS>(part, d);
+        if (owner && active) {
             float a = d[0], b = d[1];
             if (p.bias) { a += __bfloat162float(p.bias[r0]); b += __bfloat162float(p.bias[r0 + 1]); }
             a = bf16_round(a);  // nn.Linear output is a bf16 tensor
@@ -158,7 +214,9 @@ __global__ void __launch_bounds__(kGemvThreads) rmsnorm_qkv_rope_kernel(const __
                                                                : p.v + (r0 - p.n_q_rows - p.n_kv_rows);
             *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(a, b);
         }
+        if (KS > 1) __syncthreads();  // `part` is reused by the next pass
     }
+#undef CC_ROWS
 }
 
 // ---------------------------------------------------------------- y = [residual +] W x
@@ -169,18 +227,25 @@ struct GemvParams {
     int K, N;
 };
 
+template <int KS>
 __global__ void __launch_bounds__(kGemvThreads) gemv_residual_kernel(const __grid_constant__ GemvParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem_raw);
     __shared__ float scratch[kGemvWarps];
-    stage_input(p.x, p.norm_w, p.eps, p.K, xs, scratch);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int pr = blockIdx.x * kGemvWarps + warp; pr < p.N / 2; pr += gridDim.x * kGemvWarps) {
+    __shared__ float part[kGemvWarps][2];
+    const int n_pairs = p.N / 2;
+#define CC_ROWS {p.w + (size_t)r0 * p.K, p.w + (size_t)(r0 + 1) * p.K}
+    CC_GEMV_PROLOGUE(2, 4, CC_ROWS)
+    for (; base < n_pairs; base += gridDim.x * GPB) {
+        const int pr = min(base + warp / KS, n_pairs - 1);
+        const bool active = base + warp / KS < n_pairs;
         const int r0 = 2 * pr;
-        const __nv_bfloat16* rows[2] = {p.w + (size_t)r0 * p.K, p.w + (size_t)(r0 + 1) * p.K};
+        const __nv_bfloat16* rows[2] = CC_ROWS;
+        if (base != (int)blockIdx.x * GPB) wd.prefetch(rows, k0, k0 + klen);
         float d[2];
-        warp_dots<2>(rows, xs, p.K, d);
-        if (lane == 0) {
+        wd.finish(rows, xs, d);
+        const bool owner = combine_split<2, KS>(part, d);
+        if (owner && active) {
             float a = bf16_round(d[0]), b = bf16_round(d[1]);
             if (p.residual) {  // h = x + attention(...) / out = h + feed_forward(...): bf16 + bf16 -> bf16
                 a = __fadd_rn(__bfloat162float(p.residual[r0]), a);
@@ -188,7 +253,9 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_residual_kernel(const __gri
             }
             *reinterpret_cast<__nv_bfloat162*>(p.out + r0) = __floats2bfloat162_rn(a, b);
         }
+        if (KS > 1) __syncthreads();
     }
+#undef CC_ROWS
 }
 
 // ---------------------------------------------------------------- ffn_norm -> silu(w1 x) * (w3 x)
@@ -199,19 +266,25 @@ struct GateParams {
     int K, N;
 };
 
+template <int KS>
 __global__ void __launch_bounds__(kGemvThreads) rmsnorm_ffn_gate_kernel(const __grid_constant__ GateParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem_raw);
     __shared__ float scratch[kGemvWarps];
-    stage_input(p.x, p.norm_w, p.eps, p.K, xs, scratch);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int pr = blockIdx.x * kGemvWarps + warp; pr < p.N / 2; pr += gridDim.x * kGemvWarps) {
+    __shared__ float part[kGemvWarps][4];
+    const int n_pairs = p.N / 2;
+#define CC_ROWS {p.w1 + (size_t)r0 * p.K, p.w1 + (size_t)(r0 + 1) * p.K, p.w3 + (size_t)r0 * p.K, p.w3 + (size_t)(r0 + 1) * p.K}
+    CC_GEMV_PROLOGUE(4, 2, CC_ROWS)
+    for (; base < n_pairs; base += gridDim.x * GPB) {
+        const int pr = min(base + warp / KS, n_pairs - 1);
+        const bool active = base + warp / KS < n_pairs;
         const int r0 = 2 * pr;
-        const __nv_bfloat16* rows[4] = {p.w1 + (size_t)r0 * p.K, p.w1 + (size_t)(r0 + 1) * p.K,
-                                        p.w3 + (size_t)r0 * p.K, p.w3 + (size_t)(r0 + 1) * p.K};
+        const __nv_bfloat16* rows[4] = CC_ROWS;
+        if (base != (int)blockIdx.x * GPB) wd.prefetch(rows, k0, k0 + klen);
         float d[4];
-        warp_dots<4>(rows, xs, p.K, d);
-        if (lane == 0) {
+        wd.finish(rows, xs, d);
+        const bool owner = combine_split<4, KS>(part, d);
+        if (owner && active) {
             float o[2];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -221,7 +294,9 @@ __global__ void __launch_bounds__(kGemvThreads) rmsnorm_ffn_gate_kernel(const __
             }
             *reinterpret_cast<__nv_bfloat162*>(p.out + r0) = __floats2bfloat162_rn(o[0], o[1]);
         }
+        if (KS > 1) __syncthreads();
     }
+#undef CC_ROWS
 }
 
 // --------------------------------------------------------------------------- host launchers
@@ -237,32 +312,62 @@ static int sm_count() {
     return g_sms;
 }
 
-static int grid_for(int n_pairs) {
-    const int want = (n_pairs + kGemvWarps - 1) / kGemvWarps;
-    const int cap = sm_count() * 4;
-    return want < cap ? want : cap;
+// K-split: the smallest KS in {1,2,4,8} (with K/KS a multiple of 256) that yields at least 4 CTAs per SM,
+// otherwise the largest valid one.  Short-and-wide products (w2, wo) would otherwise leave most SMs
+// with too few loads in flight.
+static int pick_ksplit(int n_pairs, int K) {
+    const int want = sm_count() * 4;
+    int best = 1;
+    for (int ks = 1; ks <= kGemvWarps; ks *= 2) {
+        if (K % (ks * 256)) break;
+        best = ks;
+        if ((long long)n_pairs * ks / kGemvWarps >= want) break;
+    }
+    return best;
 }
 
-template <typename K, typename P>
-static int launch(K kernel, const P& p, int n_pairs, int Kdim, cudaStream_t stream, const char* what) {
+template <typename P, typename K1, typename K2, typename K4, typename K8>
+static int launch_split(K1 k1, K2 k2, K4 k4, K8 k8, const P& p, int n_pairs, int Kdim, cudaStream_t stream, const char* what) {
+    const int ks = pick_ksplit(n_pairs, Kdim);
     const size_t smem = (size_t)Kdim * 2;
-    static thread_local const void* raised[8] = {};
-    if (smem > 48 * 1024) {  // raise the per-function cap once, to the device limit
-        bool done = false;
-        for (int i = 0; i < 8; ++i) done |= raised[i] == (const void*)kernel;
-        if (!done) {
-            int dev = 0, optin = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-            if (e != cudaSuccess) return set_cuda_error(e, what);
-            for (int i = 0; i < 8; ++i)
-                if (!raised[i]) { raised[i] = (const void*)kernel; break; }
+    const int gpb = kGemvWarps / ks;
+    int grid = (n_pairs + gpb - 1) / gpb;
+    const int cap = sm_count() * 8;
+    if (grid > cap) grid = cap;
+    auto go = [&](auto kernel) -> int {
+        static thread_local const void* raised[16] = {};
+        if (smem > 48 * 1024) {  // raise the per-function cap once, to the device limit
+            bool done = false;
+            for (int i = 0; i < 16; ++i) done |= raised[i] == (const void*)kernel;
+            if (!done) {
+                int dev = 0, optin = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+                cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+                if (e != cudaSuccess) return set_cuda_error(e, what);
+                for (int i = 0; i < 16; ++i)
+                    if (!raised[i]) { raised[i] = (const void*)kernel; break; }
+            }
         }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kGemvThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = pdl_enabled() ? 1 : 0;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+        return e == cudaSuccess ? CC_OK : set_cuda_error(e, what);
+    };
+    switch (ks) {
+    case 1: return go(k1);
+    case 2: return go(k2);
+    case 4: return go(k4);
+    default: return go(k8);
     }
-    kernel<<<grid_for(n_pairs), kGemvThreads, smem, stream>>>(p);
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? CC_OK : set_cuda_error(e, what);
 }
 
 int rmsnorm_qkv_rope_impl(const void* x, const void* norm_w, float eps, const void* wqkv, const void* bias,
@@ -274,7 +379,8 @@ int rmsnorm_qkv_rope_impl(const void* x, const void* norm_w, float eps, const vo
                    (const __nv_bfloat16*)bias, (const __nv_bfloat16*)freqs, input_pos,
                    (__nv_bfloat16*)q, (__nv_bfloat16*)k, (__nv_bfloat16*)v, eps, dim,
                    n_q_heads * head_dim, n_kv_heads * head_dim, head_dim};
-    return launch(rmsnorm_qkv_rope_kernel, p, (p.n_q_rows + 2 * p.n_kv_rows) / 2, dim, stream, "cc_rmsnorm_qkv_rope");
+    return launch_split(rmsnorm_qkv_rope_kernel<1>, rmsnorm_qkv_rope_kernel<2>, rmsnorm_qkv_rope_kernel<4>, rmsnorm_qkv_rope_kernel<8>,
+                        p, (p.n_q_rows + 2 * p.n_kv_rows) / 2, dim, stream, "cc_rmsnorm_qkv_rope");
 }
 
 int gemv_residual_impl(const void* x, const void* norm_w, float eps, const void* w, const void* residual, void* out,
@@ -283,7 +389,8 @@ int gemv_residual_impl(const void* x, const void* norm_w, float eps, const void*
     if (K % 256 || N % 2) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_gemv_residual: K must be a multiple of 256, N even");
     GemvParams p = {(const __nv_bfloat16*)x, (const __nv_bfloat16*)norm_w, (const __nv_bfloat16*)w,
                     (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, eps, K, N};
-    return launch(gemv_residual_kernel, p, N / 2, K, stream, "cc_gemv_residual");
+    return launch_split(gemv_residual_kernel<1>, gemv_residual_kernel<2>, gemv_residual_kernel<4>, gemv_residual_kernel<8>,
+                        p, N / 2, K, stream, "cc_gemv_residual");
 }
 
 int rmsnorm_ffn_gate_impl(const void* x, const void* norm_w, float eps, const void* w1, const void* w3, void* out,
@@ -292,7 +399,8 @@ int rmsnorm_ffn_gate_impl(const void* x, const void* norm_w, float eps, const vo
     if (K % 256 || N % 2) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_rmsnorm_ffn_gate: K must be a multiple of 256, N even");
     GateParams p = {(const __nv_bfloat16*)x, (const __nv_bfloat16*)norm_w, (const __nv_bfloat16*)w1,
                     (const __nv_bfloat16*)w3, (__nv_bfloat16*)out, eps, K, N};
-    return launch(rmsnorm_ffn_gate_kernel, p, N / 2, K, stream, "cc_rmsnorm_ffn_gate");
+    return launch_split(rmsnorm_ffn_gate_kernel<1>, rmsnorm_ffn_gate_kernel<2>, rmsnorm_ffn_gate_kernel<4>, rmsnorm_ffn_gate_kernel<8>,
+                        p, N / 2, K, stream, "cc_rmsnorm_ffn_gate");
 }
 
 }  // namespace cc

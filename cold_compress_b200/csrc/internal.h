@@ -5,6 +5,7 @@
 #include "../../include/cc_b200.h"
 
 namespace cc {
+bool pdl_enabled();                                       // programmatic dependent launch (CC_B200_PDL=0 turns it off)
 int set_error(int code, const char* msg);                 // records msg for cc_last_error(), returns code
 int set_cuda_error(cudaError_t e, const char* where);     // CC_ERR_CUDA with the runtime's message
 int decode_step_impl(const CcCacheState* st, const CcDecodeArgs* a, cudaStream_t stream);

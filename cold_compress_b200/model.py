@@ -188,7 +188,8 @@ class Transformer(nn.Module):
                                  att.n_local_heads, att.head_dim)
             y = att.kv_cache.decode_step(b["q"].view(1, att.n_head, 1, att.head_dim),
                                          b["k"].view(1, att.n_local_heads, 1, att.head_dim),
-                                         b["v"].view(1, att.n_local_heads, 1, att.head_dim), ip, input_ids=idx)
+                                         b["v"].view(1, att.n_local_heads, 1, att.head_dim), ip, input_ids=idx,
+                                         overlap_predecessor=True)  # predecessor = this layer's projection
             if att.tp_group is None:
                 ops.gemv_residual(y.view(-1), None, 0.0, att.wo.weight, x, h)
             else:  # row-parallel wo: partial sums, one all-reduce, then the residual (tp.py:156-160)

@@ -22,7 +22,7 @@ META_ORDER = _lib._STATE_INTS
 
 _library.define(
     "decode_step(Tensor q, Tensor k_new, Tensor v_new, Tensor input_pos, Tensor(a!)[] state, int[] meta, "
-    "Tensor(b!) y, Tensor(c!) fill_idx, Tensor(d!) probs, int phases, bool is_punc) -> ()")
+    "Tensor(b!) y, Tensor(c!) fill_idx, Tensor(d!) probs, int phases, bool is_punc, int flags=0) -> ()")
 _library.define("key_norms(Tensor k, Tensor(a!) key_norm) -> ()")
 _library.define(
     "prefill_gather(Tensor(a!)[] state, int[] meta, Tensor k_prompt, Tensor v_prompt, Tensor keep_idx) -> ()")
@@ -67,14 +67,14 @@ def _require_cuda(*tensors):
             raise _lib.CcError("cold_compress_b200 ops need contiguous tensors")
 
 
-def _decode_step(q, k_new, v_new, input_pos, state, meta, y, fill_idx, probs, phases, is_punc):
+def _decode_step(q, k_new, v_new, input_pos, state, meta, y, fill_idx, probs, phases, is_punc, flags=0):
     _require_cuda(q, k_new, v_new, input_pos, y, fill_idx, probs, *state)
     lib = _lib.load()
     st = _c_state(state, meta)
     a = _lib.CcDecodeArgs()
     a.q, a.k_new, a.v_new, a.input_pos = _ptr(q), _ptr(k_new), _ptr(v_new), _ptr(input_pos)
     a.y, a.fill_idx, a.probs = _ptr(y), _ptr(fill_idx), _ptr(probs)
-    a.is_punc, a.phases = int(is_punc), int(phases)
+    a.is_punc, a.phases, a.flags = int(is_punc), int(phases), int(flags)
     _lib.check(lib.cc_decode_step(C.byref(st), C.byref(a), _stream()), "cc_decode_step")
 
 

@@ -54,6 +54,13 @@ extern "C" {
 #define CC_PHASE_SCORE       4  /* KVCache.update_state decode branch (cache.py:690-723)    */
 #define CC_PHASE_ALL         7
 
+/* ---- per-call flags ------------------------------------------------------ */
+#define CC_FLAG_OVERLAP_PREDECESSOR 1  /* the kernel launched just before this one on the stream does
+                                          not write this layer's cache or policy state (it is the q/k/v
+                                          projection, or another layer's step): cc_decode_step may then
+                                          start early (programmatic dependent launch) and fetch K/V and
+                                          policy state while that kernel is still running               */
+
 /* ---- hybrid per-head strategy bits (cache.py:896-950 substrings of the name) */
 #define CC_HYB_FULL          1
 #define CC_HYB_WINDOW        2
@@ -125,6 +132,8 @@ typedef struct CcDecodeArgs {
                                   it is the input.  May be NULL in the fused step.        */
     int32_t        is_punc;    /* hybrid: 1 if the new token id is punctuation (cache.py:969-971) */
     int32_t        phases;     /* CC_PHASE_* mask; CC_PHASE_ALL for the fused step        */
+    int32_t        flags;      /* CC_FLAG_*                                                */
+    int32_t        reserved1;
 } CcDecodeArgs;
 
 /* ABI / build identification. */

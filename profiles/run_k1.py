@@ -54,7 +54,7 @@ else:
         stream.synchronize()
         with torch.cuda.graph(graph, stream=stream):
             for c in caches:
-                c.decode_step(q, k, v, pos)
+                c.decode_step(q, k, v, pos, overlap_predecessor=len(caches) > 1)
         ts = []
         for i in range(a.steps + 3):
             flush.fill_(i & 255)

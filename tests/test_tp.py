@@ -1,0 +1,42 @@
+"""Tensor-parallel tests.  CPU: world_size-2 gloo run of the sharding + all-reduce host logic.
+GPU (needs >= 2 devices, `gpurun --gpus 2`): head-sharded decode reproduces the unsharded run."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _torchrun(n, *args, timeout=600):
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", "29517", str(ROOT / "tests" / "tp_worker.py"), *args]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+
+
+def test_tp_host_logic_gloo_world2():
+    env_cuda = os.environ.get("CUDA_VISIBLE_DEVICES")
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+    try:
+        r = _torchrun(2, "heavy_hitter")
+    finally:
+        if env_cuda is None:
+            os.environ.pop("CUDA_VISIBLE_DEVICES", None)
+        else:
+            os.environ["CUDA_VISIBLE_DEVICES"] = env_cuda
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("tp host logic ok") == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("strategy", ["heavy_hitter", "recent_global"])
+def test_tp_decode_nccl_world2(strategy):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    r = _torchrun(2, strategy)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("tp decode ok") == 2

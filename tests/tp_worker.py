@@ -1,0 +1,112 @@
+"""Worker for the tensor-parallel tests: launched by torchrun with world_size ranks (gloo/CPU or nccl/GPU).
+
+Every rank builds the same seeded small model, shards it with tp.apply_tp, and runs prefill (+ decode on
+GPU).  Rank 0 also runs the unsharded model and checks that the sharded run reproduces it: logits close,
+and -- on GPU -- every local KV head evicts exactly the slots the same head evicts in the unsharded run
+(policies are per head, so head sharding must not change any decision)."""
+import os
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def build(device, strategy, seed=0):
+    from cold_compress_b200.model import ModelArgs, Transformer
+    cfg = ModelArgs(block_size=512, vocab_size=1000, n_layer=2, n_head=8, dim=1024, n_local_heads=4,
+                    intermediate_size=1024, rope_base=500000)
+    torch.manual_seed(seed)
+    model = Transformer(cfg)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if "norm" not in name:
+                p.normal_(0.0, 0.05)
+    return model.to(device=device, dtype=torch.bfloat16).eval()
+
+
+def caches(model, device, strategy, L=64):
+    from cold_compress_b200 import generation_utils as gu
+    from cold_compress_b200.tokenizer import SyntheticTokenizer
+    ck = dict(max_cache_length=[float(L)], cache_bits=None, cache_length_pattern="tile", cache_strategy=[strategy],
+              cache_strategy_pattern="tile", prompt_compression_strategy=[strategy], global_tokens=4, recent_window=10,
+              history_window_size=1, attn_thresholding=False, min_recovery_frac=0.9)
+    gu.setup_caches(model, SyntheticTokenizer(), torch.device(device), 400, ck)
+
+
+def main():
+    strategy = sys.argv[1] if len(sys.argv) > 1 else "heavy_hitter"
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    os.environ.setdefault("LOCAL_WORLD_SIZE", str(world))
+    use_cuda = torch.cuda.is_available() and torch.cuda.device_count() >= world
+    from cold_compress_b200 import tp
+    tp.maybe_init_dist()
+    device = f"cuda:{rank}" if use_cuda else "cpu"
+    from cold_compress_b200 import generation_utils as gu
+
+    full = build(device, strategy)
+    sharded = build(device, strategy)
+    tp.apply_tp(sharded)
+    assert sharded.config.n_local_heads == 4 // world and sharded.layers[0].attention.wqkv.out_features == (8 + 8) * 128 // world
+    torch.manual_seed(11)
+    S = 100
+    prompt = torch.randint(0, 1000, (S,), dtype=torch.int32, device=device)
+    with torch.no_grad():
+        if not use_cuda:
+            # CPU (gloo): the cache kernels are CUDA-only, so exercise the sharded projections + all-reduces
+            # through one block's prefill-style forward without caches
+            x = (torch.randn(1, 16, 1024) * 0.5).to(torch.bfloat16)
+            dist.broadcast(x, 0)
+            fa, fs = full.layers[0], sharded.layers[0]
+            ref = fa.feed_forward(fa.ffn_norm(x))
+            got = fs.feed_forward(fs.ffn_norm(x))
+            assert torch.allclose(ref.float(), got.float(), atol=3e-2, rtol=3e-2), "sharded FFN != full FFN"
+            from cold_compress_b200.model import precompute_freqs_cis
+            fc = precompute_freqs_cis(64, 128, 500000, torch.bfloat16)[:16]
+            qf, kf, vf = fa.attention._project(fa.attention_norm(x), fc)
+            qs, ks, vs = fs.attention._project(fs.attention_norm(x), fc)
+            hq, hk = 8 // world, 4 // world
+            assert torch.equal(qs, qf[:, rank * hq:(rank + 1) * hq]) and torch.equal(ks, kf[:, rank * hk:(rank + 1) * hk])
+            assert torch.equal(vs, vf[:, rank * hk:(rank + 1) * hk])
+            y = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf, is_causal=True, enable_gqa=True)
+            ys = torch.nn.functional.scaled_dot_product_attention(qs, ks, vs, is_causal=True, enable_gqa=True)
+            out_ref = fa.attention.wo(y.transpose(1, 2).reshape(1, 16, -1))
+            out = fs.attention.wo(ys.transpose(1, 2).reshape(1, 16, -1))
+            dist.all_reduce(out)
+            assert torch.allclose(out_ref.float(), out.float(), atol=3e-2, rtol=3e-2), "sharded attention output != full"
+            print(f"rank {rank}: tp host logic ok")
+        else:
+            caches(full, device, strategy)
+            caches(sharded, device, strategy)
+            t_full, _ = gu.prefill(full, prompt.view(1, -1), torch.arange(S, device=device))
+            t_sh, _ = gu.prefill(sharded, prompt.view(1, -1), torch.arange(S, device=device))
+            hk = 4 // world
+            for lf, ls in zip(full.layers, sharded.layers):
+                cf, cs = lf.attention.kv_cache, ls.attention.kv_cache
+                if cf.pos.shape[1] > 1:
+                    assert torch.equal(cs.pos, cf.pos[:, rank * hk:(rank + 1) * hk]), "prefill kept different tokens"
+            pos = torch.tensor([S], dtype=torch.int32, device=device)
+            tok = torch.randint(0, 1000, (1, 1), dtype=torch.int32, device=device)
+            for t in range(6):
+                dist.broadcast(tok, 0)
+                lf = full(tok, pos, is_prefill=False).float()
+                ls = sharded(tok, pos, is_prefill=False).float()
+                err = (lf - ls).abs().max().item()
+                assert err <= 0.03 * lf.abs().max().item() + 0.03, f"step {t}: logits differ by {err}"
+                if t < 2:
+                    for a, b in zip(full.layers, sharded.layers):
+                        fi, si = a.attention.kv_cache._fill_idx, b.attention.kv_cache._fill_idx
+                        assert torch.equal(si, fi[rank * hk:(rank + 1) * hk]), "a local head evicted a different slot"
+                tok = torch.randint(0, 1000, (1, 1), dtype=torch.int32, device=device)
+                pos += 1
+            print(f"rank {rank}: tp decode ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
