@@ -360,12 +360,26 @@ def cpu_decode_token(tok, pos):
     return int(torch.argmax(torch.softmax(logits[0, -1].float(), dim=-1)))
 
 
+def usable_cores() -> int:
+    """Cores this process may actually use: min(affinity mask, cgroup CPU quota, OMP_NUM_THREADS)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = Path("/sys/fs/cgroup/cpu.max").read_text().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    if os.environ.get("OMP_NUM_THREADS", "").isdigit():
+        n = min(n, int(os.environ["OMP_NUM_THREADS"]))
+    return max(1, n)
+
+
 def cpu_reference(sample_seconds=20.0, warmup=1, steps=None):
     """tokens/s of the reference's CPU path (port): whole-model decode on the host cores."""
     from oracle import oracle
     # usable cores = the affinity mask (a container may see 128 logical CPUs but own 32; oversubscribing
     # torch's intra-op pool beyond that collapses its GEMV throughput by 60x)
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = usable_cores()
     torch.set_num_threads(cores)
     cpu_model()
     tok, pos = 17, PROMPT_LEN

@@ -94,6 +94,22 @@ __device__ __forceinline__ void st_cluster_v4f32(uint32_t addr, float4 v) {
                  :: "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// Asynchronous store into a peer CTA's shared memory that also signals the peer's mbarrier with the
+// number of bytes written (st.async ... mbarrier::complete_tx): data and "it has arrived" in one
+// message, without a cluster-wide barrier or a CTA-wide release fence on the sender.
+__device__ __forceinline__ void st_async_u32(uint32_t remote_addr, uint32_t v, uint32_t remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];"
+                 :: "r"(remote_addr), "r"(v), "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void st_async_u64(uint32_t remote_addr, uint64_t v, uint32_t remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u64 [%0], %1, [%2];"
+                 :: "r"(remote_addr), "l"(v), "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void st_async_v4f32(uint32_t remote_addr, float4 v, uint32_t remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                 :: "r"(remote_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_mbar) : "memory");
+}
+
 // ------------------------------------------------------------------ mbarrier + TMA bulk copy
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));

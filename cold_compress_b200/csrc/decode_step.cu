@@ -74,7 +74,7 @@ __host__ __device__ inline SmemLayout make_layout(int D, int G, int chunk_rows, 
     s.ssum = off;  off += kMaxG * 8;
     s.x0 = off;    off += 128;
     s.maskb = off; off += align_up(local_rows, 128);
-    s.bars = off;  off += align_up(2 * n_stages * 8, 128);
+    s.bars = off;  off += align_up((2 * n_stages + 4) * 8, 128);  // K ring, V ring, 4 exchange barriers
     s.misc = off;  off += 512;
     s.total = off;
     return s;
@@ -201,12 +201,24 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     uint8_t* maskb = smem + lay.maskb;
     uint64_t* kbar = reinterpret_cast<uint64_t*>(smem + lay.bars);
     uint64_t* vbar = kbar + NS;
+    uint64_t* xbar = vbar + NS;  // [0] X0 (L2 max), [1] X1, [2] X2, [3] X3: single-use exchange barriers
     float* misc = reinterpret_cast<float*>(smem + lay.misc);
     uint32_t* miscu = reinterpret_cast<uint32_t*>(misc);
     unsigned long long* ssum = reinterpret_cast<unsigned long long*>(smem + lay.ssum);  // [kMaxG] local fixed-point sums
 
     stamp(p, 0);
-    cluster_arrive_relaxed();  // B0: this CTA has started (its shared memory may be written by peers)
+    constexpr int NW = 2 + 2 * G;  // words of an X1 record
+    if (tid == 0) {
+        for (int s = 0; s < 2 * NS + 4; ++s) mbar_init(&kbar[s], 1);
+        mbar_fence_init();
+        // every exchange delivers a known number of bytes into this CTA: arm the barriers right away
+        mbar_expect_tx(&xbar[0], (uint32_t)C * 4);
+        mbar_expect_tx(&xbar[1], (uint32_t)C * NW * 4);
+        mbar_expect_tx(&xbar[2], (uint32_t)C * G * 8);
+        mbar_expect_tx(&xbar[3], (uint32_t)G * D * 4);
+    }
+    // B0: this CTA has started and its exchange barriers exist; peers wait for this before they send
+    cluster_arrive_release();
     bool b0_waited = false;
 
     // ---- hybrid: per-head decision from scalars (every CTA of the cluster computes the same)
@@ -243,8 +255,6 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
 
     // ---- 0. barriers + as many K/V chunks in flight as the ring holds
     if (tid == 0) {
-        for (int s = 0; s < 2 * NS; ++s) mbar_init(&kbar[s], 1);
-        mbar_fence_init();
         fence_proxy_async();
         const int pre = min(NS, nlc_live);
         for (int j = 0; j < pre; ++j) {
@@ -273,23 +283,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         maskb[lr] = (s < L) ? st.mask[(size_t)h * L + s] : 0;
     }
 
-    // Everything above reads only this layer's cache and policy state, which no kernel in flight
-    // writes; q / k_new / v_new come from the projection kernel launched just before this one.
-    pdl_launch_dependents();
-    pdl_wait();
-    // query rows of this KV group and the new value slice, in registers
-    float q[G][8];
-    uint4 vnew8 = make_uint4(0, 0, 0, 0);
-    if (do_attend) {
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const uint4 v = *reinterpret_cast<const uint4*>(
-                reinterpret_cast<const uint16_t*>(p.a.q) + (size_t)(h * G + g) * D + li * 8);
-            unpack8(v, q[g]);
-        }
-        if (do_evict)
-            vnew8 = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.a.v_new) + (size_t)h * D + li * 8);
-    }
+    pdl_launch_dependents();  // the next kernel in the stream may start its own independent prologue
 
     // ---- 1. L2 only: key_norm.max() over every head and slot (cache.py:602) = X0 exchange
     float l2_max = 0.f;
@@ -311,10 +305,9 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             if (tid < C) {
                 float mm = misc[kMiscWarpMax];
                 for (int w = 1; w < kWarps; ++w) mm = fmaxf(mm, misc[kMiscWarpMax + w]);
-                st_cluster_f32(map_to_rank(smem_u32(&x0[rank]), tid), mm);
+                st_async_u32(map_to_rank(smem_u32(&x0[rank]), tid), __float_as_uint(mm), map_to_rank(smem_u32(&xbar[0]), tid));
             }
-            cluster_arrive_release();
-            cluster_wait_acquire();
+            mbar_wait(&xbar[0], 0);
             l2_max = x0[0];
             for (int r = 1; r < C; ++r) l2_max = fmaxf(l2_max, x0[r]);
         }
@@ -403,6 +396,23 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         ckey = warp_min_u64(ckey);
     }
     stamp(p, 2);
+    // Everything above reads only this layer's cache and policy state, which no kernel in flight
+    // writes (CC_FLAG_OVERLAP_PREDECESSOR); q / k_new / v_new come from the projection kernel launched
+    // just before this one: wait for it here, with the K/V tiles already on their way.
+    pdl_wait();
+    // query rows of this KV group and the new value slice, in registers
+    float q[G][8];
+    uint4 vnew8 = make_uint4(0, 0, 0, 0);
+    if (do_attend) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const uint4 v = *reinterpret_cast<const uint4*>(
+                reinterpret_cast<const uint16_t*>(p.a.q) + (size_t)(h * G + g) * D + li * 8);
+            unpack8(v, q[g]);
+        }
+        if (do_evict)
+            vnew8 = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.a.v_new) + (size_t)h * D + li * 8);
+    }
     // local row of this CTA's candidate (it owns the slot by construction)
     int cand_local = -1;
     if (ckey != kNoKey) {
@@ -442,27 +452,36 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             if (j == 0) stamp(p, 3);
             const int rows_c = chunk_rows_valid(j);
             const uint8_t* kbase = kring + stage * chunk_bytes;
-            for (int r0 = warp * RPW; r0 < CH; r0 += kWarps * RPW) {
-                const int r = r0 + sub;
-                const bool valid = r < rows_c;
-                float kf[8];
-                uint4 kv = make_uint4(0, 0, 0, 0);
-                if (valid) kv = *reinterpret_cast<const uint4*>(kbase + r * kRowBytes + li * 16);
-                unpack8(kv, kf);
-                float part[G];
+            // up to 4 row pairs per warp per pass, all fetched before the dependent math (ILP)
+            constexpr int UR = 4;
+            for (int r0 = warp * RPW; r0 < CH; r0 += UR * kWarps * RPW) {
+                uint4 kv[UR];
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) acc = __fmaf_rn(q[g][i], kf[i], acc);
-                    part[g] = acc;
+                for (int u = 0; u < UR; ++u) {
+                    const int r = r0 + u * kWarps * RPW + sub;
+                    kv[u] = (r < rows_c) ? *reinterpret_cast<const uint4*>(kbase + r * kRowBytes + li * 16)
+                                         : make_uint4(0, 0, 0, 0);
                 }
-                int gsel;
-                const float dot = group_reduce_multi<LPR, G>(part, li, &gsel);
-                // naive path rounds q@k^T to bf16, then * scale to bf16 (attention_utils.py:37)
-                const float v = NAIVE ? bf16_round(__fmul_rn(bf16_round(dot), p.scale)) : __fmul_rn(dot, p.scale);
-                const int lr = (j << chs) + r;
-                if (gsel < G && r < CH) lg[gsel * stride + lr] = (valid && maskb[lr]) ? v : -CUDART_INF_F;
+#pragma unroll
+                for (int u = 0; u < UR; ++u) {
+                    const int r = r0 + u * kWarps * RPW + sub;
+                    float kf[8];
+                    unpack8(kv[u], kf);
+                    float part[G];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc = __fmaf_rn(q[g][i], kf[i], acc);
+                        part[g] = acc;
+                    }
+                    int gsel;
+                    const float dot = group_reduce_multi<LPR, G>(part, li, &gsel);
+                    // naive path rounds q@k^T to bf16, then * scale to bf16 (attention_utils.py:37)
+                    const float v = NAIVE ? bf16_round(__fmul_rn(bf16_round(dot), p.scale)) : __fmul_rn(dot, p.scale);
+                    const int lr = (j << chs) + r;
+                    if (gsel < G && r < CH) lg[gsel * stride + lr] = (r < rows_c && maskb[lr]) ? v : -CUDART_INF_F;
+                }
             }
             __syncthreads();
             if (tid == 0 && j + NS < nlc_live) {
@@ -496,20 +515,25 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     }
     __syncthreads();
     if (!b0_waited) cluster_wait_acquire();
-    constexpr int NW = 2 + 2 * G;
     for (int idx = tid; idx < C * NW; idx += kThreads) {
         const int dest = idx / NW, w = idx % NW;
-        st_cluster_u32(map_to_rank(smem_u32(&rec[rank * kRecWords + w]), dest), miscu[kMiscMyRec + w]);
+        st_async_u32(map_to_rank(smem_u32(&rec[rank * kRecWords + w]), dest), miscu[kMiscMyRec + w],
+                     map_to_rank(smem_u32(&xbar[1]), dest));
     }
-    cluster_arrive_release();
-    cluster_wait_acquire();
+    mbar_wait(&xbar[1], 0);
     stamp(p, 5);
 
-    // ---- 6. winner + global max per query head (every warp redundantly: no block barrier needed)
+    // ---- 6. winner + global max per query head (every warp redundantly: no block barrier needed).
+    // Lane l looks at record r = l & 15; the two half-warps split the query heads (even / odd).
+    const int rl = lane & 15, gh = lane >> 4;
     uint64_t wkey = kNoKey;
-    if (lane < C) wkey = (uint64_t)rec[lane * kRecWords] | ((uint64_t)rec[lane * kRecWords + 1] << 32);
+    if (rl < C) wkey = (uint64_t)rec[rl * kRecWords] | ((uint64_t)rec[rl * kRecWords + 1] << 32);
     const bool lane_has_cand = wkey != kNoKey;
-    wkey = warp_min_u64(wkey);
+#pragma unroll
+    for (int d = 8; d >= 1; d >>= 1) {
+        const uint64_t o = __shfl_xor_sync(0xffffffffu, wkey, d);
+        wkey = o < wkey ? o : wkey;
+    }
     const bool has_slot = do_evict && wkey != kNoKey;  // a slot is overwritten this step
     const int widx = has_slot ? (int)(uint32_t)(wkey & 0xffffffffu) : -1;
     const int owner = has_slot ? (widx >> chs) % C : -1;
@@ -519,20 +543,29 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     if (needs_epoch && rank == 0 && tid == 0) red_release_gpu_add(&st.sync_words[0], 1);  // shared reads done
     float gmax[G], newlg[G];
     if (do_attend) {
+        constexpr int GH = (G + 1) / 2;  // query heads per half-warp
+        float part[GH];
+#pragma unroll
+        for (int j = 0; j < GH; ++j) {
+            const int g = 2 * j + gh;
+            float m = -CUDART_INF_F;
+            if (rl < C && g < G) {
+                m = __uint_as_float(rec[rl * kRecWords + 2 + g]);
+                // a candidate that is not overwritten keeps its logit; the overwritten one only if the new
+                // token does not replace it in attention (hybrid drop: slot L-1 stays as it was)
+                if (lane_has_cand && (rl != owner || !has_new))
+                    m = fmaxf(m, __uint_as_float(rec[rl * kRecWords + 2 + G + g]));
+            }
+            part[j] = m;
+        }
+#pragma unroll
+        for (int d = 8; d >= 1; d >>= 1)
+#pragma unroll
+            for (int j = 0; j < GH; ++j) part[j] = fmaxf(part[j], __shfl_xor_sync(0xffffffffu, part[j], d));
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             newlg[g] = has_new ? misc[kMiscNewLg + g] : -CUDART_INF_F;
-            float m = -CUDART_INF_F;
-            if (lane < C) {
-                m = __uint_as_float(rec[lane * kRecWords + 2 + g]);
-                // a candidate that is not overwritten keeps its logit; the overwritten one only if the new
-                // token does not replace it in attention (hybrid drop: slot L-1 stays as it was)
-                if (lane_has_cand && (lane != owner || !has_new))
-                    m = fmaxf(m, __uint_as_float(rec[lane * kRecWords + 2 + G + g]));
-            }
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
-            gmax[g] = fmaxf(m, newlg[g]);
+            gmax[g] = fmaxf(__shfl_sync(0xffffffffu, part[g / 2], (g & 1) * 16), newlg[g]);
         }
     }
     const int patch_row = (i_own && has_new) ? widx_local : -1;  // this row now holds the new token
@@ -562,10 +595,9 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         stamp(p, 7);
         for (int idx = tid; idx < C * G; idx += kThreads) {
             const int dest = idx / G, g = idx % G;
-            st_cluster_u64(map_to_rank(smem_u32(&sums[rank * kMaxG + g]), dest), ssum[g]);
+            st_async_u64(map_to_rank(smem_u32(&sums[rank * kMaxG + g]), dest), ssum[g], map_to_rank(smem_u32(&xbar[2]), dest));
         }
-        cluster_arrive_release();
-        cluster_wait_acquire();
+        mbar_wait(&xbar[2], 0);
         stamp(p, 8);
         // ---- 9a. probabilities (every warp sums the C partial denominators itself)
         float sumf[G];
@@ -643,16 +675,19 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             }
         }
         __syncthreads();
-        const int SL = G * D / C;  // outputs reduced by each CTA of the cluster
-        for (int o = tid; o < G * D; o += kThreads) {
-            float s = red[o];
+        const int SL = G * D / C;  // outputs reduced by each CTA of the cluster (a multiple of 4)
+        for (int o4 = tid; o4 < G * D / 4; o4 += kThreads) {
+            const int o = o4 * 4;
+            float4 s = *reinterpret_cast<const float4*>(&red[o]);
 #pragma unroll
-            for (int w = 1; w < kWarps; ++w) s += red[w * G * D + o];
+            for (int w = 1; w < kWarps; ++w) {
+                const float4 t = *reinterpret_cast<const float4*>(&red[w * G * D + o]);
+                s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+            }
             const int dest = o / SL, off = o % SL;
-            st_cluster_f32(map_to_rank(smem_u32(&yx[rank * SL + off]), dest), s);
+            st_async_v4f32(map_to_rank(smem_u32(&yx[rank * SL + off]), dest), s, map_to_rank(smem_u32(&xbar[3]), dest));
         }
         stamp(p, 11);
-        cluster_arrive_release();
     }
 
     // ======== off the critical path: global state writes, overlapped with the X3 barrier ========
@@ -760,7 +795,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     }
 
     if (do_attend) {
-        cluster_wait_acquire();
+        mbar_wait(&xbar[3], 0);
         stamp(p, 12);
         const int SL = G * D / C;
         __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.a.y) + (size_t)h * G * D;
@@ -882,6 +917,9 @@ static int make_plan(const CcCacheState* st, bool needs_epoch, LaunchPlan* out) 
             if (cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
             // every cluster of the layer must be co-resident: the epoch barrier needs it for correctness,
             // and a second wave of clusters would double the step time in any case
+            if (getenv("CC_B200_DEBUG_PLAN"))
+                fprintf(stderr, "[cc plan] D=%d G=%d policy=%d L=%d: C=%d stages=%d smem=%u max_active_clusters=%d\n", D, G,
+                        st->policy, L, C, ns, lay.total, max_clusters);
             if (max_clusters < H && C > 1) continue;
             (void)needs_epoch;
             LaunchPlan p = {fn, C, chs, mlc, ns, stride, lay.total};
