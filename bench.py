@@ -110,6 +110,9 @@ def build_gpu_model(device, world):
     if world > 1:
         from cold_compress_b200.tp import apply_tp
         apply_tp(model)
+    if os.environ.get("CC_WARM_MB"):  # experiments: MB of w1/w3 rows the cache step pre-loads into L2 (-1 = none)
+        mb = int(os.environ["CC_WARM_MB"])
+        model.warm_l2_ffn_bytes = -1 if mb < 0 else mb << 20
     return model.eval()
 
 

@@ -161,7 +161,8 @@ class KVCache(nn.Module):
     def decode_step(self, q, k_val, v_val, input_pos, **kwargs):
         """ONE kernel: evict -> overwrite -> attend -> pool -> score.  q [1,Hq,1,D]; returns y [1,Hq,1,D].
         overlap_predecessor=True promises that the kernel launched just before on this stream does not
-        write this cache (CC_FLAG_OVERLAP_PREDECESSOR): the step then starts fetching early."""
+        write this cache (CC_FLAG_OVERLAP_PREDECESSOR): the step then starts fetching early.
+        warm_l2=[tensors]: read-only tensors (up to 3) the step pulls into L2 while HBM is idle."""
         return self._launch(_lib.PHASE_ALL, q, k_val, v_val, input_pos, **kwargs)
 
     def attend(self, q, input_pos):
@@ -222,7 +223,8 @@ class KVCache(nn.Module):
             v_val.reshape(-1, self.head_dim) if v_val is not None else e,
             ip, self._state_list(), self._meta(G), out["y"], fill_idx, probs, phases,
             bool(kwargs.get("is_punc", False)),
-            _lib.FLAG_OVERLAP_PREDECESSOR if kwargs.get("overlap_predecessor") else 0)
+            _lib.FLAG_OVERLAP_PREDECESSOR if kwargs.get("overlap_predecessor") else 0,
+            list(kwargs.get("warm_l2", ())))
         return out["y"].view(1, self.n_heads * G, 1, self.head_dim) if q is not None else None
 
     # ---- prefill fill ---------------------------------------------------------------------

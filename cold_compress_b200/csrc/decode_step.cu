@@ -43,7 +43,12 @@ constexpr int kMaxG = 8;
 constexpr int kRecWords = 2 + 2 * kMaxG;  // X1 record: key64, lmax[G], candlogit[G]
 constexpr uint64_t kNoKey = ~0ull;
 
+struct SmemLayout {
+    uint32_t kring, vring, lg, red, yx, rec, sums, ssum, x0, maskb, bars, misc, total;
+};
+
 struct DecodeParams {
+    SmemLayout lay;     // shared-memory carve-up, computed once on the host
     CcCacheState st;
     CcDecodeArgs a;
     int ch_shift;       // log2(rows per chunk)
@@ -51,11 +56,8 @@ struct DecodeParams {
     int n_stages;       // ring depth for K and for V
     int lg_stride;      // floats per query head in the logit/prob array
     float scale;        // (float)(1/sqrt(D))
+    int c_shift;        // log2(cluster size)
     unsigned long long* trace;  // diagnostics: [gridDim.x][16] globaltimer stamps (NULL = off)
-};
-
-struct SmemLayout {
-    uint32_t kring, vring, lg, red, yx, rec, sums, ssum, x0, maskb, bars, misc, total;
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
@@ -169,8 +171,8 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int li = lane % LPR, sub = lane / LPR;
-    const int C = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
-    const int h = blockIdx.x / C;
+    const int csh = p.c_shift, C = 1 << csh, rank = (int)cluster_ctarank();
+    const int h = blockIdx.x >> csh;
     const CcCacheState& st = p.st;
     const int L = st.max_cache_length, H = st.n_kv_heads;
     const int chs = p.ch_shift, CH = 1 << chs;
@@ -185,11 +187,11 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
 
     // chunk-cyclic ownership: local chunk j <-> global chunk rank + j*C; local row lr = j*CH + r
     const int n_chunks_total = (L + CH - 1) >> chs;
-    const int nlc = n_chunks_total > rank ? (n_chunks_total - rank + C - 1) / C : 0;
+    const int nlc = n_chunks_total > rank ? (n_chunks_total - rank + C - 1) >> csh : 0;
     const int local_rows = nlc << chs;
-    auto slot_of = [&](int lr) { return (((lr >> chs) * C + rank) << chs) + (lr & (CH - 1)); };
+    auto slot_of = [&](int lr) { return ((((lr >> chs) << csh) + rank) << chs) + (lr & (CH - 1)); };
 
-    const SmemLayout lay = make_layout(D, G, CH, p.max_local_chunks << chs, NS, stride);
+    const SmemLayout& lay = p.lay;
     uint8_t* kring = smem + lay.kring;
     uint8_t* vring = smem + lay.vring;
     float* lg = reinterpret_cast<float*>(smem + lay.lg);
@@ -246,12 +248,12 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         live_limit = min(L, hyb_cts + ((do_evict && hyb_mode == kHybAppend) ? 1 : 0));
     }
     const int live_chunks_total = (live_limit + CH - 1) >> chs;
-    const int nlc_live = do_attend ? (live_chunks_total > rank ? (live_chunks_total - rank + C - 1) / C : 0) : 0;
+    const int nlc_live = do_attend ? (live_chunks_total > rank ? (live_chunks_total - rank + C - 1) >> csh : 0) : 0;
     const int live_rows = nlc_live << chs;
 
     const uint16_t* kc = reinterpret_cast<const uint16_t*>(st.k_cache) + (size_t)h * L * D;
     const uint16_t* vc = reinterpret_cast<const uint16_t*>(st.v_cache) + (size_t)h * L * D;
-    auto chunk_rows_valid = [&](int j) { return min(CH, L - (((j * C + rank)) << chs)); };
+    auto chunk_rows_valid = [&](int j) { return min(CH, L - ((((j << csh) + rank)) << chs)); };
 
     // ---- 0. barriers + as many K/V chunks in flight as the ring holds
     if (tid == 0) {
@@ -260,12 +262,12 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         for (int j = 0; j < pre; ++j) {
             const uint32_t bytes = chunk_rows_valid(j) * kRowBytes;
             mbar_expect_tx(&kbar[j], bytes);
-            tma_load_1d(kring + j * chunk_bytes, kc + ((size_t)(j * C + rank) << chs) * D, bytes, &kbar[j]);
+            tma_load_1d(kring + j * chunk_bytes, kc + ((size_t)((j << csh) + rank) << chs) * D, bytes, &kbar[j]);
         }
         for (int j = 0; j < pre; ++j) {
             const uint32_t bytes = chunk_rows_valid(j) * kRowBytes;
             mbar_expect_tx(&vbar[j], bytes);
-            tma_load_1d(vring + j * chunk_bytes, vc + ((size_t)(j * C + rank) << chs) * D, bytes, &vbar[j]);
+            tma_load_1d(vring + j * chunk_bytes, vc + ((size_t)((j << csh) + rank) << chs) * D, bytes, &vbar[j]);
         }
     }
     if (tid < kMaxG) ssum[tid] = 0ull;
@@ -383,11 +385,11 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             } else {
                 // append at min(L-1, cts); a dropped token is parked in slot L-1 (cache.py:973-979)
                 const int idx = hyb_mode == kHybAppend ? min(L - 1, hyb_cts) : L - 1;
-                if (tid == 0 && ((idx >> chs) % C) == rank) ckey = (uint64_t)(uint32_t)idx;
+                if (tid == 0 && ((idx >> chs) & (C - 1)) == rank) ckey = (uint64_t)(uint32_t)idx;
             }
         } else {  // CC_POLICY_EXTERNAL: the caller chose the slot
             const int64_t idx = p.a.fill_idx[st.pos_heads == 1 ? 0 : h];
-            if (tid == 0 && idx >= 0 && idx < L && (((int)idx >> chs) % C) == rank) ckey = (uint64_t)(uint32_t)idx;
+            if (tid == 0 && idx >= 0 && idx < L && (((int)idx >> chs) & (C - 1)) == rank) ckey = (uint64_t)(uint32_t)idx;
         }
         ckey = warp_min_u64(ckey);
         if (lane == 0) reinterpret_cast<unsigned long long*>(miscu + kMiscWarpKey)[warp] = ckey;
@@ -396,6 +398,18 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         ckey = warp_min_u64(ckey);
     }
     stamp(p, 2);
+    // L2 warm-up hints: from here on this kernel mostly waits on latencies and HBM is idle; ask the
+    // memory system to stream the next projections' weights into L2 meanwhile (4 KiB per request,
+    // requests dealt round-robin over all CTAs).  Issued after this kernel's own loads.
+    for (int i = 0; i < p.a.n_prefetch; ++i) {
+        const char* base = reinterpret_cast<const char*>(p.a.prefetch[i].ptr);
+        const unsigned long long bytes = p.a.prefetch[i].bytes;
+        const unsigned long long n_req = (bytes + 4095) >> 12;
+        for (unsigned long long c = (unsigned long long)tid * gridDim.x + blockIdx.x; c < n_req; c += (unsigned long long)kThreads * gridDim.x) {
+            const unsigned long long off = c << 12;
+            l2_prefetch_bulk(base + off, (uint32_t)min(4096ull, bytes - off));
+        }
+    }
     // Everything above reads only this layer's cache and policy state, which no kernel in flight
     // writes (CC_FLAG_OVERLAP_PREDECESSOR); q / k_new / v_new come from the projection kernel launched
     // just before this one: wait for it here, with the K/V tiles already on their way.
@@ -417,7 +431,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     int cand_local = -1;
     if (ckey != kNoKey) {
         const int s = (int)(uint32_t)(ckey & 0xffffffffu);
-        cand_local = (((s >> chs) / C) << chs) + (s & (CH - 1));
+        cand_local = (((s >> chs) >> csh) << chs) + (s & (CH - 1));
     }
     // a dropped token does not take part in attention (its slot's mask stays as it was)
     const bool attend_new = do_evict && !(hybrid && hyb_mode == kHybDrop);
@@ -489,7 +503,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
                 const int jn = j + NS;
                 const uint32_t bytes = chunk_rows_valid(jn) * kRowBytes;
                 mbar_expect_tx(&kbar[stage], bytes);
-                tma_load_1d(kring + stage * chunk_bytes, kc + ((size_t)(jn * C + rank) << chs) * D, bytes, &kbar[stage]);
+                tma_load_1d(kring + stage * chunk_bytes, kc + ((size_t)((jn << csh) + rank) << chs) * D, bytes, &kbar[stage]);
             }
         }
         // ---- 4. row max without the local candidate, and the candidate's own logits -> my X1 record
@@ -536,9 +550,9 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     }
     const bool has_slot = do_evict && wkey != kNoKey;  // a slot is overwritten this step
     const int widx = has_slot ? (int)(uint32_t)(wkey & 0xffffffffu) : -1;
-    const int owner = has_slot ? (widx >> chs) % C : -1;
+    const int owner = has_slot ? (widx >> chs) & (C - 1) : -1;
     const bool i_own = has_slot && owner == rank;
-    const int widx_local = has_slot ? (((widx >> chs) / C) << chs) + (widx & (CH - 1)) : -1;
+    const int widx_local = has_slot ? (((widx >> chs) >> csh) << chs) + (widx & (CH - 1)) : -1;
     const bool has_new = has_slot && attend_new;  // ... and the new token attends to itself there
     if (needs_epoch && rank == 0 && tid == 0) red_release_gpu_add(&st.sync_words[0], 1);  // shared reads done
     float gmax[G], newlg[G];
@@ -652,7 +666,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
                     const int jn = j + NS;
                     const uint32_t bytes = chunk_rows_valid(jn) * kRowBytes;
                     mbar_expect_tx(&vbar[stage], bytes);
-                    tma_load_1d(vring + stage * chunk_bytes, vc + ((size_t)(jn * C + rank) << chs) * D, bytes, &vbar[stage]);
+                    tma_load_1d(vring + stage * chunk_bytes, vc + ((size_t)((jn << csh) + rank) << chs) * D, bytes, &vbar[stage]);
                 }
             }
         }
@@ -675,7 +689,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             }
         }
         __syncthreads();
-        const int SL = G * D / C;  // outputs reduced by each CTA of the cluster (a multiple of 4)
+        const int SL = (G * D) >> csh;  // outputs reduced by each CTA of the cluster (a multiple of 4)
         for (int o4 = tid; o4 < G * D / 4; o4 += kThreads) {
             const int o = o4 * 4;
             float4 s = *reinterpret_cast<const float4*>(&red[o]);
@@ -684,7 +698,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
                 const float4 t = *reinterpret_cast<const float4*>(&red[w * G * D + o]);
                 s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
             }
-            const int dest = o / SL, off = o % SL;
+            const int dest = o / SL, off = o - dest * SL;
             st_async_v4f32(map_to_rank(smem_u32(&yx[rank * SL + off]), dest), s, map_to_rank(smem_u32(&xbar[3]), dest));
         }
         stamp(p, 11);
@@ -797,7 +811,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     if (do_attend) {
         mbar_wait(&xbar[3], 0);
         stamp(p, 12);
-        const int SL = G * D / C;
+        const int SL = (G * D) >> csh;
         __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.a.y) + (size_t)h * G * D;
         for (int t = tid; t < SL; t += kThreads) {
             float s = yx[t];
@@ -961,6 +975,10 @@ static int validate(const CcCacheState* st, const CcDecodeArgs* a) {
         if (!st->sync_words) return set_error(CC_ERR_INVALID_ARG, "hybrid needs sync_words");
     }
     if (st->policy == CC_POLICY_L2 && !st->key_norm) return set_error(CC_ERR_INVALID_ARG, "null key_norm");
+    if (a->n_prefetch < 0 || a->n_prefetch > 3) return set_error(CC_ERR_INVALID_ARG, "n_prefetch must be 0..3");
+    for (int i = 0; i < a->n_prefetch; ++i)
+        if (!a->prefetch[i].ptr || ((uintptr_t)a->prefetch[i].ptr & 15) || (a->prefetch[i].bytes & 15))
+            return set_error(CC_ERR_INVALID_ARG, "prefetch ranges must be non-null and 16-byte aligned/sized");
     if ((st->policy == CC_POLICY_RECENT_GLOBAL || st->policy == CC_POLICY_L2) && !st->sync_words)
         return set_error(CC_ERR_INVALID_ARG, "this policy needs sync_words");
     if (st->policy == CC_POLICY_RECENT_GLOBAL && st->global_tokens >= st->max_cache_length)
@@ -986,6 +1004,10 @@ int decode_step_impl(const CcCacheState* st, const CcDecodeArgs* a, cudaStream_t
     p.n_stages = plan.n_stages;
     p.lg_stride = plan.lg_stride;
     p.scale = (float)(1.0 / sqrt((double)st->head_dim));
+    p.lay = make_layout(st->head_dim, st->q_per_kv, 1 << plan.ch_shift, plan.max_local_chunks << plan.ch_shift,
+                        plan.n_stages, plan.lg_stride);
+    p.c_shift = 0;
+    while ((1 << p.c_shift) < plan.cluster) ++p.c_shift;
     p.trace = g_trace;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(st->n_kv_heads * plan.cluster);

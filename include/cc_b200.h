@@ -133,7 +133,11 @@ typedef struct CcDecodeArgs {
     int32_t        is_punc;    /* hybrid: 1 if the new token id is punctuation (cache.py:969-971) */
     int32_t        phases;     /* CC_PHASE_* mask; CC_PHASE_ALL for the fused step        */
     int32_t        flags;      /* CC_FLAG_*                                                */
-    int32_t        reserved1;
+    int32_t        n_prefetch; /* number of valid entries in prefetch[] (0..3)            */
+    /* Optional L2 warm-up: read-only device ranges (16-byte aligned, e.g. the weights of the
+       projections that run right after this step) that the kernel asks the memory system to pull
+       into L2 while it is itself waiting on latencies and HBM is idle.  Pure hint. */
+    struct { const void* ptr; uint64_t bytes; } prefetch[3];
 } CcDecodeArgs;
 
 /* ABI / build identification. */
