@@ -36,7 +36,8 @@ class CcCacheState(C.Structure):
 class CcDecodeArgs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("q", "k_new", "v_new", "input_pos", "y", "fill_idx", "probs")] + [
         ("is_punc", C.c_int32), ("phases", C.c_int32), ("flags", C.c_int32), ("n_prefetch", C.c_int32)] + [
-        (f"prefetch{i}_{f}", t) for i in range(3) for f, t in (("ptr", C.c_void_p), ("bytes", C.c_uint64))]
+        (f"prefetch{i}_{f}", t) for i in range(3) for f, t in (("ptr", C.c_void_p), ("bytes", C.c_uint64))] + [
+        ("is_punc_dev", C.c_void_p)]
 
 
 # every symbol include/cc_b200.h declares: name -> (restype, argtypes)

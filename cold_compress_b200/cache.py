@@ -224,7 +224,7 @@ class KVCache(nn.Module):
             ip, self._state_list(), self._meta(G), out["y"], fill_idx, probs, phases,
             bool(kwargs.get("is_punc", False)),
             _lib.FLAG_OVERLAP_PREDECESSOR if kwargs.get("overlap_predecessor") else 0,
-            list(kwargs.get("warm_l2", ())))
+            list(kwargs.get("warm_l2", ())), kwargs.get("is_punc_dev"))
         return out["y"].view(1, self.n_heads * G, 1, self.head_dim) if q is not None else None
 
     # ---- prefill fill ---------------------------------------------------------------------
@@ -451,8 +451,9 @@ class KVCacheHybrid(KVCacheHeavyHitter):
 
     def _launch(self, phases, q, k_val, v_val, input_pos, probs_in=None, **kwargs):
         if "is_punc" not in kwargs and hasattr(self, "punc_ids") and kwargs.get("input_ids") is not None:
-            kwargs["is_punc"] = bool(torch.isin(kwargs["input_ids"].reshape(-1)[-1:].to(self.punc_ids.device),
-                                                self.punc_ids).item())
+            # device-side flag: no host read, so the step stays capturable in a CUDA graph
+            kwargs["is_punc_dev"] = torch.isin(kwargs["input_ids"].reshape(-1)[-1:].to(self.punc_ids.device),
+                                               self.punc_ids).to(torch.uint8)
         return super()._launch(phases, q, k_val, v_val, input_pos, probs_in=probs_in, **kwargs)
 
     def update_state(self, input_pos, k_val, v_val, is_prefill, attn, **kwargs):

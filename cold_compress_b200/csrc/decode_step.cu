@@ -227,13 +227,14 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     int hyb_mode = kHybAppend, hyb_bits = 0, hyb_cts = 0, hyb_rw = 0;
     int64_t hyb_counter = 0;
     int live_limit = L;  // slots >= live_limit cannot be live: their chunks are never loaded
+    const bool is_punc = hybrid && (p.a.is_punc_dev ? p.a.is_punc_dev[0] != 0 : p.a.is_punc != 0);
     if constexpr (hybrid) {
         hyb_bits = st.hyb_strategy_bits[h];
         hyb_cts = st.cache_cts[h];
         hyb_rw = (hyb_bits & CC_HYB_WINDOW) ? st.hyb_recent_window[h] : 0;
         if (st.attn_counter) hyb_counter = st.attn_counter[0];
         if (do_evict) {
-            if (((hyb_bits & CC_HYB_PUNC) && p.a.is_punc) || (hyb_bits & CC_HYB_FULL)) {
+            if (((hyb_bits & CC_HYB_PUNC) && is_punc) || (hyb_bits & CC_HYB_FULL)) {
                 hyb_mode = kHybAppend;
             } else {
                 int budget = st.global_tokens;
@@ -734,7 +735,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
                 reinterpret_cast<double*>(st.attn_history_num)[(size_t)h * L + widx] = 0.0;  // cache.py:753-763
                 st.attn_history_denom[(size_t)h * L + widx] = 0;
             }
-            if (hybrid && p.a.is_punc && st.punc_mask) st.punc_mask[(size_t)h * L + widx] = 1;  // cache.py:1011-1016
+            if (hybrid && is_punc && st.punc_mask) st.punc_mask[(size_t)h * L + widx] = 1;  // cache.py:1011-1016
             if (needs_epoch) {  // head-constant pos, key_norm, counters are read by every cluster: write after all have read
                 const int32_t target = (gen + 1) * H;
                 while (ld_acquire_gpu(&st.sync_words[0]) - target < 0) {}
@@ -744,7 +745,7 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             if (st.pos_heads != 1 || h == 0) st.pos[(size_t)pos_row * L + widx] = ipos;
             if constexpr (hybrid) {
                 if (hyb_mode == kHybAppend) st.cache_cts[h] = hyb_cts + 1;
-                if (h == 0 && p.a.is_punc && st.num_punc) st.num_punc[0] += 1;
+                if (h == 0 && is_punc && st.num_punc) st.num_punc[0] += 1;
             } else if (h == 0) {
                 st.cache_cts[0] += (pos_old == -1) ? 1 : 0;  // cache.py:330, 356-360
             }

@@ -22,7 +22,7 @@ META_ORDER = _lib._STATE_INTS
 
 _library.define(
     "decode_step(Tensor q, Tensor k_new, Tensor v_new, Tensor input_pos, Tensor(a!)[] state, int[] meta, "
-    "Tensor(b!) y, Tensor(c!) fill_idx, Tensor(d!) probs, int phases, bool is_punc, int flags, Tensor[] warm) -> ()")
+    "Tensor(b!) y, Tensor(c!) fill_idx, Tensor(d!) probs, int phases, bool is_punc, int flags, Tensor[] warm, Tensor? is_punc_dev=None) -> ()")
 _library.define("key_norms(Tensor k, Tensor(a!) key_norm) -> ()")
 _library.define(
     "prefill_gather(Tensor(a!)[] state, int[] meta, Tensor k_prompt, Tensor v_prompt, Tensor keep_idx) -> ()")
@@ -67,7 +67,7 @@ def _require_cuda(*tensors):
             raise _lib.CcError("cold_compress_b200 ops need contiguous tensors")
 
 
-def _decode_step(q, k_new, v_new, input_pos, state, meta, y, fill_idx, probs, phases, is_punc, flags=0, warm=()):
+def _decode_step(q, k_new, v_new, input_pos, state, meta, y, fill_idx, probs, phases, is_punc, flags=0, warm=(), is_punc_dev=None):
     _require_cuda(q, k_new, v_new, input_pos, y, fill_idx, probs, *state)
     lib = _lib.load()
     st = _c_state(state, meta)
@@ -75,6 +75,7 @@ def _decode_step(q, k_new, v_new, input_pos, state, meta, y, fill_idx, probs, ph
     a.q, a.k_new, a.v_new, a.input_pos = _ptr(q), _ptr(k_new), _ptr(v_new), _ptr(input_pos)
     a.y, a.fill_idx, a.probs = _ptr(y), _ptr(fill_idx), _ptr(probs)
     a.is_punc, a.phases, a.flags = int(is_punc), int(phases), int(flags)
+    a.is_punc_dev = None if is_punc_dev is None else is_punc_dev.data_ptr()
     a.n_prefetch = min(3, len(warm))
     for i, t in enumerate(warm[:3]):  # L2 warm-up hints: contiguous read-only tensors (views allowed)
         setattr(a, f"prefetch{i}_ptr", t.data_ptr())

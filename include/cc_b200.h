@@ -138,6 +138,8 @@ typedef struct CcDecodeArgs {
        projections that run right after this step) that the kernel asks the memory system to pull
        into L2 while it is itself waiting on latencies and HBM is idle.  Pure hint. */
     struct { const void* ptr; uint64_t bytes; } prefetch[3];
+    const uint8_t* is_punc_dev; /* hybrid: optional device flag (bool [1]) that overrides is_punc, so the
+                                   step can be captured in a CUDA graph without a host read           */
 } CcDecodeArgs;
 
 /* ABI / build identification. */

@@ -301,6 +301,7 @@ int cc_oracle_decode_step(const CcCacheState* st, const CcDecodeArgs* a) {
     if (H < 1 || G < 1 || L < 1) return fail(CC_ERR_INVALID_ARG, "bad shape");
     int32_t input_pos = a->input_pos[0];
     int phases = a->phases ? a->phases : CC_PHASE_ALL;
+    int is_punc = a->is_punc_dev ? a->is_punc_dev[0] != 0 : a->is_punc != 0;
     int naive = st->attn_mode == CC_ATTN_NAIVE_BF16;
     int64_t idx[256];
     int stored[256], evict[256];
@@ -325,7 +326,7 @@ int cc_oracle_decode_step(const CcCacheState* st, const CcDecodeArgs* a) {
             break;
         case CC_POLICY_HYBRID:
             for (int h = 0; h < H; ++h)
-                idx[h] = hybrid_select(st, h, input_pos, a->is_punc, &evict[h], &stored[h]);
+                idx[h] = hybrid_select(st, h, input_pos, is_punc, &evict[h], &stored[h]);
             break;
         default: return fail(CC_ERR_INVALID_ARG, "bad policy");
         }
@@ -345,7 +346,7 @@ int cc_oracle_decode_step(const CcCacheState* st, const CcDecodeArgs* a) {
             if (st->policy == CC_POLICY_HYBRID) {
                 /* mask only for heads that grew; evicting heads keep mask[idx] == 1; dropped untouched */
                 if (stored[h] && !evict[h]) st->mask[(size_t)h * L + i] = 1;
-                if (a->is_punc && st->punc_mask) st->punc_mask[(size_t)h * L + i] = 1;
+                if (is_punc && st->punc_mask) st->punc_mask[(size_t)h * L + i] = 1;
             } else {
                 st->mask[(size_t)h * L + i] = 1;
             }
@@ -358,7 +359,7 @@ int cc_oracle_decode_step(const CcCacheState* st, const CcDecodeArgs* a) {
         }
         if (st->policy == CC_POLICY_HYBRID) {
             for (int h = 0; h < H; ++h) st->cache_cts[h] += (stored[h] && !evict[h]) ? 1 : 0;
-            if (a->is_punc && st->num_punc) st->num_punc[0] += 1;
+            if (is_punc && st->num_punc) st->num_punc[0] += 1;
         } else {
             st->cache_cts[0] += incr[0]; /* cache_cts += num_insertions[:1] (cache.py:330) */
         }

@@ -81,4 +81,4 @@ def test_abi_exports_every_declared_symbol():
         assert hasattr(lib, name)
     assert lib.cc_abi_version() == _lib.ABI_VERSION and b"sm_100a" in lib.cc_build_info()
     import ctypes as C
-    assert C.sizeof(_lib.CcCacheState) == 12 * 4 + 18 * 8 and C.sizeof(_lib.CcDecodeArgs) == 7 * 8 + 16 + 3 * 16
+    assert C.sizeof(_lib.CcCacheState) == 12 * 4 + 18 * 8 and C.sizeof(_lib.CcDecodeArgs) == 7 * 8 + 16 + 3 * 16 + 8
