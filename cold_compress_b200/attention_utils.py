@@ -41,7 +41,7 @@ def scaled_dot_product_attention(query, key, value, attn_mask=None, dropout_p=0.
 
 
 @torch.no_grad()
-def prefill_attention_stats(q, k, v, obs_len: int = 16, block: int = 512):
+def prefill_attention_stats(q, k, v, obs_len: int = 16, block: int = 512, windows=()):
     """Causal self-attention over a prompt with GQA.
 
     q [1, Hq, S, D], k/v [1, Hkv, S, D] (bf16, post-RoPE).  Returns (y [1, Hq, S, D], PrefillAttnStats).
@@ -57,6 +57,7 @@ def prefill_attention_stats(q, k, v, obs_len: int = 16, block: int = 512):
     y = torch.empty(Hkv, G, S, D, dtype=q.dtype, device=q.device)
     col_sum = torch.zeros(Hkv, S, dtype=torch.float32, device=q.device)
     obs_rows = torch.zeros(Hkv, obs_len, S, dtype=q.dtype, device=q.device)
+    band = {int(w): torch.zeros(Hkv, S, dtype=torch.float32, device=q.device) for w in windows}
     cols = torch.arange(S, device=q.device)
     for i0 in range(0, S, block):
         i1 = min(S, i0 + block)
@@ -68,9 +69,13 @@ def prefill_attention_stats(q, k, v, obs_len: int = 16, block: int = 512):
         y[:, :, i0:i1] = (p @ vv[:, :i1]).view(Hkv, G, B, D)
         pooled = p.view(Hkv, G, B, i1).mean(dim=1)                                       # model.py:413-418
         col_sum[:, :i1] += pooled.float().sum(dim=1)
+        for w, acc in band.items():  # rows i of this block that still see column j inside a window of w
+            inside = (torch.arange(i0, i1, device=q.device).view(-1, 1) - cols[:i1].view(1, -1)) < w
+            acc[:, :i1] += (pooled.float() * inside).sum(dim=1)
         lo = max(i0, S - obs_len)
         if lo < i1:
             obs_rows[:, lo - (S - obs_len): i1 - (S - obs_len), :i1] = pooled[:, lo - i0:, :]
     stats = PrefillAttnStats(col_sum=col_sum.to(q.dtype).unsqueeze(0),
-                             obs_mean=obs_rows.float().mean(dim=1).to(q.dtype).unsqueeze(0), obs_len=obs_len)
+                             obs_mean=obs_rows.float().mean(dim=1).to(q.dtype).unsqueeze(0), obs_len=obs_len,
+                             band_sum=band or None)
     return y.view(1, Hq, S, D), stats

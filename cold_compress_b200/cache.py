@@ -456,10 +456,126 @@ class KVCacheHybrid(KVCacheHeavyHitter):
                                                self.punc_ids).to(torch.uint8)
         return super()._launch(phases, q, k_val, v_val, input_pos, probs_in=probs_in, **kwargs)
 
+    # ---- prefill: head profiling (reference cache.py:1066-1272) --------------------------------------
+    def profiling_windows(self, seq_len):
+        """Window sizes (in tokens) whose band sums the prefill attention must provide."""
+        out = set()
+        for s in self.hybrid_strategies:
+            if "window" in s["strategy"]:
+                out.add(max(1, int(s["recent_window"] * seq_len)))
+        return sorted(out)
+
+    def _special_mask(self, input_ids):
+        ids = input_ids.reshape(-1)
+        m = torch.zeros_like(ids, dtype=torch.bool)
+        for seq in self.special_id_seqs:
+            n = len(seq)
+            if n == 1:
+                m |= ids == seq[0]
+            else:
+                t = torch.tensor(seq, device=ids.device, dtype=ids.dtype)
+                win = ids.unfold(0, n, 1) if ids.numel() >= n else ids.new_zeros((0, n))
+                hit = (win == t).all(dim=1).nonzero().flatten()
+                for k in range(n):
+                    m[hit + k] = True
+        return m
+
+    def _column_masks(self, cum_attn, special, punc, total_len, seq_len):
+        """Per strategy: (column mask [H, S] of tokens kept for every query, window size or 0).
+        Same construction as reference build_masks (cache.py:1066-1136), without the S x S tensors:
+        a strategy's mask is `column mask | causal band of `window` tokens`."""
+        H = cum_attn.shape[0] if cum_attn is not None else self.n_heads
+        dev = self.pos.device
+        cols = torch.arange(seq_len, device=dev)
+        out = []
+        for s in self.hybrid_strategies:
+            name = s["strategy"]
+            col = (cols < self.global_tokens).expand(H, -1).clone()
+            if "special" in name:
+                col |= special.view(1, -1)
+            if "punc" in name:
+                col |= punc.view(1, -1)
+            window = max(1, int(s["recent_window"] * total_len)) if "window" in name else 0
+            if "heavy_hitter" in name:
+                # candidates: tokens the LAST query does not already keep (cache.py:1103)
+                last_row = col[0] | (cols > seq_len - 1 - window) if window else col[0]
+                avail = (~last_row).nonzero().flatten()
+                num_hh = math.ceil(min(s["heavy_hitter_frac"] * total_len, avail.numel()))
+                if num_hh > 0:
+                    top = cum_attn[:, avail].topk(num_hh, dim=1).indices
+                    col.scatter_(1, avail[top], True)
+            if name == "full":
+                col.fill_(True)
+            out.append((col, window))
+        return out
+
+    @torch.no_grad()
+    def profile_and_update(self, input_pos, k_val, v_val, attn, **kwargs):
+        """Choose a strategy per head from the prompt's attention (FastGen), lay the prompt out with the
+        kept tokens first, seed masks / counts / history.  `attn` is a PrefillAttnStats with band sums
+        (or the reference's full [1,H,S,S] map, reduced here).  Deviations from the reference, both
+        documented in DESIGN.md: recovered mass is computed from column and band sums (same value up to
+        bf16 rounding of the reference's row sums), and kept tokens are laid out in ascending position
+        (the reference's order comes from an unstable argsort)."""
+        from .prompt_compression import PrefillAttnStats
+        input_ids = kwargs["input_ids"].reshape(-1)
+        S, H, dev = input_ids.numel(), self.n_heads, self.pos.device
+        assert self.max_cache_length >= S
+        special = self._special_mask(input_ids) if self.requires_special else torch.zeros(S, dtype=torch.bool, device=dev)
+        punc = torch.isin(input_ids, self.punc_ids) if hasattr(self, "punc_ids") else torch.zeros(S, dtype=torch.bool, device=dev)
+        if hasattr(self, "num_special"):
+            self.num_special.fill_(int(special.sum()))
+        if hasattr(self, "num_punc"):
+            self.num_punc.fill_(int(punc.sum()))
+        if not isinstance(attn, PrefillAttnStats):  # full map given: reduce it
+            full = attn[0]
+            wins = self.profiling_windows(S)
+            idx = torch.arange(S, device=dev)
+            band = {w: (full.float() * ((idx.view(-1, 1) - idx.view(1, -1)) < w)).sum(dim=1) for w in wins}
+            attn = PrefillAttnStats(col_sum=full.sum(dim=1).unsqueeze(0), obs_mean=None, obs_len=0, band_sum=band)
+        col_sum = attn.col_sum[0].float()                        # [H, S]
+        cum_attn = (attn.col_sum[0] / (S - input_pos)).to(self.k_cache.dtype)   # cache.py:1158
+        # 1. recovered attention mass of every strategy (cache.py:1165-1173)
+        scores = []
+        for col, window in self._column_masks(cum_attn.float(), special, punc, S, S):
+            mass = (col_sum * col).sum(dim=1)
+            if window:
+                mass = mass + (attn.band_sum[window] * (~col)).sum(dim=1)
+            scores.append(mass / S)                              # mean over the S queries (rows sum to 1)
+        scores = torch.stack(scores)                             # [n_strategies, H]
+        strategies = (scores >= self.min_recovery_frac).int().argmax(dim=0)
+        self.set_head_strategies(strategies.cpu())
+        # 2. tokens each head keeps, with budgets relative to the cache length (cache.py:1177-1185)
+        fill = self._column_masks(cum_attn.float(), special, punc, self.max_cache_length, S)
+        cols = torch.arange(S, device=dev)
+        keep = torch.zeros(H, S, dtype=torch.bool, device=dev)
+        for h in range(H):
+            col, window = fill[int(strategies[h])]
+            keep[h] = col[h] | ((cols > S - 1 - window) if window else False)
+        # 3. kept tokens first (ascending), then the rest; everything is copied, unkept slots are cleared
+        order = torch.sort((~keep).int() * S + cols.view(1, -1), dim=1).indices
+        ex = order.view(1, H, S, 1).expand(-1, -1, -1, self.head_dim)
+        self.k_cache[:, :, :S] = k_val.gather(2, ex)
+        self.v_cache[:, :, :S] = v_val.gather(2, ex)
+        self.pos[:, :, :S] = input_pos.view(1, -1).expand(H, -1).gather(1, order).int()
+        cts = keep.sum(dim=1).int()
+        self.cache_cts.copy_(cts)
+        live = cols.view(1, -1) < cts.view(-1, 1)
+        self.pos[0, :, :S].masked_fill_(~live, -1)
+        self.k_cache[0, :, :S].masked_fill_(~live.unsqueeze(-1), 0)
+        self.v_cache[0, :, :S].masked_fill_(~live.unsqueeze(-1), 0)
+        self.mask[0, :, 0, :S] = live
+        if hasattr(self, "special_mask"):
+            self.special_mask[0, :, :S] = special.view(1, -1).expand(H, -1).gather(1, order)
+        if hasattr(self, "punc_mask"):
+            self.punc_mask[0, :, :S] = punc.view(1, -1).expand(H, -1).gather(1, order)
+        if self.requires_heavy_hitter:
+            self._seed_history(input_pos, cum_attn.gather(1, order).unsqueeze(0))
+            self.resync_history()
+
     def update_state(self, input_pos, k_val, v_val, is_prefill, attn, **kwargs):
         if is_prefill:
-            raise NotImplementedError("hybrid head profiling at prefill (reference cache.py:1066-1272) is not built "
-                                      "yet: inject a profiled state (see tests) or use another strategy")
+            return self.profile_and_update(input_pos, k_val, v_val, attn, **kwargs)
         if self.requires_heavy_hitter:
             super().update_state(input_pos, k_val, v_val, is_prefill, attn, **kwargs)
 

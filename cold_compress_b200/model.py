@@ -207,9 +207,10 @@ class Transformer(nn.Module):
         ops.gemv_residual(x, self.norm.weight, eps, self.output.weight, None, b["logits"])
         return b["logits"].view(1, 1, -1)
 
-    # bytes of the next projections' weights the cache step asks L2 to pre-load while HBM is idle:
-    # all of wo plus the leading rows of w1 / w3 (B200: 126 MB L2, the step lasts ~9 us = ~55 MB of HBM time)
-    warm_l2_ffn_bytes = 10 << 20
+    # Optional L2 warm-up: bytes of w1 / w3 rows (plus all of wo) the cache step asks L2 to pre-load while it
+    # waits on its own latencies (cc_decode_step prefetch hints).  Measured on B200 (profiles/r1_notes.md):
+    # 333 tok/s without, 332 / 331 / 329 / 325 tok/s with wo / +10 / +24 / +40 MB -- no gain, so it is off.
+    warm_l2_ffn_bytes = -1
 
     def _warm_ranges(self, att, ffn):
         if self.warm_l2_ffn_bytes < 0:
@@ -311,12 +312,14 @@ class Attention(nn.Module):
         cache = self.kv_cache
         kwargs = {"input_ids": input_ids}
         if cache.return_attn():
-            y, attn = prefill_attention_stats(q, k, v)
+            windows = cache.profiling_windows(q.shape[2]) if hasattr(cache, "profiling_windows") else ()
+            y, attn = prefill_attention_stats(q, k, v, windows=windows)
         else:
             y, attn = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=True), None
         input_pos, k, v, attn = self.compress_prompt(input_pos, k, v, attn)
         cache.update_kv(input_pos, k, v, True, **kwargs)
-        if isinstance(attn, PrefillAttnStats):  # prompt fit the cache: seed with the column means directly
+        if isinstance(attn, PrefillAttnStats) and not hasattr(cache, "profile_and_update"):
+            # prompt fit the cache: seed with the column means directly
             seq_len = attn.col_sum.shape[-1]
             attn = attn.col_sum / (seq_len - input_pos)
         cache.update_state(input_pos, k, v, True, attn, **kwargs)

@@ -25,6 +25,10 @@ class PrefillAttnStats:
     col_sum: torch.Tensor   # [1, Hkv, S] bf16
     obs_mean: torch.Tensor  # [1, Hkv, S] bf16
     obs_len: int
+    # optional, for hybrid head profiling (cache.py:1066-1187): for each requested window size W,
+    # band_sum[W][h, j] = sum over the W queries i in [j, j+W) of P[h, i, j] (fp32), i.e. the attention a
+    # sliding window of W tokens recovers at column j
+    band_sum: dict = None
 
     @property
     def shape(self):

@@ -84,3 +84,47 @@ def test_ops_refuse_cpu_tensors():
     z = torch.zeros(1, 8, 1, 128, dtype=torch.bfloat16)
     with pytest.raises(_lib.CcError):
         c.decode_step(z, z[:, :2], z[:, :2], torch.zeros(1, dtype=torch.int32))
+
+
+def test_hybrid_end_to_end_prefill_profile_and_graph_decode():
+    """FastGen hybrid: prefill profiles heads (host tensor code), decode runs in the fused kernel with the
+    device-side punctuation flag, eager and CUDA-graph decode agree token for token."""
+    from cold_compress_b200 import generation_utils as gu
+    from cold_compress_b200.model import ModelArgs, Transformer
+    from cold_compress_b200.tokenizer import SyntheticTokenizer
+    strategies = [{"strategy": "special"}, {"strategy": "special_punc"},
+                  {"strategy": "special_punc_heavy_hitter", "heavy_hitter_frac": 0.3},
+                  {"strategy": "special_punc_heavy_hitter_window", "recent_window": 0.3, "heavy_hitter_frac": 0.3},
+                  {"strategy": "full"}]
+
+    def build():
+        cfg = ModelArgs(block_size=512, vocab_size=64, n_layer=2, n_head=8, dim=1024, n_local_heads=2,
+                        intermediate_size=1024, rope_base=500000)
+        torch.manual_seed(4)
+        m = Transformer(cfg)
+        with torch.no_grad():
+            for name, p in m.named_parameters():
+                if "norm" not in name:
+                    p.normal_(0.0, 0.05)
+        m = m.to(device="cuda", dtype=torch.bfloat16).eval()
+        ck = dict(max_cache_length=[1.0], cache_bits=None, cache_length_pattern="tile", cache_strategy=["hybrid"],
+                  cache_strategy_pattern="tile", prompt_compression_strategy=["full"], global_tokens=4,
+                  recent_window=10, history_window_size=1, attn_thresholding=False, min_recovery_frac=0.5,
+                  hybrid_strategies=strategies)
+        gu.setup_caches(m, SyntheticTokenizer(vocab_size=64), torch.device("cuda"), 160, ck)
+        return m
+
+    a, b = build(), build()
+    torch.manual_seed(2)
+    prompt = torch.randint(0, 64, (100,), dtype=torch.int32, device="cuda")
+    prefill, eager = gu.compile_funcs(False)
+    _, graphed = gu.compile_funcs(True)
+    seq_a, _, _ = gu.generate(a, prompt, prefill, eager, max_new_tokens=40)
+    seq_b, _, _ = gu.generate(b, prompt, prefill, graphed, max_new_tokens=40)
+    assert torch.equal(seq_a, seq_b)
+    for la, lb in zip(a.layers, b.layers):
+        ca, cb = la.attention.kv_cache, lb.attention.kv_cache
+        assert torch.equal(ca.cache_cts, cb.cache_cts) and torch.equal(ca.pos, cb.pos)
+        assert int(ca.cache_cts.max()) <= 100 + 40 and int(ca.cache_cts.min()) >= 4
+    stats = a.get_cache_stats(100, 40)
+    assert "compression_ratio_avg" in stats and "avg_strategy_idx_avg" in stats
