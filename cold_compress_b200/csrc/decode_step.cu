@@ -415,56 +415,19 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     // writes (CC_FLAG_OVERLAP_PREDECESSOR); q / k_new / v_new come from the projection kernel launched
     // just before this one: wait for it here, with the K/V tiles already on their way.
     pdl_wait();
-    // Logit-phase lane layout: a cache row is handled by LR = 4*GS lanes.  Lane (gs, c) owns the dot-product
-    // chains c, c+4, (c+8, c+12) of the canonical 8-element-chain tree (so the two outer tree levels are
-    // local adds and only two shuffle levels remain) for the GL query heads gs*GL .. gs*GL+GL-1.
-    constexpr int NCH = LPR / 4;                               // chains per lane: 4 (D=128) or 2 (D=64)
-    constexpr int GS = G <= 2 ? 1 : G <= 4 ? 2 : 4;            // query-head splits per row
-    constexpr int GL = (G + GS - 1) / GS;                      // query heads per lane (<= 2)
-    constexpr int LR = 4 * GS;                                 // lanes per row
-    constexpr int RPI = 32 / LR;                               // rows per warp iteration
-    const int lc = lane & 3, lgs = (lane >> 2) % GS, lrow = lane / LR;
-    float qv[GL][NCH][8];
+    // query rows of this KV group and the new value slice, in registers
+    float q[G][8];
     uint4 vnew8 = make_uint4(0, 0, 0, 0);
     if (do_attend) {
 #pragma unroll
-        for (int gl = 0; gl < GL; ++gl) {
-            const int g = min(lgs * GL + gl, G - 1);
-#pragma unroll
-            for (int m = 0; m < NCH; ++m) {
-                const uint4 v = *reinterpret_cast<const uint4*>(
-                    reinterpret_cast<const uint16_t*>(p.a.q) + (size_t)(h * G + g) * D + (lc + 4 * m) * 8);
-                unpack8(v, qv[gl][m]);
-            }
+        for (int g = 0; g < G; ++g) {
+            const uint4 v = *reinterpret_cast<const uint4*>(
+                reinterpret_cast<const uint16_t*>(p.a.q) + (size_t)(h * G + g) * D + li * 8);
+            unpack8(v, q[g]);
         }
         if (do_evict)
             vnew8 = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.a.v_new) + (size_t)h * D + li * 8);
     }
-    // logits of one row for this lane's query heads: local chains, the two outer tree levels, then a
-    // multi-value butterfly over the 4 chain lanes.  Returns the value and which query head it is.
-    auto row_logit = [&](const uint4 (&kv)[NCH], int* g_out) -> float {
-        float t[GL];
-#pragma unroll
-        for (int gl = 0; gl < GL; ++gl) {
-            float ch[NCH];
-#pragma unroll
-            for (int m = 0; m < NCH; ++m) {
-                float kf[8];
-                unpack8(kv[m], kf);
-                float acc = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc = __fmaf_rn(qv[gl][m][i], kf[i], acc);
-                ch[m] = acc;
-            }
-            // tree levels at chain distance 8 and 4 (D=128) / 4 (D=64): chains c, c+4, c+8, c+12 are local
-            if constexpr (NCH == 4) t[gl] = __fadd_rn(__fadd_rn(ch[0], ch[2]), __fadd_rn(ch[1], ch[3]));
-            else t[gl] = __fadd_rn(ch[0], ch[1]);
-        }
-        int gsel;
-        const float dot = group_reduce_multi<4, GL>(t, lc, &gsel);
-        *g_out = lgs * GL + gsel;
-        return NAIVE ? bf16_round(__fmul_rn(bf16_round(dot), p.scale)) : __fmul_rn(dot, p.scale);
-    };
     // local row of this CTA's candidate (it owns the slot by construction)
     int cand_local = -1;
     if (ckey != kNoKey) {
@@ -477,13 +440,21 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
     // ---- 3. logits over the K ring (canonical dot tree), new-token logits by the last warp
     if (do_attend) {
         if (attend_new && warp == kWarps - 1) {
-            uint4 kv[NCH];
+            float kf[8];
+            const uint4 kv = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.a.k_new) + (size_t)h * D + li * 8);
+            unpack8(kv, kf);
+            float part[G];
 #pragma unroll
-            for (int m = 0; m < NCH; ++m)
-                kv[m] = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.a.k_new) + (size_t)h * D + (lc + 4 * m) * 8);
-            int g;
-            const float v = row_logit(kv, &g);
-            if (lrow == 0 && g < G) misc[kMiscNewLg + g] = v;  // replicated lanes write the same value
+            for (int g = 0; g < G; ++g) {
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc = __fmaf_rn(q[g][i], kf[i], acc);
+                part[g] = acc;
+            }
+            int gsel;
+            const float dot = group_reduce_multi<LPR, G>(part, li, &gsel);
+            const float v = NAIVE ? bf16_round(__fmul_rn(bf16_round(dot), p.scale)) : __fmul_rn(dot, p.scale);
+            if (sub == 0 && gsel < G) misc[kMiscNewLg + gsel] = v;  // replicated lanes write the same value
         }
         // rows of chunks that cannot be live
         for (int lr = live_rows + tid; lr < local_rows; lr += kThreads)
@@ -496,25 +467,35 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             if (j == 0) stamp(p, 3);
             const int rows_c = chunk_rows_valid(j);
             const uint8_t* kbase = kring + stage * chunk_bytes;
-            // each warp takes RPI rows per pass; two passes are fetched before the dependent math (ILP)
-            constexpr int UR = 2;
-            for (int r0 = warp * RPI; r0 < CH; r0 += UR * kWarps * RPI) {
-                uint4 kv[UR][NCH];
+            // up to 4 row pairs per warp per pass, all fetched before the dependent math (ILP)
+            constexpr int UR = 4;
+            for (int r0 = warp * RPW; r0 < CH; r0 += UR * kWarps * RPW) {
+                uint4 kv[UR];
 #pragma unroll
                 for (int u = 0; u < UR; ++u) {
-                    const int r = r0 + u * kWarps * RPI + lrow;
-#pragma unroll
-                    for (int m = 0; m < NCH; ++m)
-                        kv[u][m] = (r < rows_c) ? *reinterpret_cast<const uint4*>(kbase + r * kRowBytes + (lc + 4 * m) * 16)
-                                                : make_uint4(0, 0, 0, 0);
+                    const int r = r0 + u * kWarps * RPW + sub;
+                    kv[u] = (r < rows_c) ? *reinterpret_cast<const uint4*>(kbase + r * kRowBytes + li * 16)
+                                         : make_uint4(0, 0, 0, 0);
                 }
 #pragma unroll
                 for (int u = 0; u < UR; ++u) {
-                    const int r = r0 + u * kWarps * RPI + lrow;
-                    int g;
-                    const float v = row_logit(kv[u], &g);
+                    const int r = r0 + u * kWarps * RPW + sub;
+                    float kf[8];
+                    unpack8(kv[u], kf);
+                    float part[G];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc = __fmaf_rn(q[g][i], kf[i], acc);
+                        part[g] = acc;
+                    }
+                    int gsel;
+                    const float dot = group_reduce_multi<LPR, G>(part, li, &gsel);
+                    // naive path rounds q@k^T to bf16, then * scale to bf16 (attention_utils.py:37)
+                    const float v = NAIVE ? bf16_round(__fmul_rn(bf16_round(dot), p.scale)) : __fmul_rn(dot, p.scale);
                     const int lr = (j << chs) + r;
-                    if (g < G && r < CH) lg[g * stride + lr] = (r < rows_c && maskb[lr]) ? v : -CUDART_INF_F;
+                    if (gsel < G && r < CH) lg[gsel * stride + lr] = (r < rows_c && maskb[lr]) ? v : -CUDART_INF_F;
                 }
             }
             __syncthreads();
