@@ -452,8 +452,9 @@ class KVCacheHybrid(KVCacheHeavyHitter):
     def _launch(self, phases, q, k_val, v_val, input_pos, probs_in=None, **kwargs):
         if "is_punc" not in kwargs and hasattr(self, "punc_ids") and kwargs.get("input_ids") is not None:
             # device-side flag: no host read, so the step stays capturable in a CUDA graph
-            kwargs["is_punc_dev"] = torch.isin(kwargs["input_ids"].reshape(-1)[-1:].to(self.punc_ids.device),
-                                               self.punc_ids).to(torch.uint8)
+            # (plain compare + any: torch.isin is not capturable)
+            tok = kwargs["input_ids"].reshape(-1)[-1:].to(self.punc_ids.dtype)
+            kwargs["is_punc_dev"] = (tok.view(1, 1) == self.punc_ids.view(1, -1)).any().to(torch.uint8).view(1)
         return super()._launch(phases, q, k_val, v_val, input_pos, probs_in=probs_in, **kwargs)
 
     # ---- prefill: head profiling (reference cache.py:1066-1272) --------------------------------------
