@@ -276,8 +276,12 @@ def run_ours(args):
                                if world == 1 and not os.environ.get("CC_BENCH_NCU") else None)
         print(json.dumps(out), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # leave without tearing NCCL down: communicators captured in CUDA graphs make
+        # destroy_process_group() hang; every rank is past its last collective here
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # --------------------------------------------------------------------------- reference arm (host CPU)
