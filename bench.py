@@ -108,8 +108,10 @@ def build_gpu_model(device, world):
             else:
                 p.normal_(0.0, 0.02, generator=gen)
     if world > 1:
-        from cold_compress_b200.tp import apply_tp
+        from cold_compress_b200.tp import apply_tp, enable_fused_exchange
         apply_tp(model)
+        if os.environ.get("CC_TP_NCCL") != "1":  # default: all-reduces fused into the projection kernels over NVLink
+            enable_fused_exchange(model)
     if os.environ.get("CC_WARM_MB"):  # experiments: MB of w1/w3 rows the cache step pre-loads into L2 (-1 = none)
         mb = int(os.environ["CC_WARM_MB"])
         model.warm_l2_ffn_bytes = -1 if mb < 0 else mb << 20
@@ -182,6 +184,7 @@ def run_ours(args):
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout (one JSON line only)
         os.environ.setdefault("LOCAL_WORLD_SIZE", str(world))
         from cold_compress_b200.tp import maybe_init_dist
         maybe_init_dist()
@@ -262,7 +265,8 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{MODEL}-shape random-init bf16, heavy_hitter + SnapKV compression, "
                                f"{CACHE_SLOTS} slots/layer, {PROMPT_LEN}-token synthetic prompt, decode @ 8k ctx",
-                   "global_batch": 1, "seq_len": PROMPT_LEN + MAX_NEW, "parallelism": f"tp{world}" if world > 1 else "none",
+                   "global_batch": 1, "seq_len": PROMPT_LEN + MAX_NEW, "parallelism": (f"tp{world} ({'fused NVLink exchange' if getattr(model, 'tp_link', None) is not None else 'NCCL all-reduce'})"
+                                   if world > 1 else "none"),
                    "l2": "per-step inputs (15 GB of weights + 134 MB of K/V) exceed the 126 MB L2",
                    "prefill_seconds": round(prefill_s, 2)},
         "e2e": {"value": round(args.steps / e2e_s, 2), "unit": "tokens/s", "h2d_bytes_per_step": 8,

@@ -40,6 +40,15 @@ class CcDecodeArgs(C.Structure):
         ("is_punc_dev", C.c_void_p)]
 
 
+class CcTpLink(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("world", "rank", "dim", "n_ops")] + [
+        (n, C.c_void_p) for n in ("peer_buf", "peer_flag", "cta_done", "epoch")]
+
+
+class CcTpArgs(C.Structure):
+    _fields_ = [("link", C.POINTER(CcTpLink)), ("send_op", C.c_int32), ("recv_op", C.c_int32), ("recv_out", C.c_void_p)]
+
+
 # every symbol include/cc_b200.h declares: name -> (restype, argtypes)
 EXPORTS = {
     "cc_abi_version": (C.c_int, []),
@@ -54,11 +63,11 @@ EXPORTS = {
                                     C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "cc_rmsnorm_qkv_rope": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
-                                      C.c_int32, C.c_int32, C.c_void_p]),
+                                      C.c_int32, C.c_int32, C.POINTER(CcTpArgs), C.c_void_p]),
     "cc_gemv_residual": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
-                                   C.c_int32, C.c_int32, C.c_void_p]),
+                                   C.c_int32, C.c_int32, C.POINTER(CcTpArgs), C.c_void_p]),
     "cc_rmsnorm_ffn_gate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
-                                      C.c_int32, C.c_int32, C.c_void_p]),
+                                      C.c_int32, C.c_int32, C.POINTER(CcTpArgs), C.c_void_p]),
 }
 
 _lib = None

@@ -64,19 +64,20 @@ int cc_prefill_gather(const CcCacheState* state, const void* k_prompt, const voi
 
 int cc_rmsnorm_qkv_rope(const void* x, const void* norm_w, float eps, const void* wqkv, const void* bias,
                         const void* freqs_cis, const int32_t* input_pos, void* q, void* k, void* v,
-                        int32_t dim, int32_t n_q_heads, int32_t n_kv_heads, int32_t head_dim, void* stream) {
+                        int32_t dim, int32_t n_q_heads, int32_t n_kv_heads, int32_t head_dim,
+                        const CcTpArgs* tp, void* stream) {
     return cc::rmsnorm_qkv_rope_impl(x, norm_w, eps, wqkv, bias, freqs_cis, input_pos, q, k, v, dim, n_q_heads,
-                                     n_kv_heads, head_dim, (cudaStream_t)stream);
+                                     n_kv_heads, head_dim, tp, (cudaStream_t)stream);
 }
 
 int cc_gemv_residual(const void* x, const void* norm_w, float eps, const void* w, const void* residual,
-                     void* out, int32_t K, int32_t N, void* stream) {
-    return cc::gemv_residual_impl(x, norm_w, eps, w, residual, out, K, N, (cudaStream_t)stream);
+                     void* out, int32_t K, int32_t N, const CcTpArgs* tp, void* stream) {
+    return cc::gemv_residual_impl(x, norm_w, eps, w, residual, out, K, N, tp, (cudaStream_t)stream);
 }
 
 int cc_rmsnorm_ffn_gate(const void* x, const void* norm_w, float eps, const void* w1, const void* w3,
-                        void* out, int32_t K, int32_t N, void* stream) {
-    return cc::rmsnorm_ffn_gate_impl(x, norm_w, eps, w1, w3, out, K, N, (cudaStream_t)stream);
+                        void* out, int32_t K, int32_t N, const CcTpArgs* tp, void* stream) {
+    return cc::rmsnorm_ffn_gate_impl(x, norm_w, eps, w1, w3, out, K, N, tp, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -37,21 +37,91 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// ---------------------------------------------------------------- fused tensor-parallel exchange
+constexpr int kMaxTp = 8;
+struct TpDev {
+    const uint64_t* peer_buf;   // [world] base addresses of the exchange buffers (bf16 [n_ops][world][dim])
+    const uint64_t* peer_flag;  // [world] base addresses of the flag arrays (i32 [n_ops][world])
+    int32_t* cta_done;
+    const int32_t* epoch;
+    __nv_bfloat16* recv_out;
+    int world, rank, dim, send_op, recv_op;
+};
+
+__device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
+    int32_t v; asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// Producer side: a pair of finished output rows goes to slot [send_op][rank] of every rank's buffer.
+__device__ __forceinline__ void tp_send_pair(const TpDev& tp, const uint64_t* peers_s, int r0, __nv_bfloat162 v) {
+    const size_t off = ((size_t)(tp.send_op * tp.world + tp.rank) * tp.dim + r0) * 2;
+    for (int p = 0; p < tp.world; ++p) *reinterpret_cast<__nv_bfloat162*>(peers_s[p] + off) = v;
+}
+
+// Producer side, end of kernel: the last CTA to finish publishes the epoch in every rank's flag array.
+__device__ __forceinline__ void tp_send_done(const TpDev& tp) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();  // this CTA's peer stores are visible system-wide
+        const int prev = atomicAdd(&tp.cta_done[tp.send_op], 1);
+        if (prev == (int)gridDim.x - 1) {
+            tp.cta_done[tp.send_op] = 0;
+            __threadfence_system();
+            const int32_t ep = *reinterpret_cast<const volatile int32_t*>(tp.epoch);
+            for (int p = 0; p < tp.world; ++p)
+                st_release_sys(reinterpret_cast<int32_t*>(tp.peer_flag[p]) + tp.send_op * tp.world + tp.rank, ep);
+        }
+    }
+}
+
 // x (bf16 [K]) -> shared memory as bf16, optionally RMS-normalised the way the reference's RMSNorm
 // does it: bf16(bf16(float(x) * rsqrt(mean(x^2) + eps)) * weight)   (model.py:452-457)
 __device__ void stage_input(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ norm_w,
-                            float eps, int K, __nv_bfloat16* xs, float* scratch) {
+                            float eps, int K, __nv_bfloat16* xs, float* scratch, const TpDev& tp) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (norm_w == nullptr) {
+    if (tp.recv_op >= 0) {
+        // consumer of a fused all-reduce: wait for every rank's partial vector of this op, then
+        // x = bf16(residual + bf16(sum of the partials))   (tp.py:156-160 + model.py:317 / 326)
+        const int32_t ep = *reinterpret_cast<const volatile int32_t*>(tp.epoch);
+        if (tid < tp.world) {
+            const int32_t* f = reinterpret_cast<const int32_t*>(tp.peer_flag[tp.rank]) + tp.recv_op * tp.world + tid;
+            while (ld_acquire_sys(f) != ep) {}
+        }
+        __syncthreads();
+        const __nv_bfloat16* recv = reinterpret_cast<const __nv_bfloat16*>(tp.peer_buf[tp.rank]) +
+                                    (size_t)tp.recv_op * tp.world * tp.dim;
+        for (int i = tid * 8; i < K; i += kGemvThreads * 8) {
+            float acc[8], f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+            for (int r = 0; r < tp.world; ++r) {
+                // written by peers over NVLink: read through L2, never through a stale L1 line
+                const uint4 v = __ldcg(reinterpret_cast<const uint4*>(recv + (size_t)r * tp.dim + i));
+                unpack8(v, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
+            unpack8(*reinterpret_cast<const uint4*>(x + i), f);
+            __nv_bfloat16 o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(__fadd_rn(f[j], bf16_round(acc[j])));
+            *reinterpret_cast<uint4*>(xs + i) = *reinterpret_cast<uint4*>(o);
+            if (blockIdx.x == 0 && tp.recv_out) *reinterpret_cast<uint4*>(tp.recv_out + i) = *reinterpret_cast<uint4*>(o);
+        }
+    } else {
         for (int i = tid * 8; i < K; i += kGemvThreads * 8)
             *reinterpret_cast<uint4*>(xs + i) = *reinterpret_cast<const uint4*>(x + i);
-        __syncthreads();
-        return;
     }
+    __syncthreads();
+    if (norm_w == nullptr) return;
+    // RMSNorm in place on the staged vector
     float ss = 0.f;
     for (int i = tid * 8; i < K; i += kGemvThreads * 8) {
         float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(x + i), f);
+        unpack8(*reinterpret_cast<const uint4*>(xs + i), f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
     }
@@ -63,7 +133,7 @@ __device__ void stage_input(const __nv_bfloat16* __restrict__ x, const __nv_bflo
     const float rstd = rsqrtf(tot / (float)K + eps);
     for (int i = tid * 8; i < K; i += kGemvThreads * 8) {
         float f[8], wv[8];
-        unpack8(*reinterpret_cast<const uint4*>(x + i), f);
+        unpack8(*reinterpret_cast<const uint4*>(xs + i), f);
         unpack8(*reinterpret_cast<const uint4*>(norm_w + i), wv);
         __nv_bfloat16 o[8];
 #pragma unroll
@@ -164,7 +234,9 @@ __device__ __forceinline__ bool combine_split(float (*part)[R], float (&out)[R])
     }                                                                                               \
     pdl_launch_dependents();                                                                        \
     pdl_wait();                                                                                     \
-    stage_input(p.x, p.norm_w, p.eps, p.K, xs, scratch);
+    __shared__ uint64_t peers_s[kMaxTp];                                                            \
+    if (p.tp.send_op >= 0 && threadIdx.x < p.tp.world) peers_s[threadIdx.x] = p.tp.peer_buf[threadIdx.x]; \
+    stage_input(p.x, p.norm_w, p.eps, p.K, xs, scratch, p.tp);
 
 // ---------------------------------------------------------------- attention_norm -> wqkv -> RoPE
 struct QkvParams {
@@ -173,6 +245,7 @@ struct QkvParams {
     __nv_bfloat16 *q, *k, *v;
     float eps;
     int K, n_q_rows, n_kv_rows, head_dim;
+    TpDev tp;
 };
 
 template <int KS>
@@ -225,6 +298,7 @@ struct GemvParams {
     __nv_bfloat16* out;
     float eps;
     int K, N;
+    TpDev tp;
 };
 
 template <int KS>
@@ -251,10 +325,12 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_residual_kernel(const __gri
                 a = __fadd_rn(__bfloat162float(p.residual[r0]), a);
                 b = __fadd_rn(__bfloat162float(p.residual[r0 + 1]), b);
             }
-            *reinterpret_cast<__nv_bfloat162*>(p.out + r0) = __floats2bfloat162_rn(a, b);
+            if (p.tp.send_op >= 0) tp_send_pair(p.tp, peers_s, r0, __floats2bfloat162_rn(a, b));
+            else *reinterpret_cast<__nv_bfloat162*>(p.out + r0) = __floats2bfloat162_rn(a, b);
         }
         if (KS > 1) __syncthreads();
     }
+    if (p.tp.send_op >= 0) tp_send_done(p.tp);
 #undef CC_ROWS
 }
 
@@ -264,6 +340,7 @@ struct GateParams {
     __nv_bfloat16* out;
     float eps;
     int K, N;
+    TpDev tp;
 };
 
 template <int KS>
@@ -300,6 +377,23 @@ __global__ void __launch_bounds__(kGemvThreads) rmsnorm_ffn_gate_kernel(const __
 }
 
 // --------------------------------------------------------------------------- host launchers
+
+static int fill_tp(const CcTpArgs* tp, int K, TpDev* out, const char* what) {
+    TpDev d = {};
+    d.send_op = d.recv_op = -1;
+    if (tp && tp->link && (tp->send_op >= 0 || tp->recv_op >= 0)) {
+        const CcTpLink* l = tp->link;
+        if (l->world < 2 || l->world > kMaxTp || l->rank < 0 || l->rank >= l->world || !l->peer_buf || !l->peer_flag ||
+            !l->cta_done || !l->epoch || tp->send_op >= l->n_ops || tp->recv_op >= l->n_ops)
+            return set_error(CC_ERR_INVALID_ARG, what);
+        if (tp->recv_op >= 0 && l->dim != K) return set_error(CC_ERR_INVALID_ARG, "tensor-parallel receive: dim must equal K");
+        d.peer_buf = l->peer_buf; d.peer_flag = l->peer_flag; d.cta_done = l->cta_done; d.epoch = l->epoch;
+        d.recv_out = (__nv_bfloat16*)tp->recv_out;
+        d.world = l->world; d.rank = l->rank; d.dim = l->dim; d.send_op = tp->send_op; d.recv_op = tp->recv_op;
+    }
+    *out = d;
+    return CC_OK;
+}
 
 static int g_sms = 0;
 static int sm_count() {
@@ -372,33 +466,39 @@ static int launch_split(K1 k1, K2 k2, K4 k4, K8 k8, const P& p, int n_pairs, int
 
 int rmsnorm_qkv_rope_impl(const void* x, const void* norm_w, float eps, const void* wqkv, const void* bias,
                           const void* freqs, const int32_t* input_pos, void* q, void* k, void* v, int dim,
-                          int n_q_heads, int n_kv_heads, int head_dim, cudaStream_t stream) {
+                          int n_q_heads, int n_kv_heads, int head_dim, const CcTpArgs* tp, cudaStream_t stream) {
     if (!x || !wqkv || !freqs || !input_pos || !q || !k || !v) return set_error(CC_ERR_INVALID_ARG, "cc_rmsnorm_qkv_rope: null argument");
     if (dim % 256 || head_dim % 2) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_rmsnorm_qkv_rope: dim must be a multiple of 256");
     QkvParams p = {(const __nv_bfloat16*)x, (const __nv_bfloat16*)norm_w, (const __nv_bfloat16*)wqkv,
                    (const __nv_bfloat16*)bias, (const __nv_bfloat16*)freqs, input_pos,
                    (__nv_bfloat16*)q, (__nv_bfloat16*)k, (__nv_bfloat16*)v, eps, dim,
-                   n_q_heads * head_dim, n_kv_heads * head_dim, head_dim};
+                   n_q_heads * head_dim, n_kv_heads * head_dim, head_dim, {}};
+    if (int rc = fill_tp(tp, dim, &p.tp, "cc_rmsnorm_qkv_rope: bad tensor-parallel link")) return rc;
+    if (p.tp.send_op >= 0) return set_error(CC_ERR_INVALID_ARG, "cc_rmsnorm_qkv_rope cannot be an all-reduce producer");
     return launch_split(rmsnorm_qkv_rope_kernel<1>, rmsnorm_qkv_rope_kernel<2>, rmsnorm_qkv_rope_kernel<4>, rmsnorm_qkv_rope_kernel<8>,
                         p, (p.n_q_rows + 2 * p.n_kv_rows) / 2, dim, stream, "cc_rmsnorm_qkv_rope");
 }
 
 int gemv_residual_impl(const void* x, const void* norm_w, float eps, const void* w, const void* residual, void* out,
-                       int K, int N, cudaStream_t stream) {
-    if (!x || !w || !out) return set_error(CC_ERR_INVALID_ARG, "cc_gemv_residual: null argument");
+                       int K, int N, const CcTpArgs* tp, cudaStream_t stream) {
+    if (!x || !w || (!out && !(tp && tp->send_op >= 0))) return set_error(CC_ERR_INVALID_ARG, "cc_gemv_residual: null argument");
     if (K % 256 || N % 2) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_gemv_residual: K must be a multiple of 256, N even");
     GemvParams p = {(const __nv_bfloat16*)x, (const __nv_bfloat16*)norm_w, (const __nv_bfloat16*)w,
-                    (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, eps, K, N};
+                    (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, eps, K, N, {}};
+    if (int rc = fill_tp(tp, K, &p.tp, "cc_gemv_residual: bad tensor-parallel link")) return rc;
+    if (p.tp.send_op >= 0 && (p.tp.dim != N || residual)) return set_error(CC_ERR_INVALID_ARG, "cc_gemv_residual: a producer writes dim rows and takes no residual");
     return launch_split(gemv_residual_kernel<1>, gemv_residual_kernel<2>, gemv_residual_kernel<4>, gemv_residual_kernel<8>,
                         p, N / 2, K, stream, "cc_gemv_residual");
 }
 
 int rmsnorm_ffn_gate_impl(const void* x, const void* norm_w, float eps, const void* w1, const void* w3, void* out,
-                          int K, int N, cudaStream_t stream) {
+                          int K, int N, const CcTpArgs* tp, cudaStream_t stream) {
     if (!x || !w1 || !w3 || !out) return set_error(CC_ERR_INVALID_ARG, "cc_rmsnorm_ffn_gate: null argument");
     if (K % 256 || N % 2) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_rmsnorm_ffn_gate: K must be a multiple of 256, N even");
     GateParams p = {(const __nv_bfloat16*)x, (const __nv_bfloat16*)norm_w, (const __nv_bfloat16*)w1,
-                    (const __nv_bfloat16*)w3, (__nv_bfloat16*)out, eps, K, N};
+                    (const __nv_bfloat16*)w3, (__nv_bfloat16*)out, eps, K, N, {}};
+    if (int rc = fill_tp(tp, K, &p.tp, "cc_rmsnorm_ffn_gate: bad tensor-parallel link")) return rc;
+    if (p.tp.send_op >= 0) return set_error(CC_ERR_INVALID_ARG, "cc_rmsnorm_ffn_gate cannot be an all-reduce producer");
     return launch_split(rmsnorm_ffn_gate_kernel<1>, rmsnorm_ffn_gate_kernel<2>, rmsnorm_ffn_gate_kernel<4>, rmsnorm_ffn_gate_kernel<8>,
                         p, N / 2, K, stream, "cc_rmsnorm_ffn_gate");
 }

@@ -17,9 +17,9 @@ int prefill_gather_impl(const CcCacheState* st, const void* k_prompt, const void
                         cudaStream_t stream);
 int rmsnorm_qkv_rope_impl(const void* x, const void* norm_w, float eps, const void* wqkv, const void* bias,
                           const void* freqs, const int32_t* input_pos, void* q, void* k, void* v, int dim,
-                          int n_q_heads, int n_kv_heads, int head_dim, cudaStream_t stream);
+                          int n_q_heads, int n_kv_heads, int head_dim, const CcTpArgs* tp, cudaStream_t stream);
 int gemv_residual_impl(const void* x, const void* norm_w, float eps, const void* w, const void* residual, void* out,
-                       int K, int N, cudaStream_t stream);
+                       int K, int N, const CcTpArgs* tp, cudaStream_t stream);
 int rmsnorm_ffn_gate_impl(const void* x, const void* norm_w, float eps, const void* w1, const void* w3, void* out,
-                          int K, int N, cudaStream_t stream);
+                          int K, int N, const CcTpArgs* tp, cudaStream_t stream);
 }  // namespace cc

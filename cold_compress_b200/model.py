@@ -112,6 +112,7 @@ class Transformer(nn.Module):
         # around the cache kernel (used by the A/B tests)
         self.fused_decode = True
         self._bufs = None
+        self.tp_link = None  # tp.enable_fused_exchange: all-reduces fused into the projection kernels
 
     def setup_caches(self, **kwargs):
         """Per layer: cache + prompt compressor from the strategy names (reference model.py:191-233)."""
@@ -181,30 +182,64 @@ class Transformer(nn.Module):
         eps = self.norm.eps
         b["x"].copy_(self.tok_embeddings(idx).view(-1))
         x, h = b["x"], b["h"]
+        link = self.tp_link
+        no_tp = ([], [], None)
+        if link is not None:
+            return self._decode_fused_tp(idx, ip, b, link)
         for layer in self.layers:
             att, ffn = layer.attention, layer.feed_forward
             ops.rmsnorm_qkv_rope(x, layer.attention_norm.weight, layer.attention_norm.eps, att.wqkv.weight,
                                  att.wqkv.bias, self.freqs_cis, ip, b["q"], b["k"], b["v"], att.n_head,
-                                 att.n_local_heads, att.head_dim)
+                                 att.n_local_heads, att.head_dim, *no_tp)
             y = att.kv_cache.decode_step(b["q"].view(1, att.n_head, 1, att.head_dim),
                                          b["k"].view(1, att.n_local_heads, 1, att.head_dim),
                                          b["v"].view(1, att.n_local_heads, 1, att.head_dim), ip, input_ids=idx,
                                          overlap_predecessor=True,  # predecessor = this layer's projection
                                          warm_l2=self._warm_ranges(att, ffn))
             if att.tp_group is None:
-                ops.gemv_residual(y.view(-1), None, 0.0, att.wo.weight, x, h)
+                ops.gemv_residual(y.view(-1), None, 0.0, att.wo.weight, x, h, *no_tp)
             else:  # row-parallel wo: partial sums, one all-reduce, then the residual (tp.py:156-160)
-                ops.gemv_residual(y.view(-1), None, 0.0, att.wo.weight, None, b["part"])
+                ops.gemv_residual(y.view(-1), None, 0.0, att.wo.weight, None, b["part"], *no_tp)
                 torch.distributed.all_reduce(b["part"], group=att.tp_group)
                 torch.add(x, b["part"], out=h)
-            ops.rmsnorm_ffn_gate(h, layer.ffn_norm.weight, layer.ffn_norm.eps, ffn.w1.weight, ffn.w3.weight, b["gate"])
+            ops.rmsnorm_ffn_gate(h, layer.ffn_norm.weight, layer.ffn_norm.eps, ffn.w1.weight, ffn.w3.weight,
+                                 b["gate"], *no_tp)
             if ffn.tp_group is None:
-                ops.gemv_residual(b["gate"], None, 0.0, ffn.w2.weight, h, x)
+                ops.gemv_residual(b["gate"], None, 0.0, ffn.w2.weight, h, x, *no_tp)
             else:
-                ops.gemv_residual(b["gate"], None, 0.0, ffn.w2.weight, None, b["part"])
+                ops.gemv_residual(b["gate"], None, 0.0, ffn.w2.weight, None, b["part"], *no_tp)
                 torch.distributed.all_reduce(b["part"], group=ffn.tp_group)
                 torch.add(h, b["part"], out=x)
-        ops.gemv_residual(x, self.norm.weight, eps, self.output.weight, None, b["logits"])
+        ops.gemv_residual(x, self.norm.weight, eps, self.output.weight, None, b["logits"], *no_tp)
+        return b["logits"].view(1, 1, -1)
+
+    def _decode_fused_tp(self, idx, ip, b, link):
+        """Tensor-parallel decode with the all-reduces fused into the projections: the row-parallel wo / w2
+        kernels write their partial outputs into every rank's exchange buffer over NVLink (op 2l / 2l+1),
+        and the next kernel sums them (+ the residual) in its prologue.  No NCCL call, no extra kernel."""
+        x, h = b["x"], b["h"]
+        lt = link.tensors()
+        prev = -1  # exchange op whose result is this layer's input (the previous layer's w2)
+        for l, layer in enumerate(self.layers):
+            att, ffn = layer.attention, layer.feed_forward
+            # input: x (layer 0) or h_prev + allreduce(w2 partials) -> written to x by CTA 0
+            ops.rmsnorm_qkv_rope(x if prev < 0 else h, layer.attention_norm.weight, layer.attention_norm.eps,
+                                 att.wqkv.weight, att.wqkv.bias, self.freqs_cis, ip, b["q"], b["k"], b["v"],
+                                 att.n_head, att.n_local_heads, att.head_dim,
+                                 lt if prev >= 0 else [], link.meta(recv_op=prev), x if prev >= 0 else None)
+            y = att.kv_cache.decode_step(b["q"].view(1, att.n_head, 1, att.head_dim),
+                                         b["k"].view(1, att.n_local_heads, 1, att.head_dim),
+                                         b["v"].view(1, att.n_local_heads, 1, att.head_dim), ip, input_ids=idx,
+                                         overlap_predecessor=True)
+            ops.gemv_residual(y.view(-1), None, 0.0, att.wo.weight, None, b["part"], lt, link.meta(send_op=2 * l), None)
+            # h = x + allreduce(wo partials), then ffn_norm -> gate
+            ops.rmsnorm_ffn_gate(x, layer.ffn_norm.weight, layer.ffn_norm.eps, ffn.w1.weight, ffn.w3.weight, b["gate"],
+                                 lt, link.meta(recv_op=2 * l), h)
+            ops.gemv_residual(b["gate"], None, 0.0, ffn.w2.weight, None, b["part"], lt, link.meta(send_op=2 * l + 1), None)
+            prev = 2 * l + 1
+        ops.gemv_residual(h, self.norm.weight, self.norm.eps, self.output.weight, None, b["logits"],
+                          lt, link.meta(recv_op=prev), x)
+        link.epoch.add_(1)
         return b["logits"].view(1, 1, -1)
 
     # Optional L2 warm-up: bytes of w1 / w3 rows (plus all of wo) the cache step asks L2 to pre-load while it

@@ -28,9 +28,12 @@ _library.define(
     "prefill_gather(Tensor(a!)[] state, int[] meta, Tensor k_prompt, Tensor v_prompt, Tensor keep_idx) -> ()")
 _library.define(
     "rmsnorm_qkv_rope(Tensor x, Tensor norm_w, float eps, Tensor wqkv, Tensor? bias, Tensor freqs_cis, "
-    "Tensor input_pos, Tensor(a!) q, Tensor(b!) k, Tensor(c!) v, int n_q_heads, int n_kv_heads, int head_dim) -> ()")
-_library.define("gemv_residual(Tensor x, Tensor? norm_w, float eps, Tensor w, Tensor? residual, Tensor(a!) out) -> ()")
-_library.define("rmsnorm_ffn_gate(Tensor x, Tensor norm_w, float eps, Tensor w1, Tensor w3, Tensor(a!) out) -> ()")
+    "Tensor input_pos, Tensor(a!) q, Tensor(b!) k, Tensor(c!) v, int n_q_heads, int n_kv_heads, int head_dim, "
+    "Tensor[] tp_link, int[] tp_meta, Tensor(d!)? recv_out) -> ()")
+_library.define("gemv_residual(Tensor x, Tensor? norm_w, float eps, Tensor w, Tensor? residual, Tensor(a!) out, "
+                "Tensor[] tp_link, int[] tp_meta, Tensor(b!)? recv_out) -> ()")
+_library.define("rmsnorm_ffn_gate(Tensor x, Tensor norm_w, float eps, Tensor w1, Tensor w3, Tensor(a!) out, "
+                "Tensor[] tp_link, int[] tp_meta, Tensor(b!)? recv_out) -> ()")
 
 
 def _ptr(t: torch.Tensor):
@@ -105,24 +108,45 @@ def _optr(t):
     return None if t is None else t.data_ptr()
 
 
-def _rmsnorm_qkv_rope(x, norm_w, eps, wqkv, bias, freqs_cis, input_pos, q, k, v, n_q_heads, n_kv_heads, head_dim):
+def _tp_args(tp_link, tp_meta, recv_out):
+    """tp_link = [peer_buf, peer_flag, cta_done, epoch] device tensors (empty list = no exchange),
+    tp_meta = [world, rank, dim, n_ops, send_op, recv_op]."""
+    if not tp_link:
+        return None, None
+    link = _lib.CcTpLink()
+    link.world, link.rank, link.dim, link.n_ops = (int(v) for v in tp_meta[:4])
+    link.peer_buf, link.peer_flag, link.cta_done, link.epoch = (t.data_ptr() for t in tp_link)
+    args = _lib.CcTpArgs()
+    args.link = C.pointer(link)
+    args.send_op, args.recv_op = int(tp_meta[4]), int(tp_meta[5])
+    args.recv_out = None if recv_out is None else recv_out.data_ptr()
+    return args, link  # keep `link` alive until the call returns
+
+
+def _rmsnorm_qkv_rope(x, norm_w, eps, wqkv, bias, freqs_cis, input_pos, q, k, v, n_q_heads, n_kv_heads, head_dim,
+                      tp_link=(), tp_meta=(), recv_out=None):
     _require_cuda(x, norm_w, wqkv, freqs_cis, input_pos, q, k, v)
+    tp, _keep = _tp_args(tp_link, tp_meta, recv_out)
     _lib.check(_lib.load().cc_rmsnorm_qkv_rope(
         x.data_ptr(), norm_w.data_ptr(), eps, wqkv.data_ptr(), _optr(bias), freqs_cis.data_ptr(), input_pos.data_ptr(),
-        q.data_ptr(), k.data_ptr(), v.data_ptr(), wqkv.shape[1], n_q_heads, n_kv_heads, head_dim, _stream()),
-        "cc_rmsnorm_qkv_rope")
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), wqkv.shape[1], n_q_heads, n_kv_heads, head_dim,
+        None if tp is None else C.byref(tp), _stream()), "cc_rmsnorm_qkv_rope")
 
 
-def _gemv_residual(x, norm_w, eps, w, residual, out):
+def _gemv_residual(x, norm_w, eps, w, residual, out, tp_link=(), tp_meta=(), recv_out=None):
     _require_cuda(x, w, out)
+    tp, _keep = _tp_args(tp_link, tp_meta, recv_out)
     _lib.check(_lib.load().cc_gemv_residual(x.data_ptr(), _optr(norm_w), eps, w.data_ptr(), _optr(residual),
-                                            out.data_ptr(), w.shape[1], w.shape[0], _stream()), "cc_gemv_residual")
+                                            out.data_ptr(), w.shape[1], w.shape[0],
+                                            None if tp is None else C.byref(tp), _stream()), "cc_gemv_residual")
 
 
-def _rmsnorm_ffn_gate(x, norm_w, eps, w1, w3, out):
+def _rmsnorm_ffn_gate(x, norm_w, eps, w1, w3, out, tp_link=(), tp_meta=(), recv_out=None):
     _require_cuda(x, norm_w, w1, w3, out)
+    tp, _keep = _tp_args(tp_link, tp_meta, recv_out)
     _lib.check(_lib.load().cc_rmsnorm_ffn_gate(x.data_ptr(), norm_w.data_ptr(), eps, w1.data_ptr(), w3.data_ptr(),
-                                               out.data_ptr(), w1.shape[1], w1.shape[0], _stream()), "cc_rmsnorm_ffn_gate")
+                                               out.data_ptr(), w1.shape[1], w1.shape[0],
+                                               None if tp is None else C.byref(tp), _stream()), "cc_rmsnorm_ffn_gate")
 
 
 _library.impl("decode_step", _decode_step, "CUDA")

@@ -105,3 +105,43 @@ def apply_tp(model: Transformer, group=None) -> None:
     cfg.n_head //= world
     cfg.dim //= world
     cfg.n_local_heads //= world
+
+
+class FusedExchange:
+    """Peer-mapped (NVLink) buffers for the all-reduce fused into the projection kernels (CcTpLink).
+
+    `torch.distributed._symmetric_memory` is used only to allocate and exchange the mappings; the
+    data path is this repo's kernels (csrc/gemv.cu: tp_send_pair / tp_send_done / stage_input)."""
+
+    def __init__(self, model: Transformer, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = group or dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        assert 2 <= self.world <= 8
+        self.dim = model.output.in_features
+        self.n_ops = 2 * len(model.layers)
+        dev = model.output.weight.device
+        self.buf = symm.empty(self.n_ops * self.world * self.dim, dtype=torch.bfloat16, device=dev)
+        self.flags = symm.empty(self.n_ops * self.world, dtype=torch.int32, device=dev)
+        self.buf.zero_()
+        self.flags.zero_()
+        hb = symm.rendezvous(self.buf, group.group_name)
+        hf = symm.rendezvous(self.flags, group.group_name)
+        torch.cuda.synchronize()
+        dist.barrier(group)
+        self.peer_buf = torch.tensor(list(hb.buffer_ptrs), dtype=torch.int64, device=dev)
+        self.peer_flag = torch.tensor(list(hf.buffer_ptrs), dtype=torch.int64, device=dev)
+        self.cta_done = torch.zeros(self.n_ops, dtype=torch.int32, device=dev)
+        self.epoch = torch.ones(1, dtype=torch.int32, device=dev)
+        self._handles = (hb, hf)
+
+    def tensors(self):
+        return [self.peer_buf, self.peer_flag, self.cta_done, self.epoch]
+
+    def meta(self, send_op=-1, recv_op=-1):
+        return [self.world, self.rank, self.dim, self.n_ops, send_op, recv_op]
+
+
+def enable_fused_exchange(model: Transformer, group=None) -> None:
+    """Switch the fused decode path of a tensor-parallel model from NCCL all-reduces to the in-kernel exchange."""
+    model.tp_link = FusedExchange(model, group)

@@ -181,6 +181,31 @@ int cc_prefill_gather(const CcCacheState* state, const void* k_prompt, const voi
                       int32_t prompt_len, void* stream);
 
 /*
+ * Tensor-parallel exchange fused into the projections (tp.py:134-138, 156-160: the all-reduce of the
+ * row-parallel wo / w2 outputs).  Every rank owns an exchange buffer bf16 [n_ops][world][dim] and a flag
+ * array i32 [n_ops][world] in peer-mapped (NVLink) memory.  A projection called with send_op >= 0 writes
+ * its partial output rows into slot [send_op][rank] of EVERY rank's buffer and, when its last CTA is
+ * done, stores the current epoch into flag [send_op][rank] of every rank.  A projection called with
+ * recv_op >= 0 first waits until all `world` flags of that op equal the epoch, then uses
+ * x = bf16(residual + bf16(sum over ranks of the partials)) as its input (and CTA 0 writes x to recv_out).
+ * The caller increments *epoch once per token after the last kernel.
+ */
+typedef struct CcTpLink {
+    int32_t world, rank, dim, n_ops;
+    const uint64_t* peer_buf;    /* device array [world]: base address of each rank's exchange buffer */
+    const uint64_t* peer_flag;   /* device array [world]: base address of each rank's flag array      */
+    int32_t*        cta_done;    /* local i32 [n_ops], zero-initialised                                */
+    const int32_t*  epoch;       /* local device i32 [1], >= 1                                         */
+} CcTpLink;
+
+typedef struct CcTpArgs {
+    const CcTpLink* link;
+    int32_t send_op;             /* -1: write `out` locally as usual                                   */
+    int32_t recv_op;             /* -1: read `x` as usual; else `x` is the residual stream             */
+    void*   recv_out;            /* bf16 [dim]: the summed input, written by CTA 0 (may be NULL)       */
+} CcTpArgs;
+
+/*
  * The rest of the decode layer (one token): bf16 matrix-vector products with the elementwise
  * work of the layer fused in.  x/out are device vectors, weights are nn.Linear weights [N, K]
  * row-major.  norm_w != NULL applies the reference's RMSNorm (model.py:446-457) to x first.
@@ -189,14 +214,16 @@ int cc_prefill_gather(const CcCacheState* state, const void* k_prompt, const voi
  *   (model.py:376-387, 507-519).  freqs_cis = the precompute_freqs_cis table [max_pos, D/2, 2].
  * cc_gemv_residual:   out = [residual +] W x      (wo: model.py:431,317; w2: 443,326; output head: 290-291)
  * cc_rmsnorm_ffn_gate: out = silu(w1 xn) * (w3 xn), xn = ffn_norm(x)   (model.py:442-443)
+ * tp (may be NULL) fuses the tensor-parallel all-reduce into producer / consumer, see CcTpArgs.
  */
 int cc_rmsnorm_qkv_rope(const void* x, const void* norm_w, float eps, const void* wqkv, const void* bias,
                         const void* freqs_cis, const int32_t* input_pos, void* q, void* k, void* v,
-                        int32_t dim, int32_t n_q_heads, int32_t n_kv_heads, int32_t head_dim, void* stream);
+                        int32_t dim, int32_t n_q_heads, int32_t n_kv_heads, int32_t head_dim,
+                        const CcTpArgs* tp, void* stream);
 int cc_gemv_residual(const void* x, const void* norm_w, float eps, const void* w, const void* residual,
-                     void* out, int32_t K, int32_t N, void* stream);
+                     void* out, int32_t K, int32_t N, const CcTpArgs* tp, void* stream);
 int cc_rmsnorm_ffn_gate(const void* x, const void* norm_w, float eps, const void* w1, const void* w3,
-                        void* out, int32_t K, int32_t N, void* stream);
+                        void* out, int32_t K, int32_t N, const CcTpArgs* tp, void* stream);
 
 #ifdef __cplusplus
 }

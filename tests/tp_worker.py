@@ -40,6 +40,8 @@ def caches(model, device, strategy, L=64):
 
 def main():
     strategy = sys.argv[1] if len(sys.argv) > 1 else "heavy_hitter"
+    fused = strategy.endswith("_fused")  # all-reduces fused into the projection kernels (tp.FusedExchange)
+    strategy = strategy.replace("_fused", "")
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     os.environ.setdefault("LOCAL_WORLD_SIZE", str(world))
     use_cuda = torch.cuda.is_available() and torch.cuda.device_count() >= world
@@ -84,6 +86,8 @@ def main():
         else:
             caches(full, device, strategy)
             caches(sharded, device, strategy)
+            if fused:
+                tp.enable_fused_exchange(sharded)
             t_full, _ = gu.prefill(full, prompt.view(1, -1), torch.arange(S, device=device))
             t_sh, _ = gu.prefill(sharded, prompt.view(1, -1), torch.arange(S, device=device))
             hk = 4 // world
