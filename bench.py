@@ -184,7 +184,7 @@ def run_ours(args):
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout (one JSON line only)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner must not land on stdout (one JSON line)
         os.environ.setdefault("LOCAL_WORLD_SIZE", str(world))
         from cold_compress_b200.tp import maybe_init_dist
         maybe_init_dist()

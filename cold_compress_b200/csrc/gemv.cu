@@ -45,7 +45,7 @@ struct TpDev {
     int32_t* cta_done;
     const int32_t* epoch;
     __nv_bfloat16* recv_out;
-    int world, rank, dim, send_op, recv_op;
+    int world, rank, dim, n_ops, send_op, recv_op;
 };
 
 __device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
@@ -55,25 +55,34 @@ __device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
-// Producer side: a pair of finished output rows goes to slot [send_op][rank] of every rank's buffer.
-__device__ __forceinline__ void tp_send_pair(const TpDev& tp, const uint64_t* peers_s, int r0, __nv_bfloat162 v) {
-    const size_t off = ((size_t)(tp.send_op * tp.world + tp.rank) * tp.dim + r0) * 2;
-    for (int p = 0; p < tp.world; ++p) *reinterpret_cast<__nv_bfloat162*>(peers_s[p] + off) = v;
-}
-
-// Producer side, end of kernel: the last CTA to finish publishes the epoch in every rank's flag array.
-__device__ __forceinline__ void tp_send_done(const TpDev& tp) {
+// Producer side, end of kernel.  Every CTA has written its rows to the local vector `out` (device-scope
+// fence + counter); the LAST CTA to finish copies the whole vector into slot [send_op][rank] of every
+// rank's exchange buffer with 16-byte stores over NVLink, issues ONE system-scope fence and publishes the
+// epoch in every rank's flag array.  (A system fence per CTA costs microseconds and ~1000 CTAs would
+// serialise on it.)
+__device__ __forceinline__ void tp_send_vector(const TpDev& tp, const __nv_bfloat16* out) {
+    __shared__ int is_last;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();  // this CTA's peer stores are visible system-wide
+        __threadfence();
         const int prev = atomicAdd(&tp.cta_done[tp.send_op], 1);
-        if (prev == (int)gridDim.x - 1) {
-            tp.cta_done[tp.send_op] = 0;
-            __threadfence_system();
-            const int32_t ep = *reinterpret_cast<const volatile int32_t*>(tp.epoch);
-            for (int p = 0; p < tp.world; ++p)
-                st_release_sys(reinterpret_cast<int32_t*>(tp.peer_flag[p]) + tp.send_op * tp.world + tp.rank, ep);
-        }
+        is_last = prev == (int)gridDim.x - 1;
+        if (is_last) tp.cta_done[tp.send_op] = 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const size_t slot = (size_t)(tp.send_op * tp.world + tp.rank) * tp.dim;
+    for (int i = threadIdx.x * 8; i < tp.dim; i += kGemvThreads * 8) {
+        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(out + i));
+        for (int p = 0; p < tp.world; ++p)
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(tp.peer_buf[p]) + slot + i) = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < tp.world) {
+        const int32_t ep = *reinterpret_cast<const volatile int32_t*>(tp.epoch);
+        st_release_sys(reinterpret_cast<int32_t*>(tp.peer_flag[threadIdx.x]) + tp.send_op * tp.world + tp.rank, ep);
     }
 }
 
@@ -86,9 +95,19 @@ __device__ void stage_input(const __nv_bfloat16* __restrict__ x, const __nv_bflo
         // consumer of a fused all-reduce: wait for every rank's partial vector of this op, then
         // x = bf16(residual + bf16(sum of the partials))   (tp.py:156-160 + model.py:317 / 326)
         const int32_t ep = *reinterpret_cast<const volatile int32_t*>(tp.epoch);
-        if (tid < tp.world) {
-            const int32_t* f = reinterpret_cast<const int32_t*>(tp.peer_flag[tp.rank]) + tp.recv_op * tp.world + tid;
-            while (ld_acquire_sys(f) != ep) {}
+        int32_t* ready = tp.cta_done + tp.n_ops + tp.recv_op;  // device-scope "all partials have arrived"
+        if (blockIdx.x == 0) {
+            // only CTA 0 polls the system-scope flags the peers write over NVLink ...
+            if (tid < tp.world) {
+                const int32_t* f = reinterpret_cast<const int32_t*>(tp.peer_flag[tp.rank]) + tp.recv_op * tp.world + tid;
+                while (ld_acquire_sys(f) != ep) {}
+            }
+            __syncthreads();
+            if (tid == 0) { __threadfence(); asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(ready), "r"(ep) : "memory"); }
+        } else if (tid == 0) {
+            // ... every other CTA waits on a device-scope word in L2
+            int32_t v;
+            do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory"); } while (v != ep);
         }
         __syncthreads();
         const __nv_bfloat16* recv = reinterpret_cast<const __nv_bfloat16*>(tp.peer_buf[tp.rank]) +
@@ -234,8 +253,6 @@ __device__ __forceinline__ bool combine_split(float (*part)[R], float (&out)[R])
     }                                                                                               \
     pdl_launch_dependents();                                                                        \
     pdl_wait();                                                                                     \
-    __shared__ uint64_t peers_s[kMaxTp];                                                            \
-    if (p.tp.send_op >= 0 && threadIdx.x < p.tp.world) peers_s[threadIdx.x] = p.tp.peer_buf[threadIdx.x]; \
     stage_input(p.x, p.norm_w, p.eps, p.K, xs, scratch, p.tp);
 
 // ---------------------------------------------------------------- attention_norm -> wqkv -> RoPE
@@ -325,12 +342,11 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_residual_kernel(const __gri
                 a = __fadd_rn(__bfloat162float(p.residual[r0]), a);
                 b = __fadd_rn(__bfloat162float(p.residual[r0 + 1]), b);
             }
-            if (p.tp.send_op >= 0) tp_send_pair(p.tp, peers_s, r0, __floats2bfloat162_rn(a, b));
-            else *reinterpret_cast<__nv_bfloat162*>(p.out + r0) = __floats2bfloat162_rn(a, b);
+            *reinterpret_cast<__nv_bfloat162*>(p.out + r0) = __floats2bfloat162_rn(a, b);
         }
         if (KS > 1) __syncthreads();
     }
-    if (p.tp.send_op >= 0) tp_send_done(p.tp);
+    if (p.tp.send_op >= 0) tp_send_vector(p.tp, p.out);
 #undef CC_ROWS
 }
 
@@ -389,7 +405,7 @@ static int fill_tp(const CcTpArgs* tp, int K, TpDev* out, const char* what) {
         if (tp->recv_op >= 0 && l->dim != K) return set_error(CC_ERR_INVALID_ARG, "tensor-parallel receive: dim must equal K");
         d.peer_buf = l->peer_buf; d.peer_flag = l->peer_flag; d.cta_done = l->cta_done; d.epoch = l->epoch;
         d.recv_out = (__nv_bfloat16*)tp->recv_out;
-        d.world = l->world; d.rank = l->rank; d.dim = l->dim; d.send_op = tp->send_op; d.recv_op = tp->recv_op;
+        d.world = l->world; d.rank = l->rank; d.dim = l->dim; d.n_ops = l->n_ops; d.send_op = tp->send_op; d.recv_op = tp->recv_op;
     }
     *out = d;
     return CC_OK;
@@ -481,7 +497,7 @@ int rmsnorm_qkv_rope_impl(const void* x, const void* norm_w, float eps, const vo
 
 int gemv_residual_impl(const void* x, const void* norm_w, float eps, const void* w, const void* residual, void* out,
                        int K, int N, const CcTpArgs* tp, cudaStream_t stream) {
-    if (!x || !w || (!out && !(tp && tp->send_op >= 0))) return set_error(CC_ERR_INVALID_ARG, "cc_gemv_residual: null argument");
+    if (!x || !w || !out) return set_error(CC_ERR_INVALID_ARG, "cc_gemv_residual: null argument");
     if (K % 256 || N % 2) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_gemv_residual: K must be a multiple of 256, N even");
     GemvParams p = {(const __nv_bfloat16*)x, (const __nv_bfloat16*)norm_w, (const __nv_bfloat16*)w,
                     (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, eps, K, N, {}};

@@ -131,7 +131,7 @@ class FusedExchange:
         dist.barrier(group)
         self.peer_buf = torch.tensor(list(hb.buffer_ptrs), dtype=torch.int64, device=dev)
         self.peer_flag = torch.tensor(list(hf.buffer_ptrs), dtype=torch.int64, device=dev)
-        self.cta_done = torch.zeros(self.n_ops, dtype=torch.int32, device=dev)
+        self.cta_done = torch.zeros(2 * self.n_ops, dtype=torch.int32, device=dev)
         self.epoch = torch.ones(1, dtype=torch.int32, device=dev)
         self._handles = (hb, hf)
 

@@ -184,8 +184,9 @@ int cc_prefill_gather(const CcCacheState* state, const void* k_prompt, const voi
  * Tensor-parallel exchange fused into the projections (tp.py:134-138, 156-160: the all-reduce of the
  * row-parallel wo / w2 outputs).  Every rank owns an exchange buffer bf16 [n_ops][world][dim] and a flag
  * array i32 [n_ops][world] in peer-mapped (NVLink) memory.  A projection called with send_op >= 0 writes
- * its partial output rows into slot [send_op][rank] of EVERY rank's buffer and, when its last CTA is
- * done, stores the current epoch into flag [send_op][rank] of every rank.  A projection called with
+ * its partial output vector to `out` as usual; its last CTA to finish copies the vector into slot
+ * [send_op][rank] of EVERY rank's buffer and then stores the current epoch into flag [send_op][rank] of
+ * every rank.  A projection called with
  * recv_op >= 0 first waits until all `world` flags of that op equal the epoch, then uses
  * x = bf16(residual + bf16(sum over ranks of the partials)) as its input (and CTA 0 writes x to recv_out).
  * The caller increments *epoch once per token after the last kernel.
@@ -194,7 +195,7 @@ typedef struct CcTpLink {
     int32_t world, rank, dim, n_ops;
     const uint64_t* peer_buf;    /* device array [world]: base address of each rank's exchange buffer */
     const uint64_t* peer_flag;   /* device array [world]: base address of each rank's flag array      */
-    int32_t*        cta_done;    /* local i32 [n_ops], zero-initialised                                */
+    int32_t*        cta_done;    /* local i32 [2 * n_ops], zero-initialised (CTA counters, then ready words) */
     const int32_t*  epoch;       /* local device i32 [1], >= 1                                         */
 } CcTpLink;
 

@@ -33,7 +33,7 @@ def test_tp_host_logic_gloo_world2():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("strategy", ["heavy_hitter", "recent_global", "heavy_hitter_fused", "l2_fused"])
+@pytest.mark.parametrize("strategy", ["heavy_hitter", "recent_global", "heavy_hitter_fused", "recent_global_fused"])
 def test_tp_decode_nccl_world2(strategy):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
