@@ -183,8 +183,13 @@ def run_ours(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
+    real_stdout = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner must not land on stdout (one JSON line)
+        # NCCL printf()s its version banner on stdout when NCCL_DEBUG=VERSION is set in the environment; the
+        # contract is ONE JSON line on stdout, so point fd 1 at stderr until the result is printed
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         os.environ.setdefault("LOCAL_WORLD_SIZE", str(world))
         from cold_compress_b200.tp import maybe_init_dist
         maybe_init_dist()
@@ -274,6 +279,9 @@ def run_ours(args):
         "gpu_launches": ours_per_step * args.steps,
         "clocks": clocks.summary(),
     }
+    if real_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
     if rank == 0:
         out["roofline"] = roof
         out["cpu_baseline"] = (cpu_reference(sample_seconds=20.0, warmup=1)

@@ -78,11 +78,12 @@ __device__ __forceinline__ void tp_send_vector(const TpDev& tp, const __nv_bfloa
         for (int p = 0; p < tp.world; ++p)
             *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(tp.peer_buf[p]) + slot + i) = v;
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < tp.world) {
+    __syncthreads();  // the CTA's peer stores are ordered before thread 0's system-scope releases below
+    if (threadIdx.x == 0) {
         const int32_t ep = *reinterpret_cast<const volatile int32_t*>(tp.epoch);
-        st_release_sys(reinterpret_cast<int32_t*>(tp.peer_flag[threadIdx.x]) + tp.send_op * tp.world + tp.rank, ep);
+        __threadfence_system();  // one fence for the whole vector
+        for (int p = 0; p < tp.world; ++p)
+            st_release_sys(reinterpret_cast<int32_t*>(tp.peer_flag[p]) + tp.send_op * tp.world + tp.rank, ep);
     }
 }
 
