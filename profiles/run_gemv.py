@@ -23,13 +23,13 @@ q, k, v = mk(Hq * D), mk(Hkv * D), mk(Hkv * D)
 out_d, out_i = mk(dim), mk(inter)
 shapes = {
     "rmsnorm_qkv_rope 6144x4096": ([mk(dim + 2 * Hkv * D, dim) for _ in range(NL)],
-                                   lambda w: ops.rmsnorm_qkv_rope(x, nw, 1e-5, w, None, freqs, pos, q, k, v, Hq, Hkv, D)),
+                                   lambda w: ops.rmsnorm_qkv_rope(x, nw, 1e-5, w, None, freqs, pos, q, k, v, Hq, Hkv, D, [], [], None)),
     "gemv_residual(wo) 4096x4096": ([mk(dim, dim) for _ in range(NL)],
-                                    lambda w: ops.gemv_residual(x, None, 0.0, w, res, out_d)),
+                                    lambda w: ops.gemv_residual(x, None, 0.0, w, res, out_d, [], [], None)),
     "rmsnorm_ffn_gate 2x14336x4096": ([(mk(inter, dim), mk(inter, dim)) for _ in range(NL)],
-                                      lambda w: ops.rmsnorm_ffn_gate(x, nw, 1e-5, w[0], w[1], out_i)),
+                                      lambda w: ops.rmsnorm_ffn_gate(x, nw, 1e-5, w[0], w[1], out_i, [], [], None)),
     "gemv_residual(w2) 4096x14336": ([mk(dim, inter) for _ in range(NL)],
-                                     lambda w: ops.gemv_residual(gate_in, None, 0.0, w, res, out_d)),
+                                     lambda w: ops.gemv_residual(gate_in, None, 0.0, w, res, out_d, [], [], None)),
 }
 tot_us = 0.0
 for name, (ws, fn) in shapes.items():
