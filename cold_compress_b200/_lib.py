@@ -49,6 +49,13 @@ class CcTpArgs(C.Structure):
     _fields_ = [("link", C.POINTER(CcTpLink)), ("send_op", C.c_int32), ("recv_op", C.c_int32), ("recv_out", C.c_void_p)]
 
 
+class CcPrefillAttnArgs(C.Structure):
+    _fields_ = [f for t in "qkvy" for f in ((t, C.c_void_p), (f"{t}_stride_s", C.c_int64), (f"{t}_stride_h", C.c_int64))] + [
+        (n, C.c_int32) for n in ("seq_len", "n_kv_heads", "q_per_kv", "head_dim", "attn_mode", "obs_len", "n_windows")] + [
+        ("windows", C.c_int32 * 4), ("reserved0", C.c_int32)] + [
+        (n, C.c_void_p) for n in ("col_sum", "obs_sum", "band_sum", "workspace")] + [("workspace_bytes", C.c_uint64)]
+
+
 # every symbol include/cc_b200.h declares: name -> (restype, argtypes)
 EXPORTS = {
     "cc_abi_version": (C.c_int, []),
@@ -61,6 +68,8 @@ EXPORTS = {
     "cc_key_norms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "cc_prefill_gather": (C.c_int, [C.POINTER(CcCacheState), C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "cc_prefill_attention_workspace": (C.c_uint64, [C.c_int32] * 5),
+    "cc_prefill_attention": (C.c_int, [C.POINTER(CcPrefillAttnArgs), C.c_void_p]),
     "cc_rmsnorm_qkv_rope": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32, C.POINTER(CcTpArgs), C.c_void_p]),

@@ -4,10 +4,11 @@
   K/V tensors (prefill, or generic use).  It is plain tensor code: the decode step never comes
   through here -- `Attention.forward` hands decode to `KVCache.decode_step` (one CUDA kernel).
 * `prefill_attention_stats` is the prefill path for caches that need attention probabilities:
-  it produces y plus the two reductions of the pooled probability map that the prompt
-  compressors and caches consume (`PrefillAttnStats`), block by block, so the [Hq, S, S] map the
-  reference materialises (4 GiB at S=8192) never exists.  Rounding points follow the reference's
-  naive path: bf16 after q@k^T, after *scale, after softmax, after the GQA mean.
+  one tcgen05 kernel (csrc/prefill_attn.cu) produces y plus the reductions of the pooled
+  probability map that the prompt compressors and caches consume (`PrefillAttnStats`), so the
+  [Hq, S, S] map the reference materialises (4 GiB at S=8192) never exists.  Rounding points
+  follow the reference's naive path: bf16 after q@k^T, after *scale, after softmax, after the
+  GQA mean.  `prefill_attention` is the same kernel without statistics.
 """
 from __future__ import annotations
 
@@ -17,6 +18,7 @@ from typing import Optional, Tuple
 import torch
 from torch.nn import functional as F
 
+from . import _lib, ops
 from .prompt_compression import PrefillAttnStats
 
 
@@ -40,42 +42,51 @@ def scaled_dot_product_attention(query, key, value, attn_mask=None, dropout_p=0.
     return p @ value, p
 
 
-@torch.no_grad()
-def prefill_attention_stats(q, k, v, obs_len: int = 16, block: int = 512, windows=()):
-    """Causal self-attention over a prompt with GQA.
+_workspace: dict = {}
 
-    q [1, Hq, S, D], k/v [1, Hkv, S, D] (bf16, post-RoPE).  Returns (y [1, Hq, S, D], PrefillAttnStats).
-    Work per query block b: logits [Hkv, G*B, S_b] with S_b = end of the block (causality)."""
+
+def _scratch(device, nbytes: int) -> torch.Tensor:
+    """Per-device scratch for the partial column sums (grown on demand, reused across layers)."""
+    buf = _workspace.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _workspace[device] = buf
+    return buf
+
+
+@torch.no_grad()
+def prefill_attention(q, k, v, attn_mode: int = _lib.ATTN_MATH_FP32):
+    """Causal GQA attention over a prompt on the tensor cores, no statistics (caches that keep no scores).
+    q [1, Hq, S, D], k/v [1, Hkv, S, D] bf16 (any row/head strides).  Returns y [1, Hq, S, D] (a view of [S, Hq, D])."""
+    _, Hq, S, D = q.shape
+    y = torch.empty(S, Hq, D, dtype=q.dtype, device=q.device)
+    ops.prefill_attention(q[0], k[0], v[0], y.permute(1, 0, 2), attn_mode, 0, [], None, None, None, None)
+    return y.permute(1, 0, 2).unsqueeze(0)
+
+
+@torch.no_grad()
+def prefill_attention_stats(q, k, v, obs_len: int = 16, windows=()):
+    """Causal self-attention over a prompt with GQA, plus the reductions of the pooled probability map.
+
+    q [1, Hq, S, D], k/v [1, Hkv, S, D] (bf16, post-RoPE; any row/head strides).  Returns
+    (y [1, Hq, S, D], PrefillAttnStats).  ONE tcgen05 kernel (csrc/prefill_attn.cu) + a fixed-order reduction
+    of its per-tile partial sums; the reference's rounding points (naive path) are applied in the kernel,
+    the final bf16 roundings of the reductions (prompt_compression.py:175, 192) here."""
+    if not q.is_cuda:
+        raise _lib.CcError("prefill_attention_stats is CUDA-only (cc_prefill_attention); there is no CPU path")
     _, Hq, S, D = q.shape
     Hkv = k.shape[1]
     G = Hq // Hkv
-    scale = 1.0 / math.sqrt(D)
     obs_len = min(obs_len, S)
-    qg = q[0].view(Hkv, G, S, D)
-    kt = k[0].transpose(-2, -1)  # [Hkv, D, S]
-    vv = v[0]
-    y = torch.empty(Hkv, G, S, D, dtype=q.dtype, device=q.device)
-    col_sum = torch.zeros(Hkv, S, dtype=torch.float32, device=q.device)
-    obs_rows = torch.zeros(Hkv, obs_len, S, dtype=q.dtype, device=q.device)
-    band = {int(w): torch.zeros(Hkv, S, dtype=torch.float32, device=q.device) for w in windows}
-    cols = torch.arange(S, device=q.device)
-    for i0 in range(0, S, block):
-        i1 = min(S, i0 + block)
-        B = i1 - i0
-        logits = (qg[:, :, i0:i1].reshape(Hkv, G * B, D) @ kt[:, :, :i1]) * scale      # bf16, bf16
-        rows = torch.arange(i0, i1, device=q.device).repeat(G).view(1, G * B, 1)
-        logits = logits.masked_fill(cols[:i1].view(1, 1, -1) > rows, float("-inf"))
-        p = torch.softmax(logits, dim=-1)                                                # fp32 inside, bf16 out
-        y[:, :, i0:i1] = (p @ vv[:, :i1]).view(Hkv, G, B, D)
-        pooled = p.view(Hkv, G, B, i1).mean(dim=1)                                       # model.py:413-418
-        col_sum[:, :i1] += pooled.float().sum(dim=1)
-        for w, acc in band.items():  # rows i of this block that still see column j inside a window of w
-            inside = (torch.arange(i0, i1, device=q.device).view(-1, 1) - cols[:i1].view(1, -1)) < w
-            acc[:, :i1] += (pooled.float() * inside).sum(dim=1)
-        lo = max(i0, S - obs_len)
-        if lo < i1:
-            obs_rows[:, lo - (S - obs_len): i1 - (S - obs_len), :i1] = pooled[:, lo - i0:, :]
-    stats = PrefillAttnStats(col_sum=col_sum.to(q.dtype).unsqueeze(0),
-                             obs_mean=obs_rows.float().mean(dim=1).to(q.dtype).unsqueeze(0), obs_len=obs_len,
-                             band_sum=band or None)
-    return y.view(1, Hq, S, D), stats
+    windows = [int(w) for w in windows]
+    dev = q.device
+    y = torch.empty(S, Hq, D, dtype=q.dtype, device=dev)
+    col = torch.empty(Hkv, S, dtype=torch.float32, device=dev)
+    obs = torch.empty(Hkv, S, dtype=torch.float32, device=dev)
+    band = torch.empty(len(windows), Hkv, S, dtype=torch.float32, device=dev) if windows else None
+    ws = _scratch(dev, ops.prefill_attention_workspace(S, Hkv, G, obs_len, len(windows)))
+    ops.prefill_attention(q[0], k[0], v[0], y.permute(1, 0, 2), _lib.ATTN_NAIVE_BF16, obs_len, windows, col, obs, band, ws)
+    stats = PrefillAttnStats(col_sum=col.to(q.dtype).unsqueeze(0),
+                             obs_mean=(obs / obs_len).to(q.dtype).unsqueeze(0), obs_len=obs_len,
+                             band_sum={w: band[i] for i, w in enumerate(windows)} if windows else None)
+    return y.permute(1, 0, 2).unsqueeze(0), stats

@@ -62,6 +62,15 @@ int cc_prefill_gather(const CcCacheState* state, const void* k_prompt, const voi
                                    (cudaStream_t)stream);
 }
 
+uint64_t cc_prefill_attention_workspace(int32_t seq_len, int32_t n_kv_heads, int32_t q_per_kv, int32_t obs_len,
+                                        int32_t n_windows) {
+    return cc::prefill_attention_workspace_impl(seq_len, n_kv_heads, q_per_kv, obs_len, n_windows);
+}
+
+int cc_prefill_attention(const CcPrefillAttnArgs* args, void* stream) {
+    return cc::prefill_attention_impl(args, (cudaStream_t)stream);
+}
+
 int cc_rmsnorm_qkv_rope(const void* x, const void* norm_w, float eps, const void* wqkv, const void* bias,
                         const void* freqs_cis, const int32_t* input_pos, void* q, void* k, void* v,
                         int32_t dim, int32_t n_q_heads, int32_t n_kv_heads, int32_t head_dim,

@@ -15,6 +15,8 @@ int key_norms_impl(const void* k, void* key_norm, int n_rows, int head_dim, cuda
 int prefill_gather_impl(const CcCacheState* st, const void* k_prompt, const void* v_prompt,
                         const int64_t* keep_idx, int keep_heads, int n_keep, int prompt_len,
                         cudaStream_t stream);
+int prefill_attention_impl(const CcPrefillAttnArgs* a, cudaStream_t stream);
+unsigned long long prefill_attention_workspace_impl(int S, int Hkv, int G, int obs_len, int n_windows);
 int rmsnorm_qkv_rope_impl(const void* x, const void* norm_w, float eps, const void* wqkv, const void* bias,
                           const void* freqs, const int32_t* input_pos, void* q, void* k, void* v, int dim,
                           int n_q_heads, int n_kv_heads, int head_dim, const CcTpArgs* tp, cudaStream_t stream);

@@ -1,0 +1,568 @@
+// prefill_attn.cu -- causal prompt attention on the 5th-gen tensor cores (tcgen05 + TMEM), with the
+// reductions of the GQA-pooled probability map that the prompt compressors and the score-keeping caches
+// consume (SnapKV observation-window mean, heavy-hitter column sums, FastGen window bands) produced in
+// the same pass, so the [Hq, S, S] map the reference materialises (attention_utils.py:36-54: 4 GiB per
+// layer at S = 8192) never exists.
+//
+// Replaces, for the prefill branch of Attention.forward (model.py:399-427):
+//   scaled_dot_product_attention(q, k, v, mask, return_attn=True)      attention_utils.py:36-54
+//   attn.view(B, Hkv, G, S, S).mean(2)                                 model.py:413-418
+//   attn[:, :, -16:, :].mean(2)  /  attn.sum(2)                        prompt_compression.py:175, 192; cache.py:704
+//   band sums of build_masks' windows                                  cache.py:1066-1173
+//
+// One CTA = one KV head x one block of QB = 128/G query positions, all G query heads of the group
+// stacked into the M = 128 rows of the MMA (row = g * QB + i), so a K/V tile is read once per group.
+// Two sweeps over the key tiles (BN = 128 keys):
+//   sweep 1  S = Q K^T (tcgen05.mma, fp32 in TMEM) -> row max and sum of exp      (softmax statistics)
+//   sweep 2  S again -> P = bf16(exp(l - max) / sum) exactly as the reference rounds it -> shared memory
+//            -> Y += P V (tcgen05.mma); the same P tile is read column-wise for the pooled reductions.
+// The reference's rounding points are kept (NAIVE: bf16 after q.k, after *scale, after softmax, after the
+// GQA mean; MATH: fp32 logits, one rounding of P for the tensor core).
+// Operands are staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a double-buffered ring; the S
+// accumulator is double-buffered in TMEM so the next tile's Q K^T runs under the current tile's softmax.
+// Per-tile partial column sums go to a scratch buffer and are added in a fixed order by a second small
+// kernel: results are bit-reproducible run to run (no floating-point atomics).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace cc {
+namespace {
+
+constexpr int BM = 128;                 // MMA rows of a query tile (G * QB, padded)
+constexpr int BN = 128;                 // keys per tile
+constexpr int ATOM_BYTES = 128 * 128;   // one 128-byte-swizzled sub-tile: 128 rows x 64 bf16
+constexpr int NTHREADS = 256;
+constexpr int MAX_WINDOWS = 4;
+constexpr int TMEM_COLS = 512;          // S0 [0,128) S1 [128,256) Y [256, 256 + D)
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct PrefillParams {
+    __nv_bfloat16* y;
+    long long y_stride_s, y_stride_h;   // elements
+    float* part_col;                    // [Hkv][n_qtiles][2][S_pad]
+    float* part_obs;                    // [Hkv][n_obs_tiles][2][S_pad]
+    float* part_band;                   // [n_windows][Hkv][n_qtiles][2][S_pad]
+    int S, S_pad, Hkv, G, QB, n_qtiles;
+    int obs_start;                      // first query row of the observation window (S = none)
+    int first_obs_tile, n_obs_tiles, n_windows;
+    int windows[MAX_WINDOWS];
+    float scale;
+    int stats;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* tm, int c0, int c1, int c2,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        :: "r"(smem_dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void mbar_init_u32(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor, 128-byte swizzle (layout type 2), descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: bf16 x bf16 -> fp32, A K-major, B K-major or MN-major
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns of this warp's TMEM lane quarter -> registers (and wait)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+    float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// ------------------------------------------------------------------ the kernel
+// grid = n_qtiles * Hkv CTAs (longest query tiles first), 256 threads: thread (row = tid % 128, half = tid / 128)
+// owns columns [64*half, 64*half + 64) of its row of every S tile (its warp's TMEM lane quarter is row / 32).
+template <int D, bool NAIVE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+prefill_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                    const __grid_constant__ CUtensorMap tm_v, const PrefillParams p) {
+    constexpr int DH = D / 64;               // 64-column (128-byte) sub-tiles along the head dimension
+    constexpr int TILE_BYTES = DH * ATOM_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[8];   // 0 q, 1-2 k[2], 3-4 v[2], 5-6 s[2], 7 pv
+    __shared__ uint32_t s_tmem_base;
+    __shared__ float s_rowstat[2][BM][2];
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & 127, half = tid >> 7;
+    const int h = blockIdx.x % p.Hkv;
+    const int qt = p.n_qtiles - 1 - blockIdx.x / p.Hkv;
+    const int i0 = qt * p.QB;
+    const int T = (min(i0 + p.QB, p.S) + BN - 1) / BN;   // key tiles this query block can see
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sQ = smem_base, sK = sQ + TILE_BYTES, sV = sK + 2 * TILE_BYTES, sP = sV + 2 * TILE_BYTES;
+    uint8_t* const sP_ptr = smem_raw + (sP - smem_u32(smem_raw));
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+
+    if (tid == 0) {
+        for (int i = 0; i < 8; ++i) mbar_init_u32(BAR(i), 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(&s_tmem_base)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (p.G * p.QB < BM) {   // rows the Q box does not cover: zero them once (they only feed unused S rows)
+        uint4* q4 = reinterpret_cast<uint4*>(smem_raw + (sQ - smem_u32(smem_raw)));
+        for (int i = tid; i < TILE_BYTES / 16; i += NTHREADS) q4[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem_base;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+
+    constexpr uint32_t IDESC_S = make_idesc(BM, BN, false);
+    constexpr uint32_t IDESC_PV = make_idesc(BM, D, true);
+
+    auto issue_k = [&](int tile, int buf) {
+        mbar_expect_tx_u32(BAR(1 + buf), TILE_BYTES);
+#pragma unroll
+        for (int dh = 0; dh < DH; ++dh)
+            tma_load_3d(sK + buf * TILE_BYTES + dh * ATOM_BYTES, &tm_k, dh * 64, tile * BN, h, BAR(1 + buf));
+    };
+    auto issue_v = [&](int tile, int buf) {
+        mbar_expect_tx_u32(BAR(3 + buf), TILE_BYTES);
+#pragma unroll
+        for (int dh = 0; dh < DH; ++dh)
+            tma_load_3d(sV + buf * TILE_BYTES + dh * ATOM_BYTES, &tm_v, dh * 64, tile * BN, h, BAR(3 + buf));
+    };
+    // S[buf] = Q K_buf^T : D/16 MMAs of K = 16
+    auto mma_s = [&](int buf) {
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+            const uint32_t off = (k >> 2) * ATOM_BYTES + (k & 3) * 32;
+            umma_bf16(tmem + buf * BN, smem_desc(sQ + off, 16, 1024), smem_desc(sK + buf * TILE_BYTES + off, 16, 1024),
+                      IDESC_S, k > 0);
+        }
+        umma_commit(BAR(5 + buf));
+    };
+    // Y (+)= P V_buf : BN/16 MMAs; V is [key][d] in shared memory = MN-major B operand
+    auto mma_pv = [&](int buf, bool first) {
+#pragma unroll
+        for (int k = 0; k < BN / 16; ++k) {
+            const uint32_t aoff = (k >> 2) * ATOM_BYTES + (k & 3) * 32;
+            umma_bf16(tmem + 2 * BN, smem_desc(sP + aoff, 16, 1024),
+                      smem_desc(sV + buf * TILE_BYTES + k * 2048, ATOM_BYTES, 1024), IDESC_PV, !(first && k == 0));
+        }
+        umma_commit(BAR(7));
+    };
+
+    const int NT = 2 * T;   // tile visits: sweep 1 then sweep 2
+    if (tid == 0) {
+        mbar_expect_tx_u32(BAR(0), (uint32_t)(DH * p.G * p.QB * 128));
+#pragma unroll
+        for (int dh = 0; dh < DH; ++dh) tma_load_3d(sQ + dh * ATOM_BYTES, &tm_q, dh * 64, i0, h * p.G, BAR(0));
+        issue_k(0, 0);
+        issue_k(1 % T, 1);          // NT >= 2 always
+        issue_v(0, 0);
+        if (T > 1) issue_v(1, 1);
+        mbar_wait_u32(BAR(0), 0);
+        mbar_wait_u32(BAR(1), 0);
+        tc_fence_after();
+        mma_s(0);
+    }
+    __syncwarp();
+
+    // this thread's row
+    const int g = row / p.QB, il = row % p.QB;
+    const int qi = i0 + il;
+    const bool row_ok = (g < p.G) && (qi < p.S);
+    float m_run = -INFINITY, s_run = 0.f;
+    float m_fin = 0.f, inv_s = 0.f;
+    const float scale = p.scale;
+
+    for (int n = 0; n < NT; ++n) {
+        const int sweep2 = n >= T;
+        const int t = sweep2 ? n - T : n;
+        const int sb = n & 1;
+        if (tid == 0 && n + 1 < NT) {   // next tile's logits under this tile's softmax
+            mbar_wait_u32(BAR(1 + ((n + 1) & 1)), ((n + 1) >> 1) & 1);
+            tc_fence_after();
+            mma_s((n + 1) & 1);
+        }
+        __syncwarp();
+        mbar_wait_u32(BAR(5 + sb), (n >> 1) & 1);
+        tc_fence_after();
+        uint32_t v0[32], v1[32];
+        tmem_ld32(tmem + lane_base + sb * BN + half * 64, v0);
+        tmem_ld32(tmem + lane_base + sb * BN + half * 64 + 32, v1);
+        if (tid == 0 && n + 2 < NT) issue_k((n + 2) % T, sb);   // K[sb] is free: its MMA has completed
+        __syncwarp();
+
+        const int kbase = t * BN + half * 64;
+        const bool need_mask = (t == T - 1);
+        float l[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+            float x = __uint_as_float(c < 32 ? v0[c & 31] : v1[c & 31]);
+            if (NAIVE) x = bf16_round(bf16_round(x) * scale); else x = x * scale;
+            if (need_mask && kbase + c > qi) x = -INFINITY;
+            l[c] = x;
+        }
+        if (!sweep2) {
+            float tmax = l[0];
+#pragma unroll
+            for (int c = 1; c < 64; ++c) tmax = fmaxf(tmax, l[c]);
+            const float m_new = fmaxf(m_run, tmax);
+            if (m_new > -INFINITY) {
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < 64; ++c) acc += ex2((l[c] - m_new) * LOG2E);
+                s_run = s_run * ex2((m_run - m_new) * LOG2E) + acc;
+                m_run = m_new;
+            }
+            if (n == T - 1) {   // merge the two column halves of every row
+                s_rowstat[half][row][0] = m_run;
+                s_rowstat[half][row][1] = s_run;
+            }
+            tc_fence_before();
+            __syncthreads();
+            if (n == T - 1) {
+                const float m0 = s_rowstat[0][row][0], s0 = s_rowstat[0][row][1];
+                const float m1 = s_rowstat[1][row][0], s1 = s_rowstat[1][row][1];
+                m_fin = fmaxf(m0, m1);   // finite: key 0 is visible to every query
+                const float tot = s0 * ex2((m0 - m_fin) * LOG2E) + s1 * ex2((m1 - m_fin) * LOG2E);
+                inv_s = 1.0f / tot;
+            }
+            continue;
+        }
+        // ---- sweep 2: P tile
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) {
+            const float p0 = ex2((l[c] - m_fin) * LOG2E) * inv_s;
+            const float p1 = ex2((l[c + 1] - m_fin) * LOG2E) * inv_s;
+            pk[c >> 1] = pack_bf16(p0, p1);
+        }
+        if (t > 0) mbar_wait_u32(BAR(7), (t - 1) & 1);   // P V of the previous tile done: sP and V[(t-1)&1] are free
+        __syncthreads();                                  // everyone finished reading the previous P tile
+        if (tid == 0 && t >= 1 && t + 1 < T) issue_v(t + 1, (t + 1) & 1);
+        {
+            uint8_t* prow = sP_ptr + half * ATOM_BYTES + row * 128;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8)
+                *reinterpret_cast<uint4*>(prow + ((c8 ^ (row & 7)) << 4)) =
+                    make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            mbar_wait_u32(BAR(3 + (t & 1)), (t >> 1) & 1);
+            tc_fence_after();
+            mma_pv(t & 1, t == 0);
+        }
+        __syncwarp();
+        if (p.stats) {   // pooled column reductions: thread (column cc, row half hs)
+            const int cc = tid & 127, hs = tid >> 7;
+            const int j = t * BN + cc;
+            const uint8_t* pcol = sP_ptr + (cc >> 6) * ATOM_BYTES + (cc & 7) * 2;
+            const int chunk = (cc & 63) >> 3;
+            float col = 0.f, obs = 0.f, band[MAX_WINDOWS] = {0.f, 0.f, 0.f, 0.f};
+            const int ib = hs * (p.QB >> 1), ie = ib + (p.QB >> 1);
+            const float fG = (float)p.G;
+            for (int i = ib; i < ie; ++i) {
+                const int q_i = i0 + i;
+                if (q_i >= p.S) break;
+                float sum = 0.f;
+                for (int gg = 0; gg < p.G; ++gg) {
+                    const int r = gg * p.QB + i;
+                    const uint16_t b = *reinterpret_cast<const uint16_t*>(pcol + r * 128 + ((chunk ^ (r & 7)) << 4));
+                    sum += bf16_bits_to_float(b);
+                }
+                const float pooled = bf16_round(__fdiv_rn(sum, fG));
+                col += pooled;
+                if (q_i >= p.obs_start) obs += pooled;
+#pragma unroll
+                for (int w = 0; w < MAX_WINDOWS; ++w)
+                    if (w < p.n_windows && q_i - j < p.windows[w]) band[w] += pooled;
+            }
+            const size_t slab = (size_t)p.S_pad;
+            p.part_col[(((size_t)h * p.n_qtiles + qt) * 2 + hs) * slab + j] = col;
+            if (qt >= p.first_obs_tile)
+                p.part_obs[(((size_t)h * p.n_obs_tiles + (qt - p.first_obs_tile)) * 2 + hs) * slab + j] = obs;
+            for (int w = 0; w < p.n_windows; ++w)
+                p.part_band[((((size_t)w * p.Hkv + h) * p.n_qtiles + qt) * 2 + hs) * slab + j] = band[w];
+        }
+    }
+
+    // ---- epilogue: Y (fp32 in TMEM) -> bf16 -> global
+    mbar_wait_u32(BAR(7), (T - 1) & 1);
+    tc_fence_after();
+    {
+        constexpr int CPT = D / 2;   // columns per thread
+        uint32_t y0[32];
+        __nv_bfloat16* yrow = p.y + (long long)(h * p.G + g) * p.y_stride_h + (long long)qi * p.y_stride_s + half * CPT;
+#pragma unroll
+        for (int part = 0; part < CPT / 32; ++part) {
+            tmem_ld32(tmem + lane_base + 2 * BN + half * CPT + part * 32, y0);
+            if (row_ok) {
+#pragma unroll
+                for (int c = 0; c < 32; c += 8) {
+                    uint4 o = make_uint4(pack_bf16(__uint_as_float(y0[c]), __uint_as_float(y0[c + 1])),
+                                         pack_bf16(__uint_as_float(y0[c + 2]), __uint_as_float(y0[c + 3])),
+                                         pack_bf16(__uint_as_float(y0[c + 4]), __uint_as_float(y0[c + 5])),
+                                         pack_bf16(__uint_as_float(y0[c + 6]), __uint_as_float(y0[c + 7])));
+                    *reinterpret_cast<uint4*>(yrow + part * 32 + c) = o;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// Fixed-order sum of the per-tile partials: one thread per (head, column).
+__global__ void __launch_bounds__(256)
+prefill_reduce_kernel(const PrefillParams p, float* __restrict__ col_sum, float* __restrict__ obs_sum,
+                      float* __restrict__ band_sum) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int h = blockIdx.y;
+    if (j >= p.S) return;
+    const size_t slab = (size_t)p.S_pad;
+    const int qt0 = j / p.QB;
+    float acc = 0.f;
+    for (int qt = qt0; qt < p.n_qtiles; ++qt) {
+        const float* a = p.part_col + (((size_t)h * p.n_qtiles + qt) * 2) * slab + j;
+        acc += a[0];
+        acc += a[slab];
+    }
+    col_sum[(size_t)h * p.S + j] = acc;
+    if (obs_sum) {
+        float o = 0.f;
+        for (int qt = max(qt0, p.first_obs_tile); qt < p.n_qtiles; ++qt) {
+            const float* a = p.part_obs + (((size_t)h * p.n_obs_tiles + (qt - p.first_obs_tile)) * 2) * slab + j;
+            o += a[0];
+            o += a[slab];
+        }
+        obs_sum[(size_t)h * p.S + j] = o;
+    }
+    for (int w = 0; w < p.n_windows; ++w) {
+        const int qt1 = min(p.n_qtiles - 1, (j + p.windows[w] - 1) / p.QB);   // later query tiles are outside the band
+        float b = 0.f;
+        for (int qt = qt0; qt <= qt1; ++qt) {
+            const float* a = p.part_band + ((((size_t)w * p.Hkv + h) * p.n_qtiles + qt) * 2) * slab + j;
+            b += a[0];
+            b += a[slab];
+        }
+        band_sum[((size_t)w * p.Hkv + h) * p.S + j] = b;
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// bf16 tensor [heads][S][D] with element strides (head, row); box = (64 columns, box_rows, box_heads), 128B swizzle
+int make_map(CUtensorMap* tm, const void* base, int D, int S, int heads, long long stride_s, long long stride_h,
+             int box_rows, int box_heads) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(CC_ERR_CUDA, "cc_prefill_attention: cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)S, (cuuint64_t)heads};
+    cuuint64_t strides[2] = {(cuuint64_t)stride_s * 2, (cuuint64_t)stride_h * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)box_heads};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char msg[160];
+        snprintf(msg, sizeof(msg), "cc_prefill_attention: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+        return set_error(CC_ERR_CUDA, msg);
+    }
+    return CC_OK;
+}
+
+int query_block(int G) {   // largest power of two <= 128 / G
+    int qb = 1;
+    while (qb * 2 * G <= BM) qb *= 2;
+    return qb;
+}
+
+struct Plan {
+    int QB, n_qtiles, S_pad, first_obs_tile, n_obs_tiles;
+    size_t col_floats, obs_floats, band_floats;
+};
+
+Plan make_plan(int S, int Hkv, int G, int obs_len, int n_windows) {
+    Plan pl;
+    pl.QB = query_block(G);
+    pl.n_qtiles = (S + pl.QB - 1) / pl.QB;
+    pl.S_pad = (S + BN - 1) / BN * BN;
+    const int obs = obs_len > S ? S : obs_len;
+    pl.first_obs_tile = obs > 0 ? (S - obs) / pl.QB : pl.n_qtiles;
+    pl.n_obs_tiles = pl.n_qtiles - pl.first_obs_tile;
+    pl.col_floats = (size_t)Hkv * pl.n_qtiles * 2 * pl.S_pad;
+    pl.obs_floats = (size_t)Hkv * pl.n_obs_tiles * 2 * pl.S_pad;
+    pl.band_floats = (size_t)n_windows * pl.col_floats;
+    return pl;
+}
+
+template <int D, bool NAIVE>
+int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const PrefillParams& p, int grid,
+           cudaStream_t stream) {
+    const int smem = 1024 + (D / 64) * ATOM_BYTES * 5 + 2 * ATOM_BYTES;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(prefill_attn_kernel<D, NAIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return set_cuda_error(e, "cc_prefill_attention: shared memory attribute");
+        configured = true;
+    }
+    prefill_attn_kernel<D, NAIVE><<<grid, NTHREADS, smem, stream>>>(tq, tk, tv, p);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? CC_OK : set_cuda_error(e, "cc_prefill_attention launch");
+}
+
+}  // namespace
+
+unsigned long long prefill_attention_workspace_impl(int S, int Hkv, int G, int obs_len, int n_windows) {
+    if (S <= 0 || Hkv <= 0 || G <= 0 || G > 16 || n_windows < 0 || n_windows > MAX_WINDOWS) return 0;
+    const Plan pl = make_plan(S, Hkv, G, obs_len, n_windows);
+    return (uint64_t)(pl.col_floats + pl.obs_floats + pl.band_floats) * sizeof(float) + 256;
+}
+
+int prefill_attention_impl(const CcPrefillAttnArgs* a, cudaStream_t stream) {
+    if (!a || !a->q || !a->k || !a->v || !a->y) return set_error(CC_ERR_INVALID_ARG, "cc_prefill_attention: null argument");
+    const int S = a->seq_len, Hkv = a->n_kv_heads, G = a->q_per_kv, D = a->head_dim;
+    if (S <= 0 || Hkv <= 0) return set_error(CC_ERR_INVALID_ARG, "cc_prefill_attention: empty problem");
+    if ((D != 64 && D != 128) || G < 1 || G > 16)
+        return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_prefill_attention: head_dim must be 64 or 128 and q_per_kv <= 16");
+    if (a->n_windows < 0 || a->n_windows > MAX_WINDOWS)
+        return set_error(CC_ERR_INVALID_ARG, "cc_prefill_attention: at most 4 band windows");
+    if (a->attn_mode != CC_ATTN_NAIVE_BF16 && a->attn_mode != CC_ATTN_MATH_FP32)
+        return set_error(CC_ERR_INVALID_ARG, "cc_prefill_attention: bad attn_mode");
+    const long long strides[] = {a->q_stride_s, a->q_stride_h, a->k_stride_s, a->k_stride_h, a->v_stride_s,
+                                 a->v_stride_h, a->y_stride_s, a->y_stride_h};
+    for (long long s : strides)
+        if (s <= 0 || (s % 8) != 0) return set_error(CC_ERR_INVALID_ARG, "cc_prefill_attention: strides must be positive multiples of 8 elements");
+    const uintptr_t ptrs[] = {(uintptr_t)a->q, (uintptr_t)a->k, (uintptr_t)a->v, (uintptr_t)a->y};
+    for (uintptr_t q : ptrs)
+        if (q % 16) return set_error(CC_ERR_INVALID_ARG, "cc_prefill_attention: tensors must be 16-byte aligned");
+    const bool stats = a->col_sum != nullptr;
+    if (!stats && (a->obs_sum || a->band_sum || a->n_windows))
+        return set_error(CC_ERR_INVALID_ARG, "cc_prefill_attention: obs_sum / band_sum need col_sum");
+    if (a->n_windows && !a->band_sum) return set_error(CC_ERR_INVALID_ARG, "cc_prefill_attention: band_sum missing");
+
+    const int obs_len = (stats && a->obs_sum) ? (a->obs_len > S ? S : a->obs_len) : 0;
+    const Plan pl = make_plan(S, Hkv, G, obs_len, stats ? a->n_windows : 0);
+    PrefillParams p;
+    p.y = (__nv_bfloat16*)a->y; p.y_stride_s = a->y_stride_s; p.y_stride_h = a->y_stride_h;
+    p.S = S; p.S_pad = pl.S_pad; p.Hkv = Hkv; p.G = G; p.QB = pl.QB; p.n_qtiles = pl.n_qtiles;
+    p.obs_start = obs_len > 0 ? S - obs_len : S;
+    p.first_obs_tile = pl.first_obs_tile; p.n_obs_tiles = pl.n_obs_tiles;
+    p.n_windows = stats ? a->n_windows : 0;
+    for (int w = 0; w < MAX_WINDOWS; ++w) p.windows[w] = w < p.n_windows ? a->windows[w] : 0;
+    p.scale = (float)(1.0 / sqrt((double)D));
+    p.stats = stats ? 1 : 0;
+    p.part_col = p.part_obs = p.part_band = nullptr;
+    if (stats) {
+        const uint64_t need = prefill_attention_workspace_impl(S, Hkv, G, obs_len, p.n_windows);
+        if (!a->workspace || a->workspace_bytes < need)
+            return set_error(CC_ERR_INVALID_ARG, "cc_prefill_attention: workspace too small (see cc_prefill_attention_workspace)");
+        float* w = (float*)(((uintptr_t)a->workspace + 255) & ~(uintptr_t)255);
+        p.part_col = w;
+        p.part_obs = w + pl.col_floats;
+        p.part_band = p.part_obs + pl.obs_floats;
+    }
+    CUtensorMap tq, tk, tv;
+    int rc;
+    if ((rc = make_map(&tq, a->q, D, S, Hkv * G, a->q_stride_s, a->q_stride_h, pl.QB, G)) != CC_OK) return rc;
+    if ((rc = make_map(&tk, a->k, D, S, Hkv, a->k_stride_s, a->k_stride_h, BN, 1)) != CC_OK) return rc;
+    if ((rc = make_map(&tv, a->v, D, S, Hkv, a->v_stride_s, a->v_stride_h, BN, 1)) != CC_OK) return rc;
+    const int grid = pl.n_qtiles * Hkv;
+    const bool naive = a->attn_mode == CC_ATTN_NAIVE_BF16;
+    if (D == 128) rc = naive ? launch<128, true>(tq, tk, tv, p, grid, stream) : launch<128, false>(tq, tk, tv, p, grid, stream);
+    else          rc = naive ? launch<64, true>(tq, tk, tv, p, grid, stream) : launch<64, false>(tq, tk, tv, p, grid, stream);
+    if (rc != CC_OK) return rc;
+    if (stats) {
+        dim3 rgrid((S + 255) / 256, Hkv);
+        prefill_reduce_kernel<<<rgrid, 256, 0, stream>>>(p, a->col_sum, obs_len > 0 ? a->obs_sum : nullptr, a->band_sum);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return set_cuda_error(e, "cc_prefill_attention reduce launch");
+    }
+    return CC_OK;
+}
+
+}  // namespace cc

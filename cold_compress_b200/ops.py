@@ -27,6 +27,9 @@ _library.define("key_norms(Tensor k, Tensor(a!) key_norm) -> ()")
 _library.define(
     "prefill_gather(Tensor(a!)[] state, int[] meta, Tensor k_prompt, Tensor v_prompt, Tensor keep_idx) -> ()")
 _library.define(
+    "prefill_attention(Tensor q, Tensor k, Tensor v, Tensor(a!) y, int attn_mode, int obs_len, int[] windows, "
+    "Tensor(b!)? col_sum, Tensor(c!)? obs_sum, Tensor(d!)? band_sum, Tensor(e!)? workspace) -> ()")
+_library.define(
     "rmsnorm_qkv_rope(Tensor x, Tensor norm_w, float eps, Tensor wqkv, Tensor? bias, Tensor freqs_cis, "
     "Tensor input_pos, Tensor(a!) q, Tensor(b!) k, Tensor(c!) v, int n_q_heads, int n_kv_heads, int head_dim, "
     "Tensor[] tp_link, int[] tp_meta, Tensor(d!)? recv_out) -> ()")
@@ -104,6 +107,33 @@ def _prefill_gather(state, meta, k_prompt, v_prompt, keep_idx):
                                      n_keep, prompt_len, _stream()), "cc_prefill_gather")
 
 
+def prefill_attention_workspace(seq_len, n_kv_heads, q_per_kv, obs_len, n_windows) -> int:
+    return int(_lib.load().cc_prefill_attention_workspace(seq_len, n_kv_heads, q_per_kv, obs_len, n_windows))
+
+
+def _prefill_attention(q, k, v, y, attn_mode, obs_len, windows, col_sum, obs_sum, band_sum, workspace):
+    """q / y [Hq, S, D] and k / v [Hkv, S, D] VIEWS (any row / head strides, D contiguous): cc_prefill_attention."""
+    for t in (q, k, v, y, col_sum, obs_sum, band_sum, workspace):
+        if t is not None and t.numel() and not t.is_cuda:
+            raise _lib.CcError("cold_compress_b200 ops run on CUDA tensors only (no CPU fallback)")
+    for t in (q, k, v, y):
+        if t.dim() != 3 or t.stride(2) != 1 or t.dtype != torch.bfloat16:
+            raise _lib.CcError("prefill_attention: expected bf16 [heads, S, D] views with a contiguous last dimension")
+    a = _lib.CcPrefillAttnArgs()
+    for name, t in (("q", q), ("k", k), ("v", v), ("y", y)):
+        setattr(a, name, t.data_ptr())
+        setattr(a, name + "_stride_h", t.stride(0))
+        setattr(a, name + "_stride_s", t.stride(1))
+    a.seq_len, a.n_kv_heads, a.q_per_kv, a.head_dim = q.shape[1], k.shape[0], q.shape[0] // k.shape[0], q.shape[2]
+    a.attn_mode, a.obs_len, a.n_windows = int(attn_mode), int(obs_len), len(windows)
+    for i, w in enumerate(windows):
+        a.windows[i] = int(w)
+    a.col_sum, a.obs_sum, a.band_sum = _optr(col_sum), _optr(obs_sum), _optr(band_sum)
+    a.workspace = _optr(workspace)
+    a.workspace_bytes = 0 if workspace is None else workspace.numel() * workspace.element_size()
+    _lib.check(_lib.load().cc_prefill_attention(C.byref(a), _stream()), "cc_prefill_attention")
+
+
 def _optr(t):
     return None if t is None else t.data_ptr()
 
@@ -155,18 +185,20 @@ _library.impl("gemv_residual", _gemv_residual, "CUDA")
 _library.impl("rmsnorm_ffn_gate", _rmsnorm_ffn_gate, "CUDA")
 _library.impl("key_norms", _key_norms, "CUDA")
 _library.impl("prefill_gather", _prefill_gather, "CUDA")
+_library.impl("prefill_attention", _prefill_attention, "CUDA")
 
 
 def _no_cpu(*_a, **_k):
     raise _lib.CcError("cold_compress_b200 ops have no CPU implementation: the decode path is CUDA (sm_100a) only")
 
 
-for _name in ("decode_step", "key_norms", "prefill_gather", "rmsnorm_qkv_rope", "gemv_residual", "rmsnorm_ffn_gate"):
+for _name in ("decode_step", "key_norms", "prefill_gather", "prefill_attention", "rmsnorm_qkv_rope", "gemv_residual", "rmsnorm_ffn_gate"):
     _library.impl(_name, _no_cpu, "CPU")
 
 decode_step = torch.ops.cold_compress_b200.decode_step
 key_norms = torch.ops.cold_compress_b200.key_norms
 prefill_gather = torch.ops.cold_compress_b200.prefill_gather
+prefill_attention = torch.ops.cold_compress_b200.prefill_attention
 rmsnorm_qkv_rope = torch.ops.cold_compress_b200.rmsnorm_qkv_rope
 gemv_residual = torch.ops.cold_compress_b200.gemv_residual
 rmsnorm_ffn_gate = torch.ops.cold_compress_b200.rmsnorm_ffn_gate

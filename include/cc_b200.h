@@ -181,6 +181,48 @@ int cc_prefill_gather(const CcCacheState* state, const void* k_prompt, const voi
                       int32_t prompt_len, void* stream);
 
 /*
+ * Causal prompt attention on the tensor cores (tcgen05) with the reductions of the GQA-pooled
+ * probability map that prompt compression and the score-keeping caches consume, in one pass:
+ * the [Hq, S, S] attention map of the reference is never materialised.
+ * Replaces, in the prefill branch of Attention.forward (model.py:399-427):
+ *   scaled_dot_product_attention(q, k, v, causal mask, return_attn=True)   attention_utils.py:36-54
+ *   attn.view(1, Hkv, G, S, S).mean(2)                                     model.py:413-418
+ *   attn[:, :, -obs_len:, :].mean(2), attn.sum(2)                          prompt_compression.py:175, 192; cache.py:704
+ *   the sliding-window masses of KVCacheHybrid.build_masks                 cache.py:1066-1173
+ * q [Hkv*G, S, D], k / v [Hkv, S, D], y [Hkv*G, S, D]: bf16, D contiguous, row / head strides in ELEMENTS
+ * (multiples of 8), so the [S, H, D] layout the projections produce is taken as is.
+ * Outputs (fp32, the caller applies the reference's final bf16 roundings):
+ *   col_sum [Hkv, S]            sum over query rows i of pooled[h, i, j]        (NULL: attention only)
+ *   obs_sum [Hkv, S]            the same over the last obs_len query rows       (NULL or obs_len 0: skipped)
+ *   band_sum [n_windows, Hkv, S] sum over rows i with i - j < windows[w]        (n_windows 0: skipped)
+ * where pooled[h, i, j] = bf16(mean over the G query heads of bf16 softmax probabilities).
+ * attn_mode CC_ATTN_NAIVE_BF16 keeps the reference's naive-path roundings (bf16 after q.k, after *scale,
+ * after softmax); CC_ATTN_MATH_FP32 keeps fp32 logits (F.scaled_dot_product_attention semantics).
+ * workspace: device scratch of at least cc_prefill_attention_workspace(...) bytes when col_sum != NULL.
+ */
+typedef struct CcPrefillAttnArgs {
+    const void* q;  int64_t q_stride_s, q_stride_h;
+    const void* k;  int64_t k_stride_s, k_stride_h;
+    const void* v;  int64_t v_stride_s, v_stride_h;
+    void*       y;  int64_t y_stride_s, y_stride_h;
+    int32_t seq_len, n_kv_heads, q_per_kv, head_dim;
+    int32_t attn_mode;       /* CC_ATTN_*                                   */
+    int32_t obs_len;         /* SnapKV observation window (prompt_compression.py:157) */
+    int32_t n_windows;       /* 0..4                                        */
+    int32_t windows[4];      /* window sizes in tokens                      */
+    int32_t reserved0;
+    float*  col_sum;
+    float*  obs_sum;
+    float*  band_sum;
+    void*   workspace;
+    uint64_t workspace_bytes;
+} CcPrefillAttnArgs;
+
+uint64_t cc_prefill_attention_workspace(int32_t seq_len, int32_t n_kv_heads, int32_t q_per_kv,
+                                        int32_t obs_len, int32_t n_windows);
+int cc_prefill_attention(const CcPrefillAttnArgs* args, void* stream);
+
+/*
  * Tensor-parallel exchange fused into the projections (tp.py:134-138, 156-160: the all-reduce of the
  * row-parallel wo / w2 outputs).  Every rank owns an exchange buffer bf16 [n_ops][world][dim] and a flag
  * array i32 [n_ops][world] in peer-mapped (NVLink) memory.  A projection called with send_op >= 0 writes

