@@ -38,7 +38,7 @@ namespace {
 constexpr int BM = 128;                 // MMA rows of a query tile (G * QB, padded)
 constexpr int BN = 128;                 // keys per tile
 constexpr int ATOM_BYTES = 128 * 128;   // one 128-byte-swizzled sub-tile: 128 rows x 64 bf16
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 512;          // 16 warps: warp w owns TMEM lane quarter w % 4 and column quarter w / 4
 constexpr int MAX_WINDOWS = 4;
 constexpr int TMEM_COLS = 512;          // S0 [0,128) S1 [128,256) Y [256, 256 + D)
 constexpr float LOG2E = 1.4426950408889634f;
@@ -46,9 +46,9 @@ constexpr float LOG2E = 1.4426950408889634f;
 struct PrefillParams {
     __nv_bfloat16* y;
     long long y_stride_s, y_stride_h;   // elements
-    float* part_col;                    // [Hkv][n_qtiles][2][S_pad]
-    float* part_obs;                    // [Hkv][n_obs_tiles][2][S_pad]
-    float* part_band;                   // [n_windows][Hkv][n_qtiles][2][S_pad]
+    float* part_col;                    // [Hkv][n_qtiles][S_pad]
+    float* part_obs;                    // [Hkv][n_obs_tiles][S_pad]
+    float* part_band;                   // [n_windows][Hkv][n_qtiles][S_pad]
     int S, S_pad, Hkv, G, QB, n_qtiles;
     int obs_start;                      // first query row of the observation window (S = none)
     int first_obs_tile, n_obs_tiles, n_windows;
@@ -122,27 +122,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ float ex2(float x) {
     float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }
+// two fp32 -> packed bf16x2 (round to nearest even), and back
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+    uint32_t d; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo)); return d;
+}
+__device__ __forceinline__ float bf16x2_lo(uint32_t d) { return __uint_as_float(d << 16); }
+__device__ __forceinline__ float bf16x2_hi(uint32_t d) { return __uint_as_float(d & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&p);
 }
 
 // ------------------------------------------------------------------ the kernel
-// grid = n_qtiles * Hkv CTAs (longest query tiles first), 256 threads: thread (row = tid % 128, half = tid / 128)
-// owns columns [64*half, 64*half + 64) of its row of every S tile (its warp's TMEM lane quarter is row / 32).
+// grid = n_qtiles * Hkv CTAs (longest query tiles first), 512 threads: thread (row = tid % 128, cq = tid / 128)
+// owns columns [32*cq, 32*cq + 32) of its row of every S tile (its warp's TMEM lane quarter is row / 32).
 template <int D, bool NAIVE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 prefill_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const PrefillParams p) {
     constexpr int DH = D / 64;               // 64-column (128-byte) sub-tiles along the head dimension
     constexpr int TILE_BYTES = DH * ATOM_BYTES;
+    constexpr int NSTAT = 2 + MAX_WINDOWS;   // col, obs, bands
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[8];   // 0 q, 1-2 k[2], 3-4 v[2], 5-6 s[2], 7 pv
     __shared__ uint32_t s_tmem_base;
-    __shared__ float s_rowstat[2][BM][2];
+    __shared__ float s_rowstat[4][BM][2];
+    __shared__ float s_comb[NSTAT][4][BN];      // per-tile column partials of the four row quarters
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int row = tid & 127, half = tid >> 7;
+    const int row = tid & 127, cq = tid >> 7;
     const int h = blockIdx.x % p.Hkv;
     const int qt = p.n_qtiles - 1 - blockIdx.x / p.Hkv;
     const int i0 = qt * p.QB;
@@ -234,6 +242,24 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     float m_fin = 0.f, inv_s = 0.f;
     const float scale = p.scale;
 
+    // pooled-map reductions: thread (column cc, row quarter rq); partials of tile t are combined and written
+    // to the scratch during tile t + 1 (after its first barrier) so no extra barrier is needed
+    const int cc = tid & 127, rq = tid >> 7;
+    const float fG = (float)p.G, invG = 1.0f / (float)p.G;
+    const bool g_pow2 = (p.G & (p.G - 1)) == 0;
+    auto flush_stats = [&](int t) {   // threads < 128: column cc of key tile t
+        const int j = t * BN + cc;
+        const size_t slab = (size_t)p.S_pad;
+        p.part_col[((size_t)h * p.n_qtiles + qt) * slab + j] =
+            ((s_comb[0][0][cc] + s_comb[0][1][cc]) + s_comb[0][2][cc]) + s_comb[0][3][cc];
+        if (qt >= p.first_obs_tile)
+            p.part_obs[((size_t)h * p.n_obs_tiles + (qt - p.first_obs_tile)) * slab + j] =
+                ((s_comb[1][0][cc] + s_comb[1][1][cc]) + s_comb[1][2][cc]) + s_comb[1][3][cc];
+        for (int w = 0; w < p.n_windows; ++w)
+            p.part_band[(((size_t)w * p.Hkv + h) * p.n_qtiles + qt) * slab + j] =
+                ((s_comb[2 + w][0][cc] + s_comb[2 + w][1][cc]) + s_comb[2 + w][2][cc]) + s_comb[2 + w][3][cc];
+    };
+
     for (int n = 0; n < NT; ++n) {
         const int sweep2 = n >= T;
         const int t = sweep2 ? n - T : n;
@@ -246,66 +272,85 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         __syncwarp();
         mbar_wait_u32(BAR(5 + sb), (n >> 1) & 1);
         tc_fence_after();
-        uint32_t v0[32], v1[32];
-        tmem_ld32(tmem + lane_base + sb * BN + half * 64, v0);
-        tmem_ld32(tmem + lane_base + sb * BN + half * 64 + 32, v1);
+        uint32_t v0[32];
+        tmem_ld32(tmem + lane_base + sb * BN + cq * 32, v0);
         if (tid == 0 && n + 2 < NT) issue_k((n + 2) % T, sb);   // K[sb] is free: its MMA has completed
         __syncwarp();
 
-        const int kbase = t * BN + half * 64;
-        const bool need_mask = (t == T - 1);
-        float l[64];
+        // logits of this thread's 32 keys, with the reference's roundings
+        float l[32];
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
-            float x = __uint_as_float(c < 32 ? v0[c & 31] : v1[c & 31]);
-            if (NAIVE) x = bf16_round(bf16_round(x) * scale); else x = x * scale;
-            if (need_mask && kbase + c > qi) x = -INFINITY;
-            l[c] = x;
+        for (int c = 0; c < 32; c += 2) {
+            float x0 = __uint_as_float(v0[c]), x1 = __uint_as_float(v0[c + 1]);
+            if (NAIVE) {
+                const uint32_t d = cvt_bf16x2(x0, x1);                                   // bf16(q.k)
+                const uint32_t e = cvt_bf16x2(bf16x2_lo(d) * scale, bf16x2_hi(d) * scale);   // bf16(. * scale)
+                l[c] = bf16x2_lo(e);
+                l[c + 1] = bf16x2_hi(e);
+            } else {
+                l[c] = x0 * scale;
+                l[c + 1] = x1 * scale;
+            }
+        }
+        if (t == T - 1) {   // only the last key tile reaches past the diagonal
+            const int kbase = t * BN + cq * 32;
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                if (kbase + c > qi) l[c] = -INFINITY;
         }
         if (!sweep2) {
             float tmax = l[0];
 #pragma unroll
-            for (int c = 1; c < 64; ++c) tmax = fmaxf(tmax, l[c]);
+            for (int c = 1; c < 32; ++c) tmax = fmaxf(tmax, l[c]);
             const float m_new = fmaxf(m_run, tmax);
             if (m_new > -INFINITY) {
-                float acc = 0.f;
+                float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-                for (int c = 0; c < 64; ++c) acc += ex2((l[c] - m_new) * LOG2E);
-                s_run = s_run * ex2((m_run - m_new) * LOG2E) + acc;
+                for (int c = 0; c < 32; c += 2) {
+                    a0 += ex2((l[c] - m_new) * LOG2E);
+                    a1 += ex2((l[c + 1] - m_new) * LOG2E);
+                }
+                s_run = s_run * ex2((m_run - m_new) * LOG2E) + (a0 + a1);
                 m_run = m_new;
             }
-            if (n == T - 1) {   // merge the two column halves of every row
-                s_rowstat[half][row][0] = m_run;
-                s_rowstat[half][row][1] = s_run;
+            if (n == T - 1) {   // merge the four column quarters of every row
+                s_rowstat[cq][row][0] = m_run;
+                s_rowstat[cq][row][1] = s_run;
             }
             tc_fence_before();
             __syncthreads();
             if (n == T - 1) {
-                const float m0 = s_rowstat[0][row][0], s0 = s_rowstat[0][row][1];
-                const float m1 = s_rowstat[1][row][0], s1 = s_rowstat[1][row][1];
-                m_fin = fmaxf(m0, m1);   // finite: key 0 is visible to every query
-                const float tot = s0 * ex2((m0 - m_fin) * LOG2E) + s1 * ex2((m1 - m_fin) * LOG2E);
+                float mq[4], sq[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { mq[c] = s_rowstat[c][row][0]; sq[c] = s_rowstat[c][row][1]; }
+                m_fin = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));   // finite: key 0 is visible to every query
+                float tot = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) tot += sq[c] * ex2((mq[c] - m_fin) * LOG2E);
                 inv_s = 1.0f / tot;
             }
             continue;
         }
         // ---- sweep 2: P tile
-        uint32_t pk[32];
+        uint32_t pk[16];
 #pragma unroll
-        for (int c = 0; c < 64; c += 2) {
+        for (int c = 0; c < 32; c += 2) {
             const float p0 = ex2((l[c] - m_fin) * LOG2E) * inv_s;
             const float p1 = ex2((l[c + 1] - m_fin) * LOG2E) * inv_s;
-            pk[c >> 1] = pack_bf16(p0, p1);
+            pk[c >> 1] = cvt_bf16x2(p0, p1);
         }
         if (t > 0) mbar_wait_u32(BAR(7), (t - 1) & 1);   // P V of the previous tile done: sP and V[(t-1)&1] are free
         __syncthreads();                                  // everyone finished reading the previous P tile
         if (tid == 0 && t >= 1 && t + 1 < T) issue_v(t + 1, (t + 1) & 1);
+        if (p.stats && t > 0 && tid < BN) flush_stats(t - 1);
         {
-            uint8_t* prow = sP_ptr + half * ATOM_BYTES + row * 128;
+            uint8_t* prow = sP_ptr + (cq >> 1) * ATOM_BYTES + row * 128;
 #pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8)
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const int c8 = (cq & 1) * 4 + c4;
                 *reinterpret_cast<uint4*>(prow + ((c8 ^ (row & 7)) << 4)) =
-                    make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
+                    make_uint4(pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+            }
         }
         fence_proxy_async();
         tc_fence_before();
@@ -317,58 +362,61 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             mma_pv(t & 1, t == 0);
         }
         __syncwarp();
-        if (p.stats) {   // pooled column reductions: thread (column cc, row half hs)
-            const int cc = tid & 127, hs = tid >> 7;
+        if (p.stats) {
             const int j = t * BN + cc;
             const uint8_t* pcol = sP_ptr + (cc >> 6) * ATOM_BYTES + (cc & 7) * 2;
             const int chunk = (cc & 63) >> 3;
             float col = 0.f, obs = 0.f, band[MAX_WINDOWS] = {0.f, 0.f, 0.f, 0.f};
-            const int ib = hs * (p.QB >> 1), ie = ib + (p.QB >> 1);
-            const float fG = (float)p.G;
+            const int nq = p.QB >> 2;
+            const int ib = rq * nq, ie = min(ib + nq, p.S - i0);
             for (int i = ib; i < ie; ++i) {
                 const int q_i = i0 + i;
-                if (q_i >= p.S) break;
                 float sum = 0.f;
                 for (int gg = 0; gg < p.G; ++gg) {
                     const int r = gg * p.QB + i;
                     const uint16_t b = *reinterpret_cast<const uint16_t*>(pcol + r * 128 + ((chunk ^ (r & 7)) << 4));
                     sum += bf16_bits_to_float(b);
                 }
-                const float pooled = bf16_round(__fdiv_rn(sum, fG));
+                const float pooled = bf16_round(g_pow2 ? sum * invG : __fdiv_rn(sum, fG));
                 col += pooled;
                 if (q_i >= p.obs_start) obs += pooled;
+                if (p.n_windows) {
 #pragma unroll
-                for (int w = 0; w < MAX_WINDOWS; ++w)
-                    if (w < p.n_windows && q_i - j < p.windows[w]) band[w] += pooled;
+                    for (int w = 0; w < MAX_WINDOWS; ++w)
+                        if (w < p.n_windows && q_i - j < p.windows[w]) band[w] += pooled;
+                }
             }
-            const size_t slab = (size_t)p.S_pad;
-            p.part_col[(((size_t)h * p.n_qtiles + qt) * 2 + hs) * slab + j] = col;
-            if (qt >= p.first_obs_tile)
-                p.part_obs[(((size_t)h * p.n_obs_tiles + (qt - p.first_obs_tile)) * 2 + hs) * slab + j] = obs;
-            for (int w = 0; w < p.n_windows; ++w)
-                p.part_band[((((size_t)w * p.Hkv + h) * p.n_qtiles + qt) * 2 + hs) * slab + j] = band[w];
+            s_comb[0][rq][cc] = col;
+            s_comb[1][rq][cc] = obs;
+#pragma unroll
+            for (int w = 0; w < MAX_WINDOWS; ++w)
+                if (w < p.n_windows) s_comb[2 + w][rq][cc] = band[w];
         }
     }
 
     // ---- epilogue: Y (fp32 in TMEM) -> bf16 -> global
     mbar_wait_u32(BAR(7), (T - 1) & 1);
     tc_fence_after();
+    __syncthreads();   // the last tile's column partials are complete
+    if (p.stats && tid < BN) flush_stats(T - 1);
     {
-        constexpr int CPT = D / 2;   // columns per thread
+        constexpr int CPT = D / 4;   // columns per thread: 32 (D = 128) or 16 (D = 64)
         uint32_t y0[32];
-        __nv_bfloat16* yrow = p.y + (long long)(h * p.G + g) * p.y_stride_h + (long long)qi * p.y_stride_s + half * CPT;
+        __nv_bfloat16* yrow = p.y + (long long)(h * p.G + g) * p.y_stride_h + (long long)qi * p.y_stride_s + cq * CPT;
+        if (CPT == 32) {
+            tmem_ld32(tmem + lane_base + 2 * BN + cq * 32, y0);
+        } else {   // D = 64: column quarters of 16; load the enclosing 32 and keep one half
+            tmem_ld32(tmem + lane_base + 2 * BN + (cq >> 1) * 32, y0);
+        }
+        if (row_ok) {
+            const int off = (CPT == 32) ? 0 : (cq & 1) * 16;
 #pragma unroll
-        for (int part = 0; part < CPT / 32; ++part) {
-            tmem_ld32(tmem + lane_base + 2 * BN + half * CPT + part * 32, y0);
-            if (row_ok) {
-#pragma unroll
-                for (int c = 0; c < 32; c += 8) {
-                    uint4 o = make_uint4(pack_bf16(__uint_as_float(y0[c]), __uint_as_float(y0[c + 1])),
-                                         pack_bf16(__uint_as_float(y0[c + 2]), __uint_as_float(y0[c + 3])),
-                                         pack_bf16(__uint_as_float(y0[c + 4]), __uint_as_float(y0[c + 5])),
-                                         pack_bf16(__uint_as_float(y0[c + 6]), __uint_as_float(y0[c + 7])));
-                    *reinterpret_cast<uint4*>(yrow + part * 32 + c) = o;
-                }
+            for (int c = 0; c < CPT; c += 8) {
+                uint4 o = make_uint4(pack_bf16(__uint_as_float(y0[off + c]), __uint_as_float(y0[off + c + 1])),
+                                     pack_bf16(__uint_as_float(y0[off + c + 2]), __uint_as_float(y0[off + c + 3])),
+                                     pack_bf16(__uint_as_float(y0[off + c + 4]), __uint_as_float(y0[off + c + 5])),
+                                     pack_bf16(__uint_as_float(y0[off + c + 6]), __uint_as_float(y0[off + c + 7])));
+                *reinterpret_cast<uint4*>(yrow + c) = o;
             }
         }
     }
@@ -390,17 +438,13 @@ prefill_reduce_kernel(const PrefillParams p, float* __restrict__ col_sum, float*
     const int qt0 = j / p.QB;
     float acc = 0.f;
     for (int qt = qt0; qt < p.n_qtiles; ++qt) {
-        const float* a = p.part_col + (((size_t)h * p.n_qtiles + qt) * 2) * slab + j;
-        acc += a[0];
-        acc += a[slab];
+        acc += p.part_col[((size_t)h * p.n_qtiles + qt) * slab + j];
     }
     col_sum[(size_t)h * p.S + j] = acc;
     if (obs_sum) {
         float o = 0.f;
         for (int qt = max(qt0, p.first_obs_tile); qt < p.n_qtiles; ++qt) {
-            const float* a = p.part_obs + (((size_t)h * p.n_obs_tiles + (qt - p.first_obs_tile)) * 2) * slab + j;
-            o += a[0];
-            o += a[slab];
+            o += p.part_obs[((size_t)h * p.n_obs_tiles + (qt - p.first_obs_tile)) * slab + j];
         }
         obs_sum[(size_t)h * p.S + j] = o;
     }
@@ -408,9 +452,7 @@ prefill_reduce_kernel(const PrefillParams p, float* __restrict__ col_sum, float*
         const int qt1 = min(p.n_qtiles - 1, (j + p.windows[w] - 1) / p.QB);   // later query tiles are outside the band
         float b = 0.f;
         for (int qt = qt0; qt <= qt1; ++qt) {
-            const float* a = p.part_band + ((((size_t)w * p.Hkv + h) * p.n_qtiles + qt) * 2) * slab + j;
-            b += a[0];
-            b += a[slab];
+            b += p.part_band[(((size_t)w * p.Hkv + h) * p.n_qtiles + qt) * slab + j];
         }
         band_sum[((size_t)w * p.Hkv + h) * p.S + j] = b;
     }
@@ -474,8 +516,8 @@ Plan make_plan(int S, int Hkv, int G, int obs_len, int n_windows) {
     const int obs = obs_len > S ? S : obs_len;
     pl.first_obs_tile = obs > 0 ? (S - obs) / pl.QB : pl.n_qtiles;
     pl.n_obs_tiles = pl.n_qtiles - pl.first_obs_tile;
-    pl.col_floats = (size_t)Hkv * pl.n_qtiles * 2 * pl.S_pad;
-    pl.obs_floats = (size_t)Hkv * pl.n_obs_tiles * 2 * pl.S_pad;
+    pl.col_floats = (size_t)Hkv * pl.n_qtiles * pl.S_pad;
+    pl.obs_floats = (size_t)Hkv * pl.n_obs_tiles * pl.S_pad;
     pl.band_floats = (size_t)n_windows * pl.col_floats;
     return pl;
 }
