@@ -133,6 +133,114 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&p);
 }
 
+// Sum v[0..7] over the 32 lanes of a warp; every lane returns the total of column
+// 4 * bit4(lane) + 2 * bit3(lane) + bit2(lane)  (transpose-reduce: 4 + 2 + 1 + 1 + 1 shuffles).
+__device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    float w[4], x[2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float keep = b4 ? v[c + 4] : v[c], send = b4 ? v[c] : v[c + 4];
+        w[c] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const float keep = b3 ? w[c + 2] : w[c], send = b3 ? w[c] : w[c + 2];
+        x[c] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    float y = (b2 ? x[1] : x[0]) + __shfl_xor_sync(0xffffffffu, b2 ? x[0] : x[1], 4);
+    y += __shfl_xor_sync(0xffffffffu, y, 2);
+    y += __shfl_xor_sync(0xffffffffu, y, 1);
+    return y;
+}
+__device__ __forceinline__ int warp_reduce8_column(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
+
+// Reductions of the GQA-pooled probabilities of one P tile (128 rows = (head g, query i) x 128 keys, bf16, the
+// swizzled A-operand layout in shared memory).  Warp `ck` owns the 8 key columns of 16-byte chunk ck; lane l reads
+// rows l, l + 32, l + 64, l + 96 (one LDS.128 each), pools over the heads (model.py:413-418), and the warp adds the
+// pooled values over the query rows.  QBL = log2(query rows per tile); row = g * QB + i.
+template <int QBL>
+__device__ __forceinline__ void tile_stats(const uint8_t* sP_ptr, float (*s_comb)[BN], const PrefillParams& p, int ck,
+                                           int lane, int i0, int jbase, bool want_obs) {
+    constexpr int QB = 1 << QBL;
+    constexpr int NI = QB >= 32 ? QB / 32 : 1;   // query rows held by one lane
+    constexpr int NK = 4 / NI;                   // heads per query row held by one lane
+    const uint8_t* base = sP_ptr + (ck >> 3) * ATOM_BYTES + lane * 128 + (((ck & 7) ^ (lane & 7)) << 4);
+    float col[8], obs[8], band[MAX_WINDOWS][8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        col[c] = 0.f; obs[c] = 0.f;
+#pragma unroll
+        for (int w = 0; w < MAX_WINDOWS; ++w) band[w][c] = 0.f;
+    }
+    const float fG = (float)p.G, invG = 1.0f / (float)p.G;
+    const bool g_pow2 = (p.G & (p.G - 1)) == 0;
+#pragma unroll
+    for (int ii = 0; ii < NI; ++ii) {
+        float sum[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) sum[c] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < NK; ++kk) {
+            const int k = ii + NI * kk;                                  // row = lane + 32 k (same swizzle phase)
+            const int g = QB >= 32 ? kk : 2 * kk + (lane >> 4);          // QB = 16: rows l + 32 k hold heads 2k, 2k + 1
+            const uint4 u = *reinterpret_cast<const uint4*>(base + k * 32 * 128);
+            if (g < p.G) {
+                sum[0] += bf16x2_lo(u.x); sum[1] += bf16x2_hi(u.x); sum[2] += bf16x2_lo(u.y); sum[3] += bf16x2_hi(u.y);
+                sum[4] += bf16x2_lo(u.z); sum[5] += bf16x2_hi(u.z); sum[6] += bf16x2_lo(u.w); sum[7] += bf16x2_hi(u.w);
+            }
+        }
+        if (QB < 32) {   // the other half of the heads sits 16 lanes away
+#pragma unroll
+            for (int c = 0; c < 8; ++c) sum[c] += __shfl_xor_sync(0xffffffffu, sum[c], 16);
+        }
+        const int i = QB >= 32 ? lane + 32 * ii : (lane & (QB - 1));
+        const int q_i = i0 + i;
+        const bool counted = (q_i < p.S) && (QB >= 32 || lane < QB);   // QB = 16: lanes 16..31 hold duplicates
+        float pooled[8];
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+            const float a = g_pow2 ? sum[c] * invG : __fdiv_rn(sum[c], fG);
+            const float b = g_pow2 ? sum[c + 1] * invG : __fdiv_rn(sum[c + 1], fG);
+            const uint32_t d = cvt_bf16x2(a, b);
+            pooled[c] = counted ? bf16x2_lo(d) : 0.f;
+            pooled[c + 1] = counted ? bf16x2_hi(d) : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) col[c] += pooled[c];
+        if (want_obs && q_i >= p.obs_start) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) obs[c] += pooled[c];
+        }
+        if (p.n_windows) {
+#pragma unroll
+            for (int w = 0; w < MAX_WINDOWS; ++w) {
+                if (w < p.n_windows) {
+                    const int lim = q_i - jbase - p.windows[w];   // column c is inside the band iff c > lim
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (c > lim) band[w][c] += pooled[c];
+                }
+            }
+        }
+    }
+    const int oc = ck * 8 + warp_reduce8_column(lane);
+    const bool writer = (lane & 3) == 0;
+    float r = warp_reduce8(col, lane);
+    if (writer) s_comb[0][oc] = r;
+    if (want_obs) {
+        r = warp_reduce8(obs, lane);
+        if (writer) s_comb[1][oc] = r;
+    }
+#pragma unroll
+    for (int w = 0; w < MAX_WINDOWS; ++w) {
+        if (w < p.n_windows) {
+            r = warp_reduce8(band[w], lane);
+            if (writer) s_comb[2 + w][oc] = r;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ the kernel
 // grid = n_qtiles * Hkv CTAs (longest query tiles first), 512 threads: thread (row = tid % 128, cq = tid / 128)
 // owns columns [32*cq, 32*cq + 32) of its row of every S tile (its warp's TMEM lane quarter is row / 32).
@@ -147,7 +255,7 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     __shared__ __align__(8) uint64_t bars[8];   // 0 q, 1-2 k[2], 3-4 v[2], 5-6 s[2], 7 pv
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_rowstat[4][BM][2];
-    __shared__ float s_comb[NSTAT][4][BN];      // per-tile column partials of the four row quarters
+    __shared__ float s_comb[NSTAT][BN];         // per-tile column sums, written to the scratch one tile later
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row = tid & 127, cq = tid >> 7;
@@ -242,22 +350,17 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     float m_fin = 0.f, inv_s = 0.f;
     const float scale = p.scale;
 
-    // pooled-map reductions: thread (column cc, row quarter rq); partials of tile t are combined and written
-    // to the scratch during tile t + 1 (after its first barrier) so no extra barrier is needed
-    const int cc = tid & 127, rq = tid >> 7;
-    const float fG = (float)p.G, invG = 1.0f / (float)p.G;
-    const bool g_pow2 = (p.G & (p.G - 1)) == 0;
+    // pooled-map reductions: warp = 16-byte chunk of key columns (tile_stats); the sums of tile t are written to the
+    // scratch during tile t + 1 (after its first barrier) so no extra barrier is needed
+    const int cc = tid & 127, lane = tid & 31;
+    const bool want_obs = qt >= p.first_obs_tile;
     auto flush_stats = [&](int t) {   // threads < 128: column cc of key tile t
         const int j = t * BN + cc;
         const size_t slab = (size_t)p.S_pad;
-        p.part_col[((size_t)h * p.n_qtiles + qt) * slab + j] =
-            ((s_comb[0][0][cc] + s_comb[0][1][cc]) + s_comb[0][2][cc]) + s_comb[0][3][cc];
-        if (qt >= p.first_obs_tile)
-            p.part_obs[((size_t)h * p.n_obs_tiles + (qt - p.first_obs_tile)) * slab + j] =
-                ((s_comb[1][0][cc] + s_comb[1][1][cc]) + s_comb[1][2][cc]) + s_comb[1][3][cc];
+        p.part_col[((size_t)h * p.n_qtiles + qt) * slab + j] = s_comb[0][cc];
+        if (want_obs) p.part_obs[((size_t)h * p.n_obs_tiles + (qt - p.first_obs_tile)) * slab + j] = s_comb[1][cc];
         for (int w = 0; w < p.n_windows; ++w)
-            p.part_band[(((size_t)w * p.Hkv + h) * p.n_qtiles + qt) * slab + j] =
-                ((s_comb[2 + w][0][cc] + s_comb[2 + w][1][cc]) + s_comb[2 + w][2][cc]) + s_comb[2 + w][3][cc];
+            p.part_band[(((size_t)w * p.Hkv + h) * p.n_qtiles + qt) * slab + j] = s_comb[2 + w][cc];
     };
 
     for (int n = 0; n < NT; ++n) {
@@ -363,34 +466,13 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         __syncwarp();
         if (p.stats) {
-            const int j = t * BN + cc;
-            const uint8_t* pcol = sP_ptr + (cc >> 6) * ATOM_BYTES + (cc & 7) * 2;
-            const int chunk = (cc & 63) >> 3;
-            float col = 0.f, obs = 0.f, band[MAX_WINDOWS] = {0.f, 0.f, 0.f, 0.f};
-            const int nq = p.QB >> 2;
-            const int ib = rq * nq, ie = min(ib + nq, p.S - i0);
-            for (int i = ib; i < ie; ++i) {
-                const int q_i = i0 + i;
-                float sum = 0.f;
-                for (int gg = 0; gg < p.G; ++gg) {
-                    const int r = gg * p.QB + i;
-                    const uint16_t b = *reinterpret_cast<const uint16_t*>(pcol + r * 128 + ((chunk ^ (r & 7)) << 4));
-                    sum += bf16_bits_to_float(b);
-                }
-                const float pooled = bf16_round(g_pow2 ? sum * invG : __fdiv_rn(sum, fG));
-                col += pooled;
-                if (q_i >= p.obs_start) obs += pooled;
-                if (p.n_windows) {
-#pragma unroll
-                    for (int w = 0; w < MAX_WINDOWS; ++w)
-                        if (w < p.n_windows && q_i - j < p.windows[w]) band[w] += pooled;
-                }
+            const int jbase = t * BN + warp * 8;
+            switch (p.QB) {
+                case 128: tile_stats<7>(sP_ptr, s_comb, p, warp, lane, i0, jbase, want_obs); break;
+                case 64:  tile_stats<6>(sP_ptr, s_comb, p, warp, lane, i0, jbase, want_obs); break;
+                case 32:  tile_stats<5>(sP_ptr, s_comb, p, warp, lane, i0, jbase, want_obs); break;
+                default:  tile_stats<4>(sP_ptr, s_comb, p, warp, lane, i0, jbase, want_obs); break;
             }
-            s_comb[0][rq][cc] = col;
-            s_comb[1][rq][cc] = obs;
-#pragma unroll
-            for (int w = 0; w < MAX_WINDOWS; ++w)
-                if (w < p.n_windows) s_comb[2 + w][rq][cc] = band[w];
         }
     }
 
@@ -540,7 +622,7 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
 }  // namespace
 
 unsigned long long prefill_attention_workspace_impl(int S, int Hkv, int G, int obs_len, int n_windows) {
-    if (S <= 0 || Hkv <= 0 || G <= 0 || G > 16 || n_windows < 0 || n_windows > MAX_WINDOWS) return 0;
+    if (S <= 0 || Hkv <= 0 || G <= 0 || G > 8 || n_windows < 0 || n_windows > MAX_WINDOWS) return 0;
     const Plan pl = make_plan(S, Hkv, G, obs_len, n_windows);
     return (uint64_t)(pl.col_floats + pl.obs_floats + pl.band_floats) * sizeof(float) + 256;
 }
@@ -549,8 +631,8 @@ int prefill_attention_impl(const CcPrefillAttnArgs* a, cudaStream_t stream) {
     if (!a || !a->q || !a->k || !a->v || !a->y) return set_error(CC_ERR_INVALID_ARG, "cc_prefill_attention: null argument");
     const int S = a->seq_len, Hkv = a->n_kv_heads, G = a->q_per_kv, D = a->head_dim;
     if (S <= 0 || Hkv <= 0) return set_error(CC_ERR_INVALID_ARG, "cc_prefill_attention: empty problem");
-    if ((D != 64 && D != 128) || G < 1 || G > 16)
-        return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_prefill_attention: head_dim must be 64 or 128 and q_per_kv <= 16");
+    if ((D != 64 && D != 128) || G < 1 || G > 8)
+        return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_prefill_attention: head_dim must be 64 or 128 and q_per_kv <= 8");
     if (a->n_windows < 0 || a->n_windows > MAX_WINDOWS)
         return set_error(CC_ERR_INVALID_ARG, "cc_prefill_attention: at most 4 band windows");
     if (a->attn_mode != CC_ATTN_NAIVE_BF16 && a->attn_mode != CC_ATTN_MATH_FP32)
