@@ -126,6 +126,10 @@ __device__ __forceinline__ float ex2(float x) {
 __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
     uint32_t d; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo)); return d;
 }
+// fp32 value of bf16(x): the high half of the packed pair {x, 0}
+__device__ __forceinline__ float round_bf16(float x) {
+    uint32_t d; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(x), "f"(0.0f)); return __uint_as_float(d);
+}
 __device__ __forceinline__ float bf16x2_lo(uint32_t d) { return __uint_as_float(d << 16); }
 __device__ __forceinline__ float bf16x2_hi(uint32_t d) { return __uint_as_float(d & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -380,20 +384,13 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         if (tid == 0 && n + 2 < NT) issue_k((n + 2) % T, sb);   // K[sb] is free: its MMA has completed
         __syncwarp();
 
-        // logits of this thread's 32 keys, with the reference's roundings
+        // logits of this thread's 32 keys, with the reference's roundings.  round_bf16 = cvt.rn.bf16x2.f32 {x, 0}:
+        // the packed result with a zero low half IS the fp32 value of bf16(x), one instruction per rounding
         float l[32];
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-            float x0 = __uint_as_float(v0[c]), x1 = __uint_as_float(v0[c + 1]);
-            if (NAIVE) {
-                const uint32_t d = cvt_bf16x2(x0, x1);                                   // bf16(q.k)
-                const uint32_t e = cvt_bf16x2(bf16x2_lo(d) * scale, bf16x2_hi(d) * scale);   // bf16(. * scale)
-                l[c] = bf16x2_lo(e);
-                l[c + 1] = bf16x2_hi(e);
-            } else {
-                l[c] = x0 * scale;
-                l[c + 1] = x1 * scale;
-            }
+        for (int c = 0; c < 32; ++c) {
+            const float x = __uint_as_float(v0[c]);
+            l[c] = NAIVE ? round_bf16(round_bf16(x) * scale) : x * scale;
         }
         if (t == T - 1) {   // only the last key tile reaches past the diagonal
             const int kbase = t * BN + cq * 32;
