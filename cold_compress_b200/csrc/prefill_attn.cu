@@ -36,11 +36,12 @@ namespace cc {
 namespace {
 
 constexpr int BM = 128;                 // MMA rows of a query tile (G * QB, padded)
-constexpr int BN = 128;                 // keys per tile
+constexpr int BN = 128;                 // keys per tile visit of a CTA ...
+constexpr int BNH = 64;                 // ... split between the two key-half groups of 8 warps
 constexpr int ATOM_BYTES = 128 * 128;   // one 128-byte-swizzled sub-tile: 128 rows x 64 bf16
 constexpr int NTHREADS = 512;          // 16 warps: warp w owns TMEM lane quarter w % 4 and column quarter w / 4
 constexpr int MAX_WINDOWS = 4;
-constexpr int TMEM_COLS = 512;          // S0 [0,128) S1 [128,256) Y [256, 256 + D)
+constexpr int TMEM_COLS = 512;          // group g: S[b] at 128 g + 64 b, Y at 256 + 128 g
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct PrefillParams {
@@ -159,17 +160,17 @@ __device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
 }
 __device__ __forceinline__ int warp_reduce8_column(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
 
-// Reductions of the GQA-pooled probabilities of one P tile (128 rows = (head g, query i) x 128 keys, bf16, the
-// swizzled A-operand layout in shared memory).  Warp `ck` owns the 8 key columns of 16-byte chunk ck; lane l reads
+// Reductions of the GQA-pooled probabilities of one P tile (128 rows = (head g, query i) x 64 keys, bf16, the
+// swizzled A-operand layout in shared memory).  Warp `ck` (0..7) owns the 8 key columns of 16-byte chunk ck; lane l reads
 // rows l, l + 32, l + 64, l + 96 (one LDS.128 each), pools over the heads (model.py:413-418), and the warp adds the
 // pooled values over the query rows.  QBL = log2(query rows per tile); row = g * QB + i.
 template <int QBL>
-__device__ __forceinline__ void tile_stats(const uint8_t* sP_ptr, float (*s_comb)[BN], const PrefillParams& p, int ck,
+__device__ __forceinline__ void tile_stats(const uint8_t* sP_ptr, float (*s_comb)[BNH], const PrefillParams& p, int ck,
                                            int lane, int i0, int jbase, bool want_obs) {
     constexpr int QB = 1 << QBL;
     constexpr int NI = QB >= 32 ? QB / 32 : 1;   // query rows held by one lane
     constexpr int NK = 4 / NI;                   // heads per query row held by one lane
-    const uint8_t* base = sP_ptr + (ck >> 3) * ATOM_BYTES + lane * 128 + (((ck & 7) ^ (lane & 7)) << 4);
+    const uint8_t* base = sP_ptr + lane * 128 + ((ck ^ (lane & 7)) << 4);
     float col[8], obs[8], band[MAX_WINDOWS][8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -246,36 +247,54 @@ __device__ __forceinline__ void tile_stats(const uint8_t* sP_ptr, float (*s_comb
 }
 
 // ------------------------------------------------------------------ the kernel
-// grid = n_qtiles * Hkv CTAs (longest query tiles first), 512 threads: thread (row = tid % 128, cq = tid / 128)
-// owns columns [32*cq, 32*cq + 32) of its row of every S tile (its warp's TMEM lane quarter is row / 32).
+// grid = n_qtiles * Hkv CTAs (longest query tiles first), 512 threads = two independent KEY-HALF GROUPS of 8 warps.
+// Group g walks the 64-key blocks [128 t + 64 g, +64) of the keys this query block can see, with its own K/V ring,
+// S accumulators, P tile, Y accumulator and barriers, so the two groups drift out of phase and one group's
+// MUFU-bound softmax overlaps the other's rounding / store / reduction phases.  In a group, thread
+// (row = t % 128, ch = t / 128) owns keys [32 ch, 32 ch + 32) of its row of every S block (TMEM lane quarter row / 32).
+// The partial accumulators Y_0 + Y_1 are added in the epilogue (fixed order: bit-reproducible).
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 256;" :: "r"(grp + 1) : "memory"); }
+
 template <int D, bool NAIVE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 prefill_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const PrefillParams p) {
-    constexpr int DH = D / 64;               // 64-column (128-byte) sub-tiles along the head dimension
-    constexpr int TILE_BYTES = DH * ATOM_BYTES;
-    constexpr int NSTAT = 2 + MAX_WINDOWS;   // col, obs, bands
+    constexpr int DH = D / 64;                  // 64-column (128-byte) sub-tiles along the head dimension
+    constexpr int Q_BYTES = DH * ATOM_BYTES;    // Q tile: 128 rows
+    constexpr int HALF_ATOM = BNH * 128;        // 64 rows x 128 bytes
+    constexpr int KV_BYTES = DH * HALF_ATOM;    // one K or V block of a group: 64 keys x D
+    constexpr int GROUP_BYTES = 4 * KV_BYTES + ATOM_BYTES;   // K[2], V[2], P (128 rows x 64 keys)
+    constexpr int NSTAT = 2 + MAX_WINDOWS;      // col, obs, bands
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[8];   // 0 q, 1-2 k[2], 3-4 v[2], 5-6 s[2], 7 pv
+    __shared__ __align__(8) uint64_t bars[16];  // 0 q; group g at 1 + 7 g: k[2], v[2], s[2], pv
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_rowstat[4][BM][2];
-    __shared__ float s_comb[NSTAT][BN];         // per-tile column sums, written to the scratch one tile later
+    __shared__ float s_comb[2][NSTAT][BNH];     // per-block column sums of each group, flushed one block later
 
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int row = tid & 127, cq = tid >> 7;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = tid >> 8, gt = tid & 255, gwarp = gt >> 5;
+    const int row = gt & 127, ch = gt >> 7;
     const int h = blockIdx.x % p.Hkv;
     const int qt = p.n_qtiles - 1 - blockIdx.x / p.Hkv;
     const int i0 = qt * p.QB;
-    const int T = (min(i0 + p.QB, p.S) + BN - 1) / BN;   // key tiles this query block can see
+    const int lim = min(i0 + p.QB, p.S);                        // keys [0, lim) are visible to this query block
+    const int T = max(0, (lim - BNH * grp + BN - 1) / BN);      // 64-key blocks of this group
+    const int T_other = max(0, (lim - BNH * (1 - grp) + BN - 1) / BN);
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sQ = smem_base, sK = sQ + TILE_BYTES, sV = sK + 2 * TILE_BYTES, sP = sV + 2 * TILE_BYTES;
+    const uint32_t sQ = smem_base;
+    const uint32_t sG = sQ + Q_BYTES + grp * GROUP_BYTES;
+    const uint32_t sK = sG, sV = sG + 2 * KV_BYTES, sP = sG + 4 * KV_BYTES;
     uint8_t* const sP_ptr = smem_raw + (sP - smem_u32(smem_raw));
     const uint32_t bar0 = smem_u32(bars);
-    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    const uint32_t BAR_Q = bar0, bG = bar0 + 8u * (1 + 7 * grp);
+    auto BAR_K = [&](int b) { return bG + 8u * b; };
+    auto BAR_V = [&](int b) { return bG + 8u * (2 + b); };
+    auto BAR_S = [&](int b) { return bG + 8u * (4 + b); };
+    const uint32_t BAR_PV = bG + 8u * 6;
 
     if (tid == 0) {
-        for (int i = 0; i < 8; ++i) mbar_init_u32(BAR(i), 1);
+        for (int i = 0; i < 15; ++i) mbar_init_u32(bar0 + 8u * i, 1);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -285,7 +304,7 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     }
     if (p.G * p.QB < BM) {   // rows the Q box does not cover: zero them once (they only feed unused S rows)
         uint4* q4 = reinterpret_cast<uint4*>(smem_raw + (sQ - smem_u32(smem_raw)));
-        for (int i = tid; i < TILE_BYTES / 16; i += NTHREADS) q4[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < Q_BYTES / 16; i += NTHREADS) q4[i] = make_uint4(0, 0, 0, 0);
         fence_proxy_async();
     }
     tc_fence_before();
@@ -293,145 +312,146 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     tc_fence_after();
     const uint32_t tmem = s_tmem_base;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + grp * 128, tY = tmem + 256 + grp * 128;
 
-    constexpr uint32_t IDESC_S = make_idesc(BM, BN, false);
+    constexpr uint32_t IDESC_S = make_idesc(BM, BNH, false);
     constexpr uint32_t IDESC_PV = make_idesc(BM, D, true);
 
-    auto issue_k = [&](int tile, int buf) {
-        mbar_expect_tx_u32(BAR(1 + buf), TILE_BYTES);
+    auto issue_k = [&](int blk, int buf) {
+        mbar_expect_tx_u32(BAR_K(buf), KV_BYTES);
 #pragma unroll
         for (int dh = 0; dh < DH; ++dh)
-            tma_load_3d(sK + buf * TILE_BYTES + dh * ATOM_BYTES, &tm_k, dh * 64, tile * BN, h, BAR(1 + buf));
+            tma_load_3d(sK + buf * KV_BYTES + dh * HALF_ATOM, &tm_k, dh * 64, blk * BN + grp * BNH, h, BAR_K(buf));
     };
-    auto issue_v = [&](int tile, int buf) {
-        mbar_expect_tx_u32(BAR(3 + buf), TILE_BYTES);
+    auto issue_v = [&](int blk, int buf) {
+        mbar_expect_tx_u32(BAR_V(buf), KV_BYTES);
 #pragma unroll
         for (int dh = 0; dh < DH; ++dh)
-            tma_load_3d(sV + buf * TILE_BYTES + dh * ATOM_BYTES, &tm_v, dh * 64, tile * BN, h, BAR(3 + buf));
+            tma_load_3d(sV + buf * KV_BYTES + dh * HALF_ATOM, &tm_v, dh * 64, blk * BN + grp * BNH, h, BAR_V(buf));
     };
-    // S[buf] = Q K_buf^T : D/16 MMAs of K = 16
+    // S[buf] = Q K_buf^T : [128 x 64], D/16 MMAs of K = 16
     auto mma_s = [&](int buf) {
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
-            const uint32_t off = (k >> 2) * ATOM_BYTES + (k & 3) * 32;
-            umma_bf16(tmem + buf * BN, smem_desc(sQ + off, 16, 1024), smem_desc(sK + buf * TILE_BYTES + off, 16, 1024),
-                      IDESC_S, k > 0);
+            const uint32_t koff = (k & 3) * 32;
+            umma_bf16(tS + buf * BNH, smem_desc(sQ + (k >> 2) * ATOM_BYTES + koff, 16, 1024),
+                      smem_desc(sK + buf * KV_BYTES + (k >> 2) * HALF_ATOM + koff, 16, 1024), IDESC_S, k > 0);
         }
-        umma_commit(BAR(5 + buf));
+        umma_commit(BAR_S(buf));
     };
-    // Y (+)= P V_buf : BN/16 MMAs; V is [key][d] in shared memory = MN-major B operand
+    // Y (+)= P V_buf : 64 keys = 4 MMAs; V is [key][d] in shared memory = MN-major B operand
     auto mma_pv = [&](int buf, bool first) {
 #pragma unroll
-        for (int k = 0; k < BN / 16; ++k) {
-            const uint32_t aoff = (k >> 2) * ATOM_BYTES + (k & 3) * 32;
-            umma_bf16(tmem + 2 * BN, smem_desc(sP + aoff, 16, 1024),
-                      smem_desc(sV + buf * TILE_BYTES + k * 2048, ATOM_BYTES, 1024), IDESC_PV, !(first && k == 0));
-        }
-        umma_commit(BAR(7));
+        for (int k = 0; k < BNH / 16; ++k)
+            umma_bf16(tY, smem_desc(sP + k * 32, 16, 1024), smem_desc(sV + buf * KV_BYTES + k * 2048, HALF_ATOM, 1024),
+                      IDESC_PV, !(first && k == 0));
+        umma_commit(BAR_PV);
     };
 
-    const int NT = 2 * T;   // tile visits: sweep 1 then sweep 2
+    const int NT = 2 * T;   // block visits of this group: sweep 1 then sweep 2
     if (tid == 0) {
-        mbar_expect_tx_u32(BAR(0), (uint32_t)(DH * p.G * p.QB * 128));
+        mbar_expect_tx_u32(BAR_Q, (uint32_t)(DH * p.G * p.QB * 128));
 #pragma unroll
-        for (int dh = 0; dh < DH; ++dh) tma_load_3d(sQ + dh * ATOM_BYTES, &tm_q, dh * 64, i0, h * p.G, BAR(0));
+        for (int dh = 0; dh < DH; ++dh) tma_load_3d(sQ + dh * ATOM_BYTES, &tm_q, dh * 64, i0, h * p.G, BAR_Q);
+    }
+    if (gt == 0 && T > 0) {
         issue_k(0, 0);
-        issue_k(1 % T, 1);          // NT >= 2 always
+        issue_k(1 % T, 1);
         issue_v(0, 0);
         if (T > 1) issue_v(1, 1);
-        mbar_wait_u32(BAR(0), 0);
-        mbar_wait_u32(BAR(1), 0);
+        mbar_wait_u32(BAR_Q, 0);
+        mbar_wait_u32(BAR_K(0), 0);
         tc_fence_after();
         mma_s(0);
     }
     __syncwarp();
 
     // this thread's row
-    const int g = row / p.QB, il = row % p.QB;
-    const int qi = i0 + il;
-    const bool row_ok = (g < p.G) && (qi < p.S);
+    const int qi = i0 + row % p.QB;
     float m_run = -INFINITY, s_run = 0.f;
     float m_fin = 0.f, inv_s = 0.f;
     const float scale = p.scale;
 
-    // pooled-map reductions: warp = 16-byte chunk of key columns (tile_stats); the sums of tile t are written to the
-    // scratch during tile t + 1 (after its first barrier) so no extra barrier is needed
-    const int cc = tid & 127, lane = tid & 31;
+    // pooled-map reductions: warp = 16-byte chunk of key columns (tile_stats); the sums of block t are written to the
+    // scratch during block t + 1 (after its first barrier) so no extra barrier is needed
     const bool want_obs = qt >= p.first_obs_tile;
-    auto flush_stats = [&](int t) {   // threads < 128: column cc of key tile t
-        const int j = t * BN + cc;
+    auto flush_stats = [&](int t) {   // group threads < 64: one key column of block t
+        const int j = t * BN + grp * BNH + gt;
         const size_t slab = (size_t)p.S_pad;
-        p.part_col[((size_t)h * p.n_qtiles + qt) * slab + j] = s_comb[0][cc];
-        if (want_obs) p.part_obs[((size_t)h * p.n_obs_tiles + (qt - p.first_obs_tile)) * slab + j] = s_comb[1][cc];
+        p.part_col[((size_t)h * p.n_qtiles + qt) * slab + j] = s_comb[grp][0][gt];
+        if (want_obs) p.part_obs[((size_t)h * p.n_obs_tiles + (qt - p.first_obs_tile)) * slab + j] = s_comb[grp][1][gt];
         for (int w = 0; w < p.n_windows; ++w)
-            p.part_band[(((size_t)w * p.Hkv + h) * p.n_qtiles + qt) * slab + j] = s_comb[2 + w][cc];
+            p.part_band[(((size_t)w * p.Hkv + h) * p.n_qtiles + qt) * slab + j] = s_comb[grp][2 + w][gt];
     };
 
-    for (int n = 0; n < NT; ++n) {
-        const int sweep2 = n >= T;
-        const int t = sweep2 ? n - T : n;
+    // one block visit up to the logits: l[c] = logit of key (block t, 32 ch + c), -inf past the diagonal
+    auto visit = [&](int n, int t, float (&l)[32]) {
         const int sb = n & 1;
-        if (tid == 0 && n + 1 < NT) {   // next tile's logits under this tile's softmax
-            mbar_wait_u32(BAR(1 + ((n + 1) & 1)), ((n + 1) >> 1) & 1);
+        if (gt == 0 && n + 1 < NT) {   // next block's logits under this block's softmax
+            mbar_wait_u32(BAR_K((n + 1) & 1), ((n + 1) >> 1) & 1);
             tc_fence_after();
             mma_s((n + 1) & 1);
         }
         __syncwarp();
-        mbar_wait_u32(BAR(5 + sb), (n >> 1) & 1);
+        mbar_wait_u32(BAR_S(sb), (n >> 1) & 1);
         tc_fence_after();
         uint32_t v0[32];
-        tmem_ld32(tmem + lane_base + sb * BN + cq * 32, v0);
-        if (tid == 0 && n + 2 < NT) issue_k((n + 2) % T, sb);   // K[sb] is free: its MMA has completed
+        tmem_ld32(tS + lane_base + sb * BNH + ch * 32, v0);
+        if (gt == 0 && n + 2 < NT) issue_k((n + 2) % T, sb);   // K[sb] is free: its MMA has completed
         __syncwarp();
-
-        // logits of this thread's 32 keys, with the reference's roundings.  round_bf16 = cvt.rn.bf16x2.f32 {x, 0}:
-        // the packed result with a zero low half IS the fp32 value of bf16(x), one instruction per rounding
-        float l[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
             const float x = __uint_as_float(v0[c]);
             l[c] = NAIVE ? round_bf16(round_bf16(x) * scale) : x * scale;
         }
-        if (t == T - 1) {   // only the last key tile reaches past the diagonal
-            const int kbase = t * BN + cq * 32;
+        if (t * BN + grp * BNH + BNH - 1 > i0) {   // the block reaches past the diagonal for some row
+            const int kbase = t * BN + grp * BNH + ch * 32;
 #pragma unroll
             for (int c = 0; c < 32; ++c)
                 if (kbase + c > qi) l[c] = -INFINITY;
         }
-        if (!sweep2) {
-            float tmax = l[0];
+    };
+
+    // ---- sweep 1: softmax statistics
+    for (int n = 0; n < T; ++n) {
+        float l[32];
+        visit(n, n, l);
+        float tmax = l[0];
 #pragma unroll
-            for (int c = 1; c < 32; ++c) tmax = fmaxf(tmax, l[c]);
-            const float m_new = fmaxf(m_run, tmax);
-            if (m_new > -INFINITY) {
-                float a0 = 0.f, a1 = 0.f;
+        for (int c = 1; c < 32; ++c) tmax = fmaxf(tmax, l[c]);
+        const float m_new = fmaxf(m_run, tmax);
+        if (m_new > -INFINITY) {
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-                for (int c = 0; c < 32; c += 2) {
-                    a0 += ex2((l[c] - m_new) * LOG2E);
-                    a1 += ex2((l[c + 1] - m_new) * LOG2E);
-                }
-                s_run = s_run * ex2((m_run - m_new) * LOG2E) + (a0 + a1);
-                m_run = m_new;
+            for (int c = 0; c < 32; c += 2) {
+                a0 += ex2((l[c] - m_new) * LOG2E);
+                a1 += ex2((l[c + 1] - m_new) * LOG2E);
             }
-            if (n == T - 1) {   // merge the four column quarters of every row
-                s_rowstat[cq][row][0] = m_run;
-                s_rowstat[cq][row][1] = s_run;
-            }
-            tc_fence_before();
-            __syncthreads();
-            if (n == T - 1) {
-                float mq[4], sq[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) { mq[c] = s_rowstat[c][row][0]; sq[c] = s_rowstat[c][row][1]; }
-                m_fin = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));   // finite: key 0 is visible to every query
-                float tot = 0.f;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) tot += sq[c] * ex2((mq[c] - m_fin) * LOG2E);
-                inv_s = 1.0f / tot;
-            }
-            continue;
+            s_run = s_run * ex2((m_run - m_new) * LOG2E) + (a0 + a1);
+            m_run = m_new;
         }
-        // ---- sweep 2: P tile
+        tc_fence_before();
+        group_sync(grp);   // every warp of the group has read S[n & 1] before the MMA two visits ahead overwrites it
+    }
+    // merge the four key quarters of every row (two per group)
+    s_rowstat[grp * 2 + ch][row][0] = m_run;
+    s_rowstat[grp * 2 + ch][row][1] = s_run;
+    __syncthreads();
+    {
+        float mq[4], sq[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { mq[c] = s_rowstat[c][row][0]; sq[c] = s_rowstat[c][row][1]; }
+        m_fin = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));   // finite: key 0 is visible to every query
+        float tot = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tot += sq[c] * ex2((mq[c] - m_fin) * LOG2E);
+        inv_s = 1.0f / tot;
+    }
+
+    // ---- sweep 2: probabilities, P V, pooled reductions
+    for (int t = 0; t < T; ++t) {
+        float l[32];
+        visit(T + t, t, l);
         uint32_t pk[16];
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
@@ -439,63 +459,68 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             const float p1 = ex2((l[c + 1] - m_fin) * LOG2E) * inv_s;
             pk[c >> 1] = cvt_bf16x2(p0, p1);
         }
-        if (t > 0) mbar_wait_u32(BAR(7), (t - 1) & 1);   // P V of the previous tile done: sP and V[(t-1)&1] are free
-        __syncthreads();                                  // everyone finished reading the previous P tile
-        if (tid == 0 && t >= 1 && t + 1 < T) issue_v(t + 1, (t + 1) & 1);
-        if (p.stats && t > 0 && tid < BN) flush_stats(t - 1);
+        if (t > 0) mbar_wait_u32(BAR_PV, (t - 1) & 1);   // P V of the previous block done: sP and V[(t-1)&1] are free
+        group_sync(grp);                                  // the group finished reading the previous P block
+        if (gt == 0 && t >= 1 && t + 1 < T) issue_v(t + 1, (t + 1) & 1);
+        if (p.stats && t > 0 && gt < BNH) flush_stats(t - 1);
         {
-            uint8_t* prow = sP_ptr + (cq >> 1) * ATOM_BYTES + row * 128;
+            uint8_t* prow = sP_ptr + row * 128;
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
-                const int c8 = (cq & 1) * 4 + c4;
+                const int c8 = ch * 4 + c4;
                 *reinterpret_cast<uint4*>(prow + ((c8 ^ (row & 7)) << 4)) =
                     make_uint4(pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
             }
         }
         fence_proxy_async();
         tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
+        group_sync(grp);
+        if (gt == 0) {
             tc_fence_after();
-            mbar_wait_u32(BAR(3 + (t & 1)), (t >> 1) & 1);
+            mbar_wait_u32(BAR_V(t & 1), (t >> 1) & 1);
             tc_fence_after();
             mma_pv(t & 1, t == 0);
         }
         __syncwarp();
         if (p.stats) {
-            const int jbase = t * BN + warp * 8;
+            const int jbase = t * BN + grp * BNH + gwarp * 8;
             switch (p.QB) {
-                case 128: tile_stats<7>(sP_ptr, s_comb, p, warp, lane, i0, jbase, want_obs); break;
-                case 64:  tile_stats<6>(sP_ptr, s_comb, p, warp, lane, i0, jbase, want_obs); break;
-                case 32:  tile_stats<5>(sP_ptr, s_comb, p, warp, lane, i0, jbase, want_obs); break;
-                default:  tile_stats<4>(sP_ptr, s_comb, p, warp, lane, i0, jbase, want_obs); break;
+                case 128: tile_stats<7>(sP_ptr, s_comb[grp], p, gwarp, lane, i0, jbase, want_obs); break;
+                case 64:  tile_stats<6>(sP_ptr, s_comb[grp], p, gwarp, lane, i0, jbase, want_obs); break;
+                case 32:  tile_stats<5>(sP_ptr, s_comb[grp], p, gwarp, lane, i0, jbase, want_obs); break;
+                default:  tile_stats<4>(sP_ptr, s_comb[grp], p, gwarp, lane, i0, jbase, want_obs); break;
             }
         }
     }
 
-    // ---- epilogue: Y (fp32 in TMEM) -> bf16 -> global
-    mbar_wait_u32(BAR(7), (T - 1) & 1);
+    // ---- epilogue: Y_0 + Y_1 (fp32 in TMEM) -> bf16 -> global
+    if (T > 0) mbar_wait_u32(BAR_PV, (T - 1) & 1);
     tc_fence_after();
-    __syncthreads();   // the last tile's column partials are complete
-    if (p.stats && tid < BN) flush_stats(T - 1);
+    __syncthreads();   // both groups' accumulators and last column sums are complete
+    tc_fence_after();
+    if (p.stats && T > 0 && gt < BNH) flush_stats(T - 1);
     {
         constexpr int CPT = D / 4;   // columns per thread: 32 (D = 128) or 16 (D = 64)
-        uint32_t y0[32];
-        __nv_bfloat16* yrow = p.y + (long long)(h * p.G + g) * p.y_stride_h + (long long)qi * p.y_stride_s + cq * CPT;
-        if (CPT == 32) {
-            tmem_ld32(tmem + lane_base + 2 * BN + cq * 32, y0);
-        } else {   // D = 64: column quarters of 16; load the enclosing 32 and keep one half
-            tmem_ld32(tmem + lane_base + 2 * BN + (cq >> 1) * 32, y0);
-        }
+        const int cq = tid >> 7, orow = tid & 127;
+        const int og = orow / p.QB, oqi = i0 + orow % p.QB;
+        const bool row_ok = (og < p.G) && (oqi < p.S);
+        const bool two = (grp == 0 ? T_other : T) > 0;   // group 1 saw at least one block
+        uint32_t y0[32], y1[32];
+        const uint32_t ycol = (CPT == 32) ? cq * 32 : (cq >> 1) * 32;   // D = 64: load the enclosing 32 columns
+        tmem_ld32(tmem + 256 + lane_base + ycol, y0);
+        if (two) tmem_ld32(tmem + 256 + 128 + lane_base + ycol, y1);
+        __nv_bfloat16* yrow = p.y + (long long)(h * p.G + og) * p.y_stride_h + (long long)oqi * p.y_stride_s + cq * CPT;
         if (row_ok) {
-            const int off = (CPT == 32) ? 0 : (cq & 1) * 16;
+            float f[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) f[c] = __uint_as_float(y0[c]) + (two ? __uint_as_float(y1[c]) : 0.f);
 #pragma unroll
             for (int c = 0; c < CPT; c += 8) {
-                uint4 o = make_uint4(pack_bf16(__uint_as_float(y0[off + c]), __uint_as_float(y0[off + c + 1])),
-                                     pack_bf16(__uint_as_float(y0[off + c + 2]), __uint_as_float(y0[off + c + 3])),
-                                     pack_bf16(__uint_as_float(y0[off + c + 4]), __uint_as_float(y0[off + c + 5])),
-                                     pack_bf16(__uint_as_float(y0[off + c + 6]), __uint_as_float(y0[off + c + 7])));
-                *reinterpret_cast<uint4*>(yrow + c) = o;
+                float e[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) e[u] = (CPT == 32) ? f[c + u] : ((cq & 1) ? f[16 + c + u] : f[c + u]);
+                *reinterpret_cast<uint4*>(yrow + c) = make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]),
+                                                                  pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
             }
         }
     }
@@ -604,7 +629,7 @@ Plan make_plan(int S, int Hkv, int G, int obs_len, int n_windows) {
 template <int D, bool NAIVE>
 int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const PrefillParams& p, int grid,
            cudaStream_t stream) {
-    const int smem = 1024 + (D / 64) * ATOM_BYTES * 5 + 2 * ATOM_BYTES;
+    const int smem = 1024 + (D / 64) * ATOM_BYTES + 2 * (4 * (D / 64) * BNH * 128 + ATOM_BYTES);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(prefill_attn_kernel<D, NAIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -670,8 +695,8 @@ int prefill_attention_impl(const CcPrefillAttnArgs* a, cudaStream_t stream) {
     CUtensorMap tq, tk, tv;
     int rc;
     if ((rc = make_map(&tq, a->q, D, S, Hkv * G, a->q_stride_s, a->q_stride_h, pl.QB, G)) != CC_OK) return rc;
-    if ((rc = make_map(&tk, a->k, D, S, Hkv, a->k_stride_s, a->k_stride_h, BN, 1)) != CC_OK) return rc;
-    if ((rc = make_map(&tv, a->v, D, S, Hkv, a->v_stride_s, a->v_stride_h, BN, 1)) != CC_OK) return rc;
+    if ((rc = make_map(&tk, a->k, D, S, Hkv, a->k_stride_s, a->k_stride_h, BNH, 1)) != CC_OK) return rc;
+    if ((rc = make_map(&tv, a->v, D, S, Hkv, a->v_stride_s, a->v_stride_h, BNH, 1)) != CC_OK) return rc;
     const int grid = pl.n_qtiles * Hkv;
     const bool naive = a->attn_mode == CC_ATTN_NAIVE_BF16;
     if (D == 128) rc = naive ? launch<128, true>(tq, tk, tv, p, grid, stream) : launch<128, false>(tq, tk, tv, p, grid, stream);
