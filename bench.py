@@ -107,6 +107,16 @@ def build_gpu_model(device, world):
                 p.fill_(1.0)
             else:
                 p.normal_(0.0, 0.02, generator=gen)
+    fake = int(os.environ.get("CC_TP_FAKE", "0"))
+    if world == 1 and fake > 1:
+        # diagnostics (profiles/): rank 0's shard of a `fake`-way split on ONE GPU with the exchanges skipped, i.e. the
+        # compute-only time of a tensor-parallel rank; the number it prints is NOT a bench value
+        from cold_compress_b200.tp import apply_tp
+        os.environ["LOCAL_RANK"], os.environ["LOCAL_WORLD_SIZE"] = "0", str(fake)
+        apply_tp(model, group=object())
+        for blk in model.layers:
+            blk.attention.tp_group = blk.feed_forward.tp_group = None
+        os.environ["LOCAL_WORLD_SIZE"] = "1"
     if world > 1:
         from cold_compress_b200.tp import apply_tp, enable_fused_exchange
         apply_tp(model)
@@ -271,7 +281,8 @@ def run_ours(args):
         "config": {"workload": f"{MODEL}-shape random-init bf16, heavy_hitter + SnapKV compression, "
                                f"{CACHE_SLOTS} slots/layer, {PROMPT_LEN}-token synthetic prompt, decode @ 8k ctx",
                    "global_batch": 1, "seq_len": PROMPT_LEN + MAX_NEW, "parallelism": (f"tp{world} ({'fused NVLink exchange' if getattr(model, 'tp_link', None) is not None else 'NCCL all-reduce'})"
-                                   if world > 1 else "none"),
+                                   if world > 1 else ("none" if not int(os.environ.get("CC_TP_FAKE", "0")) > 1 else
+                                                      f"DIAGNOSTIC: rank-0 shard of tp{os.environ['CC_TP_FAKE']}, exchanges skipped")),
                    "l2": "per-step inputs (15 GB of weights + 134 MB of K/V) exceed the 126 MB L2",
                    "prefill_seconds": round(prefill_s, 2)},
         "e2e": {"value": round(args.steps / e2e_s, 2), "unit": "tokens/s", "h2d_bytes_per_step": 8,
@@ -285,7 +296,7 @@ def run_ours(args):
     if rank == 0:
         out["roofline"] = roof
         out["cpu_baseline"] = (cpu_reference(sample_seconds=20.0, warmup=1)
-                               if world == 1 and not os.environ.get("CC_BENCH_NCU") else None)
+                               if world == 1 and not os.environ.get("CC_BENCH_NCU") and not os.environ.get("CC_TP_FAKE") else None)
         print(json.dumps(out), flush=True)
     if world > 1:
         # leave without tearing NCCL down: communicators captured in CUDA graphs make

@@ -40,8 +40,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ---------------------------------------------------------------- fused tensor-parallel exchange
 constexpr int kMaxTp = 8;
 struct TpDev {
-    const uint64_t* peer_buf;   // [world] base addresses of the exchange buffers (bf16 [n_ops][world][dim])
-    const uint64_t* peer_flag;  // [world] base addresses of the flag arrays (i32 [n_ops][world])
+    const uint64_t* peer_buf;   // [world] base addresses of the exchange buffers (u64 [n_ops][world][dim / 2])
+    const uint64_t* peer_flag;  // unused (flag-in-data protocol)
     int32_t* cta_done;
     const int32_t* epoch;
     __nv_bfloat16* recv_out;
@@ -55,35 +55,72 @@ __device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
-// Producer side, end of kernel.  Every CTA has written its rows to the local vector `out` (device-scope
-// fence + counter); the LAST CTA to finish copies the whole vector into slot [send_op][rank] of every
-// rank's exchange buffer with 16-byte stores over NVLink, issues ONE system-scope fence and publishes the
-// epoch in every rank's flag array.  (A system fence per CTA costs microseconds and ~1000 CTAs would
-// serialise on it.)
-__device__ __forceinline__ void tp_send_vector(const TpDev& tp, const __nv_bfloat16* out) {
-    __shared__ int is_last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const int prev = atomicAdd(&tp.cta_done[tp.send_op], 1);
-        is_last = prev == (int)gridDim.x - 1;
-        if (is_last) tp.cta_done[tp.send_op] = 0;
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    const size_t slot = (size_t)(tp.send_op * tp.world + tp.rank) * tp.dim;
-    for (int i = threadIdx.x * 8; i < tp.dim; i += kGemvThreads * 8) {
-        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(out + i));
-        for (int p = 0; p < tp.world; ++p)
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(tp.peer_buf[p]) + slot + i) = v;
-    }
-    __syncthreads();  // the CTA's peer stores are ordered before thread 0's system-scope releases below
-    if (threadIdx.x == 0) {
-        const int32_t ep = *reinterpret_cast<const volatile int32_t*>(tp.epoch);
-        __threadfence_system();  // one fence for the whole vector
-        for (int p = 0; p < tp.world; ++p)
-            st_release_sys(reinterpret_cast<int32_t*>(tp.peer_flag[p]) + tp.send_op * tp.world + tp.rank, ep);
+// Exchange protocol: flag-in-data ("LL") words.  The exchange buffer of a rank is u64 [n_ops][world][dim / 2]; word
+// [op][r][i] = {two bf16 partial sums (rows 2i, 2i+1) of rank r, epoch}.  8-byte stores are delivered atomically
+// over NVLink, so a word whose upper half equals the current epoch carries valid data: no fences, no flags, no
+// "last CTA" -- the producer lane that owns a row pair stores it straight into every rank's buffer the moment it is
+// computed, and the exchange costs one NVLink write latency.
+__device__ __forceinline__ void tp_push_pair(const TpDev& tp, int r0, float a, float b, int32_t ep) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    const uint32_t data = *reinterpret_cast<const uint32_t*>(&v);
+    const size_t word = (size_t)(tp.send_op * tp.world + tp.rank) * (tp.dim / 2) + (r0 >> 1);
+    for (int p = 0; p < tp.world; ++p)
+        asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};"
+                     :: "l"(reinterpret_cast<uint64_t*>(tp.peer_buf[p]) + word), "r"(data), "r"((uint32_t)ep) : "memory");
+}
+// Consumer side: 8 elements of x per thread and pass = 4 words from each of the W ranks.  All 4 W loads are issued
+// before any flag is looked at (one memory round trip when the data is there; re-polled as a whole otherwise).
+// 16 bytes (8 bf16 of x) into the staging buffer of every CTA of this cluster (DSMEM stores)
+__device__ __forceinline__ void stage_broadcast(__nv_bfloat16* xs_elem, uint4 v, uint32_t nct) {
+    const uint32_t local = smem_u32(xs_elem);
+    for (uint32_t r = 0; r < nct; ++r)
+        asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};"
+                     :: "r"(map_to_rank(local, r)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Consumer side.  The CTAs of a cluster split the vector: each collects ITS slice [i_begin, i_end) -- 8 elements per
+// thread and pass = 4 words from each of the W ranks, all 4 W loads issued before any flag is looked at (one memory
+// round trip when the data is there; re-polled as a whole otherwise) -- and broadcasts the summed slice into the
+// shared memory of every CTA of the cluster, so the partial vectors cross L2 once per cluster, not once per CTA.
+template <int W>
+__device__ __forceinline__ void tp_collect(const TpDev& tp, const uint64_t* recv, uint32_t ep, const __nv_bfloat16* x,
+                                           __nv_bfloat16* xs, int i_begin, int i_end, uint32_t nct) {
+    const int tid = threadIdx.x;
+    for (int i = i_begin + tid * 8; i < i_end; i += kGemvThreads * 8) {
+        uint32_t d[W][4];
+        uint32_t bad;
+        do {
+            bad = 0;
+#pragma unroll
+            for (int r = 0; r < W; ++r) {
+                if (r < tp.world) {
+                    const uint64_t* w = recv + (size_t)r * (tp.dim / 2) + (i >> 1);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t f;
+                        asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(d[r][j]), "=r"(f) : "l"(w + j) : "memory");
+                        bad |= f ^ ep;
+                    }
+                }
+            }
+        } while (bad);
+        float acc[8], f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int r = 0; r < W; ++r) {   // rank order: the same bits on every rank
+            if (r < tp.world) {
+                unpack8(make_uint4(d[r][0], d[r][1], d[r][2], d[r][3]), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
+        }
+        unpack8(*reinterpret_cast<const uint4*>(x + i), f);
+        __nv_bfloat16 o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(__fadd_rn(f[j], bf16_round(acc[j])));
+        stage_broadcast(xs + i, *reinterpret_cast<uint4*>(o), nct);
+        if (blockIdx.x < nct && tp.recv_out) *reinterpret_cast<uint4*>(tp.recv_out + i) = *reinterpret_cast<uint4*>(o);
     }
 }
 
@@ -92,50 +129,29 @@ __device__ __forceinline__ void tp_send_vector(const TpDev& tp, const __nv_bfloa
 __device__ void stage_input(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ norm_w,
                             float eps, int K, __nv_bfloat16* xs, float* scratch, const TpDev& tp) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // the CTAs of a cluster stage one slice each and broadcast it (DSMEM): x crosses L2 once per cluster
+    const uint32_t nct = cluster_nctarank(), cr = cluster_ctarank();
+    const int slice = K / (int)nct;              // K % 256 == 0 and nct in {1, 2, 4, 8}: a multiple of 32
+    const int i_begin = (int)cr * slice, i_end = i_begin + slice;
+    cluster_wait_acquire();   // every CTA of the cluster has started (arrive at kernel entry)
     if (tp.recv_op >= 0) {
-        // consumer of a fused all-reduce: wait for every rank's partial vector of this op, then
-        // x = bf16(residual + bf16(sum of the partials))   (tp.py:156-160 + model.py:317 / 326)
-        const int32_t ep = *reinterpret_cast<const volatile int32_t*>(tp.epoch);
-        int32_t* ready = tp.cta_done + tp.n_ops + tp.recv_op;  // device-scope "all partials have arrived"
-        if (blockIdx.x == 0) {
-            // only CTA 0 polls the system-scope flags the peers write over NVLink ...
-            if (tid < tp.world) {
-                const int32_t* f = reinterpret_cast<const int32_t*>(tp.peer_flag[tp.rank]) + tp.recv_op * tp.world + tid;
-                while (ld_acquire_sys(f) != ep) {}
-            }
-            __syncthreads();
-            if (tid == 0) { __threadfence(); asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(ready), "r"(ep) : "memory"); }
-        } else if (tid == 0) {
-            // ... every other CTA waits on a device-scope word in L2
-            int32_t v;
-            do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory"); } while (v != ep);
-        }
-        __syncthreads();
-        const __nv_bfloat16* recv = reinterpret_cast<const __nv_bfloat16*>(tp.peer_buf[tp.rank]) +
-                                    (size_t)tp.recv_op * tp.world * tp.dim;
-        for (int i = tid * 8; i < K; i += kGemvThreads * 8) {
-            float acc[8], f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-            for (int r = 0; r < tp.world; ++r) {
-                // written by peers over NVLink: read through L2, never through a stale L1 line
-                const uint4 v = __ldcg(reinterpret_cast<const uint4*>(recv + (size_t)r * tp.dim + i));
-                unpack8(v, f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += f[j];
-            }
-            unpack8(*reinterpret_cast<const uint4*>(x + i), f);
-            __nv_bfloat16 o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(__fadd_rn(f[j], bf16_round(acc[j])));
-            *reinterpret_cast<uint4*>(xs + i) = *reinterpret_cast<uint4*>(o);
-            if (blockIdx.x == 0 && tp.recv_out) *reinterpret_cast<uint4*>(tp.recv_out + i) = *reinterpret_cast<uint4*>(o);
+        // consumer of a fused all-reduce: collect every rank's partial vector of this op (polling the flag-in-data
+        // words), then x = bf16(residual + bf16(sum of the partials))   (tp.py:156-160 + model.py:317 / 326)
+        const uint32_t ep = (uint32_t)*reinterpret_cast<const volatile int32_t*>(tp.epoch);
+        const uint64_t* recv = reinterpret_cast<const uint64_t*>(tp.peer_buf[tp.rank]) +
+                               (size_t)tp.recv_op * tp.world * (tp.dim / 2);
+        switch (tp.world) {
+        case 2: tp_collect<2>(tp, recv, ep, x, xs, i_begin, i_end, nct); break;
+        case 4: tp_collect<4>(tp, recv, ep, x, xs, i_begin, i_end, nct); break;
+        case 8: tp_collect<8>(tp, recv, ep, x, xs, i_begin, i_end, nct); break;
+        default: tp_collect<kMaxTp>(tp, recv, ep, x, xs, i_begin, i_end, nct); break;
         }
     } else {
-        for (int i = tid * 8; i < K; i += kGemvThreads * 8)
-            *reinterpret_cast<uint4*>(xs + i) = *reinterpret_cast<const uint4*>(x + i);
+        for (int i = i_begin + tid * 8; i < i_end; i += kGemvThreads * 8)
+            stage_broadcast(xs + i, *reinterpret_cast<const uint4*>(x + i), nct);
     }
-    __syncthreads();
+    cluster_arrive_release();   // a cluster of one CTA degenerates to a CTA barrier
+    cluster_wait_acquire();
     if (norm_w == nullptr) return;
     // RMSNorm in place on the staged vector
     float ss = 0.f;
@@ -241,6 +257,7 @@ __device__ __forceinline__ bool combine_split(float (*part)[R], float (&out)[R])
 // Skeleton shared by the three kernels: every warp owns row group `base + warp / KS` and the K-slice
 // `warp % KS`.  First pass: weights are requested BEFORE the dependency wait and the input staging.
 #define CC_GEMV_PROLOGUE(R_, NV_, ROWS_OF)                                                          \
+    cluster_arrive_relaxed(); /* paired with the wait in stage_input: peers exist before DSMEM stores */ \
     constexpr int GPB = kGemvWarps / KS;                                                            \
     const int warp = threadIdx.x >> 5;                                                              \
     const int klen = p.K / KS, k0 = (warp % KS) * klen;                                             \
@@ -328,6 +345,7 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_residual_kernel(const __gri
     const int n_pairs = p.N / 2;
 #define CC_ROWS {p.w + (size_t)r0 * p.K, p.w + (size_t)(r0 + 1) * p.K}
     CC_GEMV_PROLOGUE(2, 4, CC_ROWS)
+    const int32_t send_ep = p.tp.send_op >= 0 ? *reinterpret_cast<const volatile int32_t*>(p.tp.epoch) : 0;
     for (; base < n_pairs; base += gridDim.x * GPB) {
         const int pr = min(base + warp / KS, n_pairs - 1);
         const bool active = base + warp / KS < n_pairs;
@@ -343,11 +361,11 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_residual_kernel(const __gri
                 a = __fadd_rn(__bfloat162float(p.residual[r0]), a);
                 b = __fadd_rn(__bfloat162float(p.residual[r0 + 1]), b);
             }
-            *reinterpret_cast<__nv_bfloat162*>(p.out + r0) = __floats2bfloat162_rn(a, b);
+            if (p.tp.send_op >= 0) tp_push_pair(p.tp, r0, a, b, send_ep);
+            else *reinterpret_cast<__nv_bfloat162*>(p.out + r0) = __floats2bfloat162_rn(a, b);
         }
         if (KS > 1) __syncthreads();
     }
-    if (p.tp.send_op >= 0) tp_send_vector(p.tp, p.out);
 #undef CC_ROWS
 }
 
@@ -400,8 +418,8 @@ static int fill_tp(const CcTpArgs* tp, int K, TpDev* out, const char* what) {
     d.send_op = d.recv_op = -1;
     if (tp && tp->link && (tp->send_op >= 0 || tp->recv_op >= 0)) {
         const CcTpLink* l = tp->link;
-        if (l->world < 2 || l->world > kMaxTp || l->rank < 0 || l->rank >= l->world || !l->peer_buf || !l->peer_flag ||
-            !l->cta_done || !l->epoch || tp->send_op >= l->n_ops || tp->recv_op >= l->n_ops)
+        if (l->world < 2 || l->world > kMaxTp || l->rank < 0 || l->rank >= l->world || !l->peer_buf ||
+            !l->epoch || (l->dim & 1) || tp->send_op >= l->n_ops || tp->recv_op >= l->n_ops)
             return set_error(CC_ERR_INVALID_ARG, what);
         if (tp->recv_op >= 0 && l->dim != K) return set_error(CC_ERR_INVALID_ARG, "tensor-parallel receive: dim must equal K");
         d.peer_buf = l->peer_buf; d.peer_flag = l->peer_flag; d.cta_done = l->cta_done; d.epoch = l->epoch;
@@ -445,6 +463,10 @@ static int launch_split(K1 k1, K2 k2, K4 k4, K8 k8, const P& p, int n_pairs, int
     int grid = (n_pairs + gpb - 1) / gpb;
     const int cap = sm_count() * 8;
     if (grid > cap) grid = cap;
+    // Input staging can be shared by the CTAs of a cluster (stage_input broadcasts over DSMEM), but measured on B200
+    // the gang scheduling + two cluster barriers cost 5-8 us per launch (profiles/r1_notes.md): clusters stay off.
+    const int cluster = 1;
+    grid = (grid + cluster - 1) / cluster * cluster;
     auto go = [&](auto kernel) -> int {
         static thread_local const void* raised[16] = {};
         if (smem > 48 * 1024) {  // raise the per-function cap once, to the device limit
@@ -465,11 +487,21 @@ static int launch_split(K1 k1, K2 k2, K4 k4, K8 k8, const P& p, int n_pairs, int
         cfg.blockDim = dim3(kGemvThreads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = stream;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr.val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = &attr;
-        cfg.numAttrs = pdl_enabled() ? 1 : 0;
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        if (cluster > 1) {
+            attr[na].id = cudaLaunchAttributeClusterDimension;
+            attr[na].val.clusterDim.x = cluster;
+            attr[na].val.clusterDim.y = attr[na].val.clusterDim.z = 1;
+            ++na;
+        }
+        if (pdl_enabled()) {
+            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        cfg.attrs = attr;
+        cfg.numAttrs = na;
         cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
         return e == cudaSuccess ? CC_OK : set_cuda_error(e, what);
     };

@@ -121,7 +121,8 @@ class FusedExchange:
         self.dim = model.output.in_features
         self.n_ops = 2 * len(model.layers)
         dev = model.output.weight.device
-        self.buf = symm.empty(self.n_ops * self.world * self.dim, dtype=torch.bfloat16, device=dev)
+        # u64 [n_ops][world][dim / 2] flag-in-data words = 4 bytes per vector element
+        self.buf = symm.empty(self.n_ops * self.world * self.dim, dtype=torch.int32, device=dev)
         self.flags = symm.empty(self.n_ops * self.world, dtype=torch.int32, device=dev)
         self.buf.zero_()
         self.flags.zero_()

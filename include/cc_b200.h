@@ -224,20 +224,21 @@ int cc_prefill_attention(const CcPrefillAttnArgs* args, void* stream);
 
 /*
  * Tensor-parallel exchange fused into the projections (tp.py:134-138, 156-160: the all-reduce of the
- * row-parallel wo / w2 outputs).  Every rank owns an exchange buffer bf16 [n_ops][world][dim] and a flag
- * array i32 [n_ops][world] in peer-mapped (NVLink) memory.  A projection called with send_op >= 0 writes
- * its partial output vector to `out` as usual; its last CTA to finish copies the vector into slot
- * [send_op][rank] of EVERY rank's buffer and then stores the current epoch into flag [send_op][rank] of
- * every rank.  A projection called with
- * recv_op >= 0 first waits until all `world` flags of that op equal the epoch, then uses
- * x = bf16(residual + bf16(sum over ranks of the partials)) as its input (and CTA 0 writes x to recv_out).
- * The caller increments *epoch once per token after the last kernel.
+ * row-parallel wo / w2 outputs).  Every rank owns an exchange buffer u64 [n_ops][world][dim / 2] in peer-mapped
+ * (NVLink) memory, zero-initialised.  Word [op][r][i] = {bf16 x 2: partial sums of rows 2i, 2i+1 from rank r |
+ * epoch << 32}: the flag travels IN the data word (8-byte stores are delivered atomically), so there are no
+ * fences, flag arrays or counters on the path.  A projection called with send_op >= 0 does not write `out`: the
+ * lane that owns a row pair stores its word straight into slot [send_op][rank] of EVERY rank's buffer.  A
+ * projection called with recv_op >= 0 polls the `world` slots of that op until every word carries the current
+ * epoch, then uses x = bf16(residual + bf16(sum over ranks, in rank order, of the partials)) as its input (and
+ * CTA 0 writes x to recv_out).  The caller increments *epoch once per token after the last kernel; n_ops >= 2
+ * distinct ops per token keep a slot from being rewritten before every rank has consumed it.
  */
 typedef struct CcTpLink {
     int32_t world, rank, dim, n_ops;
     const uint64_t* peer_buf;    /* device array [world]: base address of each rank's exchange buffer */
-    const uint64_t* peer_flag;   /* device array [world]: base address of each rank's flag array      */
-    int32_t*        cta_done;    /* local i32 [2 * n_ops], zero-initialised (CTA counters, then ready words) */
+    const uint64_t* peer_flag;   /* unused by the flag-in-data protocol (kept for ABI stability), may be NULL */
+    int32_t*        cta_done;    /* unused, may be NULL                                                       */
     const int32_t*  epoch;       /* local device i32 [1], >= 1                                         */
 } CcTpLink;
 
