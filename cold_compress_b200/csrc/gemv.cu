@@ -133,7 +133,7 @@ __device__ void stage_input(const __nv_bfloat16* __restrict__ x, const __nv_bflo
     const uint32_t nct = cluster_nctarank(), cr = cluster_ctarank();
     const int slice = K / (int)nct;              // K % 256 == 0 and nct in {1, 2, 4, 8}: a multiple of 32
     const int i_begin = (int)cr * slice, i_end = i_begin + slice;
-    cluster_wait_acquire();   // every CTA of the cluster has started (arrive at kernel entry)
+    if (nct > 1) cluster_wait_acquire();   // every CTA of the cluster has started (arrive at kernel entry)
     if (tp.recv_op >= 0) {
         // consumer of a fused all-reduce: collect every rank's partial vector of this op (polling the flag-in-data
         // words), then x = bf16(residual + bf16(sum of the partials))   (tp.py:156-160 + model.py:317 / 326)
@@ -150,8 +150,12 @@ __device__ void stage_input(const __nv_bfloat16* __restrict__ x, const __nv_bflo
         for (int i = i_begin + tid * 8; i < i_end; i += kGemvThreads * 8)
             stage_broadcast(xs + i, *reinterpret_cast<const uint4*>(x + i), nct);
     }
-    cluster_arrive_release();   // a cluster of one CTA degenerates to a CTA barrier
-    cluster_wait_acquire();
+    if (nct > 1) {
+        cluster_arrive_release();
+        cluster_wait_acquire();
+    } else {
+        __syncthreads();
+    }
     if (norm_w == nullptr) return;
     // RMSNorm in place on the staged vector
     float ss = 0.f;
@@ -257,7 +261,7 @@ __device__ __forceinline__ bool combine_split(float (*part)[R], float (&out)[R])
 // Skeleton shared by the three kernels: every warp owns row group `base + warp / KS` and the K-slice
 // `warp % KS`.  First pass: weights are requested BEFORE the dependency wait and the input staging.
 #define CC_GEMV_PROLOGUE(R_, NV_, ROWS_OF)                                                          \
-    cluster_arrive_relaxed(); /* paired with the wait in stage_input: peers exist before DSMEM stores */ \
+    if (cluster_nctarank() > 1) cluster_arrive_relaxed(); /* paired with the wait in stage_input */  \
     constexpr int GPB = kGemvWarps / KS;                                                            \
     const int warp = threadIdx.x >> 5;                                                              \
     const int klen = p.K / KS, k0 = (warp % KS) * klen;                                             \
