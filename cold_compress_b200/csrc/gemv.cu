@@ -72,6 +72,7 @@ __device__ __forceinline__ void tp_push_pair(const TpDev& tp, int r0, float a, f
 // before any flag is looked at (one memory round trip when the data is there; re-polled as a whole otherwise).
 // 16 bytes (8 bf16 of x) into the staging buffer of every CTA of this cluster (DSMEM stores)
 __device__ __forceinline__ void stage_broadcast(__nv_bfloat16* xs_elem, uint4 v, uint32_t nct) {
+    if (nct == 1) { *reinterpret_cast<uint4*>(xs_elem) = v; return; }
     const uint32_t local = smem_u32(xs_elem);
     for (uint32_t r = 0; r < nct; ++r)
         asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};"
