@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "internal.h"
@@ -83,34 +84,32 @@ __device__ __forceinline__ void stage_broadcast(__nv_bfloat16* xs_elem, uint4 v,
 // thread and pass = 4 words from each of the W ranks, all 4 W loads issued before any flag is looked at (one memory
 // round trip when the data is there; re-polled as a whole otherwise) -- and broadcasts the summed slice into the
 // shared memory of every CTA of the cluster, so the partial vectors cross L2 once per cluster, not once per CTA.
-template <int W>
 __device__ __forceinline__ void tp_collect(const TpDev& tp, const uint64_t* recv, uint32_t ep, const __nv_bfloat16* x,
                                            __nv_bfloat16* xs, int i_begin, int i_end, uint32_t nct) {
     const int tid = threadIdx.x;
     for (int i = i_begin + tid * 8; i < i_end; i += kGemvThreads * 8) {
-        uint32_t d[W][4];
-        uint32_t bad;
-        do {
-            bad = 0;
-#pragma unroll
-            for (int r = 0; r < W; ++r) {
-                if (r < tp.world) {
-                    const uint64_t* w = recv + (size_t)r * (tp.dim / 2) + (i >> 1);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t f;
-                        asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(d[r][j]), "=r"(f) : "l"(w + j) : "memory");
-                        bad |= f ^ ep;
-                    }
-                }
-            }
-        } while (bad);
         float acc[8], f[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        // two ranks (8 loads) per round: the prefetched weight registers of the caller stay live across this loop
+        for (int r0 = 0; r0 < tp.world; r0 += 2) {   // rank order: the same bits on every rank (world is even)
+            uint32_t d[2][4];
+            uint32_t bad;
+            do {
+                bad = 0;
 #pragma unroll
-        for (int r = 0; r < W; ++r) {   // rank order: the same bits on every rank
-            if (r < tp.world) {
+                for (int r = 0; r < 2; ++r) {
+                    const uint64_t* w = recv + (size_t)(r0 + r) * (tp.dim / 2) + (i >> 1);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t fl;
+                        asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(d[r][j]), "=r"(fl) : "l"(w + j) : "memory");
+                        bad |= fl ^ ep;
+                    }
+                }
+            } while (bad);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
                 unpack8(make_uint4(d[r][0], d[r][1], d[r][2], d[r][3]), f);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[j] += f[j];
@@ -141,12 +140,7 @@ __device__ void stage_input(const __nv_bfloat16* __restrict__ x, const __nv_bflo
         const uint32_t ep = (uint32_t)*reinterpret_cast<const volatile int32_t*>(tp.epoch);
         const uint64_t* recv = reinterpret_cast<const uint64_t*>(tp.peer_buf[tp.rank]) +
                                (size_t)tp.recv_op * tp.world * (tp.dim / 2);
-        switch (tp.world) {
-        case 2: tp_collect<2>(tp, recv, ep, x, xs, i_begin, i_end, nct); break;
-        case 4: tp_collect<4>(tp, recv, ep, x, xs, i_begin, i_end, nct); break;
-        case 8: tp_collect<8>(tp, recv, ep, x, xs, i_begin, i_end, nct); break;
-        default: tp_collect<kMaxTp>(tp, recv, ep, x, xs, i_begin, i_end, nct); break;
-        }
+        tp_collect(tp, recv, ep, x, xs, i_begin, i_end, nct);
     } else {
         for (int i = i_begin + tid * 8; i < i_end; i += kGemvThreads * 8)
             stage_broadcast(xs + i, *reinterpret_cast<const uint4*>(x + i), nct);
@@ -423,7 +417,7 @@ static int fill_tp(const CcTpArgs* tp, int K, TpDev* out, const char* what) {
     d.send_op = d.recv_op = -1;
     if (tp && tp->link && (tp->send_op >= 0 || tp->recv_op >= 0)) {
         const CcTpLink* l = tp->link;
-        if (l->world < 2 || l->world > kMaxTp || l->rank < 0 || l->rank >= l->world || !l->peer_buf ||
+        if (l->world < 2 || l->world > kMaxTp || (l->world & 1) || l->rank < 0 || l->rank >= l->world || !l->peer_buf ||
             !l->epoch || (l->dim & 1) || tp->send_op >= l->n_ops || tp->recv_op >= l->n_ops)
             return set_error(CC_ERR_INVALID_ARG, what);
         if (tp->recv_op >= 0 && l->dim != K) return set_error(CC_ERR_INVALID_ARG, "tensor-parallel receive: dim must equal K");

@@ -82,3 +82,24 @@ def test_abi_exports_every_declared_symbol():
     assert lib.cc_abi_version() == _lib.ABI_VERSION and b"sm_100a" in lib.cc_build_info()
     import ctypes as C
     assert C.sizeof(_lib.CcCacheState) == 12 * 4 + 18 * 8 and C.sizeof(_lib.CcDecodeArgs) == 7 * 8 + 16 + 3 * 16 + 8
+
+
+def test_kernel_register_budgets():
+    """Occupancy guard on the build log (ptxas -v): the one-token projection kernels must stay at <= 80 registers
+    (3 CTAs of 256 threads per SM -- at 128 they drop to 2 and lose 10-15 % of their bandwidth, profiles/r1_notes.md),
+    the prefill kernel at <= 128 (512 threads), and nothing may spill more than a few bytes."""
+    import re
+    from pathlib import Path
+    log = (Path(__file__).resolve().parent.parent / "cold_compress_b200" / "build_log.txt").read_text()
+    entries = re.findall(r"Compiling entry function '(\S+)' for 'sm_100a'.*?(\d+) bytes spill stores.*?Used (\d+) registers", log, re.S)
+    assert entries, "build_log.txt has no ptxas -v output"
+    seen = set()
+    for name, spill, regs in entries:
+        spill, regs = int(spill), int(regs)
+        assert spill <= 16, f"{name}: {spill} bytes of spills"
+        for key, cap in (("rmsnorm_qkv_rope_kernel", 80), ("gemv_residual_kernel", 80), ("rmsnorm_ffn_gate_kernel", 80),
+                         ("prefill_attn_kernel", 128)):
+            if key in name:
+                seen.add(key)
+                assert regs <= cap, f"{name}: {regs} registers > {cap}"
+    assert len(seen) == 4
