@@ -71,23 +71,12 @@ __device__ __forceinline__ void tp_push_pair(const TpDev& tp, int r0, float a, f
 }
 // Consumer side: 8 elements of x per thread and pass = 4 words from each of the W ranks.  All 4 W loads are issued
 // before any flag is looked at (one memory round trip when the data is there; re-polled as a whole otherwise).
-// 16 bytes (8 bf16 of x) into the staging buffer of every CTA of this cluster (DSMEM stores)
-__device__ __forceinline__ void stage_broadcast(__nv_bfloat16* xs_elem, uint4 v, uint32_t nct) {
-    if (nct == 1) { *reinterpret_cast<uint4*>(xs_elem) = v; return; }
-    const uint32_t local = smem_u32(xs_elem);
-    for (uint32_t r = 0; r < nct; ++r)
-        asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};"
-                     :: "r"(map_to_rank(local, r)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-// Consumer side.  The CTAs of a cluster split the vector: each collects ITS slice [i_begin, i_end) -- 8 elements per
-// thread and pass = 4 words from each of the W ranks, all 4 W loads issued before any flag is looked at (one memory
-// round trip when the data is there; re-polled as a whole otherwise) -- and broadcasts the summed slice into the
-// shared memory of every CTA of the cluster, so the partial vectors cross L2 once per cluster, not once per CTA.
+// Consumer side: 8 elements of x per thread and pass = 4 words from each rank; the 8 loads of two ranks are issued
+// before any flag is looked at (one memory round trip when the data is there; re-polled as a whole otherwise).
 __device__ __forceinline__ void tp_collect(const TpDev& tp, const uint64_t* recv, uint32_t ep, const __nv_bfloat16* x,
-                                           __nv_bfloat16* xs, int i_begin, int i_end, uint32_t nct) {
+                                           __nv_bfloat16* xs, int K) {
     const int tid = threadIdx.x;
-    for (int i = i_begin + tid * 8; i < i_end; i += kGemvThreads * 8) {
+    for (int i = tid * 8; i < K; i += kGemvThreads * 8) {
         float acc[8], f[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -119,8 +108,8 @@ __device__ __forceinline__ void tp_collect(const TpDev& tp, const uint64_t* recv
         __nv_bfloat16 o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(__fadd_rn(f[j], bf16_round(acc[j])));
-        stage_broadcast(xs + i, *reinterpret_cast<uint4*>(o), nct);
-        if (blockIdx.x < nct && tp.recv_out) *reinterpret_cast<uint4*>(tp.recv_out + i) = *reinterpret_cast<uint4*>(o);
+        *reinterpret_cast<uint4*>(xs + i) = *reinterpret_cast<uint4*>(o);
+        if (blockIdx.x == 0 && tp.recv_out) *reinterpret_cast<uint4*>(tp.recv_out + i) = *reinterpret_cast<uint4*>(o);
     }
 }
 
@@ -129,28 +118,18 @@ __device__ __forceinline__ void tp_collect(const TpDev& tp, const uint64_t* recv
 __device__ void stage_input(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ norm_w,
                             float eps, int K, __nv_bfloat16* xs, float* scratch, const TpDev& tp) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // the CTAs of a cluster stage one slice each and broadcast it (DSMEM): x crosses L2 once per cluster
-    const uint32_t nct = cluster_nctarank(), cr = cluster_ctarank();
-    const int slice = K / (int)nct;              // K % 256 == 0 and nct in {1, 2, 4, 8}: a multiple of 32
-    const int i_begin = (int)cr * slice, i_end = i_begin + slice;
-    if (nct > 1) cluster_wait_acquire();   // every CTA of the cluster has started (arrive at kernel entry)
     if (tp.recv_op >= 0) {
         // consumer of a fused all-reduce: collect every rank's partial vector of this op (polling the flag-in-data
         // words), then x = bf16(residual + bf16(sum of the partials))   (tp.py:156-160 + model.py:317 / 326)
         const uint32_t ep = (uint32_t)*reinterpret_cast<const volatile int32_t*>(tp.epoch);
         const uint64_t* recv = reinterpret_cast<const uint64_t*>(tp.peer_buf[tp.rank]) +
                                (size_t)tp.recv_op * tp.world * (tp.dim / 2);
-        tp_collect(tp, recv, ep, x, xs, i_begin, i_end, nct);
+        tp_collect(tp, recv, ep, x, xs, K);
     } else {
-        for (int i = i_begin + tid * 8; i < i_end; i += kGemvThreads * 8)
-            stage_broadcast(xs + i, *reinterpret_cast<const uint4*>(x + i), nct);
+        for (int i = tid * 8; i < K; i += kGemvThreads * 8)
+            *reinterpret_cast<uint4*>(xs + i) = *reinterpret_cast<const uint4*>(x + i);
     }
-    if (nct > 1) {
-        cluster_arrive_release();
-        cluster_wait_acquire();
-    } else {
-        __syncthreads();
-    }
+    __syncthreads();
     if (norm_w == nullptr) return;
     // RMSNorm in place on the staged vector
     float ss = 0.f;
@@ -256,7 +235,6 @@ __device__ __forceinline__ bool combine_split(float (*part)[R], float (&out)[R])
 // Skeleton shared by the three kernels: every warp owns row group `base + warp / KS` and the K-slice
 // `warp % KS`.  First pass: weights are requested BEFORE the dependency wait and the input staging.
 #define CC_GEMV_PROLOGUE(R_, NV_, ROWS_OF)                                                          \
-    if (cluster_nctarank() > 1) cluster_arrive_relaxed(); /* paired with the wait in stage_input */  \
     constexpr int GPB = kGemvWarps / KS;                                                            \
     const int warp = threadIdx.x >> 5;                                                              \
     const int klen = p.K / KS, k0 = (warp % KS) * klen;                                             \
@@ -462,10 +440,8 @@ static int launch_split(K1 k1, K2 k2, K4 k4, K8 k8, const P& p, int n_pairs, int
     int grid = (n_pairs + gpb - 1) / gpb;
     const int cap = sm_count() * 8;
     if (grid > cap) grid = cap;
-    // Input staging can be shared by the CTAs of a cluster (stage_input broadcasts over DSMEM), but measured on B200
-    // the gang scheduling + two cluster barriers cost 5-8 us per launch (profiles/r1_notes.md): clusters stay off.
-    const int cluster = 1;
-    grid = (grid + cluster - 1) / cluster * cluster;
+    // (sharing the input staging between the CTAs of a cluster over DSMEM was measured 5-8 us per launch SLOWER:
+    // gang scheduling + two cluster barriers, profiles/r1_notes.md)
     auto go = [&](auto kernel) -> int {
         static thread_local const void* raised[16] = {};
         if (smem > 48 * 1024) {  // raise the per-function cap once, to the device limit
@@ -486,21 +462,11 @@ static int launch_split(K1 k1, K2 k2, K4 k4, K8 k8, const P& p, int n_pairs, int
         cfg.blockDim = dim3(kGemvThreads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = stream;
-        cudaLaunchAttribute attr[2];
-        int na = 0;
-        if (cluster > 1) {
-            attr[na].id = cudaLaunchAttributeClusterDimension;
-            attr[na].val.clusterDim.x = cluster;
-            attr[na].val.clusterDim.y = attr[na].val.clusterDim.z = 1;
-            ++na;
-        }
-        if (pdl_enabled()) {
-            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attr[na].val.programmaticStreamSerializationAllowed = 1;
-            ++na;
-        }
-        cfg.attrs = attr;
-        cfg.numAttrs = na;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = pdl_enabled() ? 1 : 0;
         cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
         return e == cudaSuccess ? CC_OK : set_cuda_error(e, what);
     };
