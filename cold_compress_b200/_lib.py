@@ -23,7 +23,7 @@ FLAG_OVERLAP_PREDECESSOR = 1
 HYB_FULL, HYB_WINDOW, HYB_HEAVY_HITTER, HYB_SPECIAL, HYB_PUNC = 1, 2, 4, 8, 16
 
 _STATE_INTS = ("policy", "attn_mode", "n_kv_heads", "q_per_kv", "head_dim", "max_cache_length",
-               "global_tokens", "recent_window", "history_window", "pos_heads", "cts_heads", "reserved0")
+               "global_tokens", "recent_window", "history_window", "pos_heads", "cts_heads", "attn_thresholding")
 _STATE_PTRS = ("k_cache", "v_cache", "pos", "mask", "cache_cts", "attn_history_num", "attn_history_denom",
                "attn_counter", "attn_history_sum", "key_norm", "hyb_strategy_bits", "hyb_recent_window", "hyb_heavy_budget",
                "special_mask", "punc_mask", "num_special", "num_punc", "sync_words")

@@ -186,7 +186,7 @@ class KVCache(nn.Module):
         W = getattr(self, "history_window_size", 1)
         return [self.policy, self.attn_mode(), self.n_heads, G, self.head_dim, self.max_cache_length,
                 int(self.global_tokens), int(getattr(self, "recent_window", 0) or 0), int(W),
-                self.pos.shape[1], self.cache_cts.numel(), 0]
+                self.pos.shape[1], self.cache_cts.numel(), int(bool(getattr(self, "attn_thresholding", False)))]
 
     def _outputs(self, G, device, dtype):
         key = (G, device, dtype)
@@ -333,13 +333,18 @@ class KVCacheHeavyHitter(KVCacheHeadSpecific):
 
     def __init__(self, max_batch_size, n_heads, head_dim, dtype=torch.bfloat16, variable_length=False, **kwargs):
         super().__init__(max_batch_size, n_heads, head_dim, dtype, variable_length, **kwargs)
-        if getattr(self, "attn_thresholding", False):
-            raise NotImplementedError("attn_thresholding=True is not built (no BASELINE config uses it)")
         W, L = self.history_window_size, self.max_cache_length
-        if W != 1 and self.policy == _lib.POLICY_HEAVY_HITTER:
-            raise NotImplementedError("heavy_hitter kernel supports history_window_size=1 (the YAML default)")
-        num_dtype = torch.float64 if W == 1 else dtype
+        thresh = bool(getattr(self, "attn_thresholding", False))
+        if thresh and W == 1:
+            # the reference's `bool_history[..., 0] += indicator` cannot be executed by torch (cache.py:719)
+            raise ValueError("attn_thresholding needs history_window_size > 1")
+        # bool indicators if thresholding, fp64 running sum if the whole history is kept, else a ring (cache.py:661-667)
+        num_dtype = torch.bool if thresh else torch.float64 if W == 1 else dtype
         self.register_buffer("attn_history_num", torch.zeros((max_batch_size, n_heads, L, W), dtype=num_dtype))
+        if W > 1 and self.policy == _lib.POLICY_HEAVY_HITTER:
+            # exact running sum of each slot's ring, maintained by the kernel (the reference re-sums the ring)
+            self.register_buffer("attn_history_sum", torch.zeros((max_batch_size, n_heads, L), dtype=torch.float64),
+                                 persistent=False)
         self.register_buffer("attn_history_denom", torch.zeros((max_batch_size, n_heads, L), dtype=torch.int32))
         self.register_buffer("attn_counter", torch.zeros((1,), dtype=torch.int64))
 
@@ -348,6 +353,13 @@ class KVCacheHeavyHitter(KVCacheHeadSpecific):
         self.attn_history_num.zero_()
         self.attn_history_denom.zero_()
         self.attn_counter.zero_()
+        if hasattr(self, "attn_history_sum"):
+            self.attn_history_sum.zero_()
+
+    def resync_history(self):
+        """Recompute the running ring sums from the ring (after the ring was written from outside the kernel)."""
+        if hasattr(self, "attn_history_sum"):
+            self.attn_history_sum.copy_(self.attn_history_num.to(torch.float64).sum(dim=-1))
 
     def return_attn(self) -> bool:
         return True
@@ -366,6 +378,8 @@ class KVCacheHeavyHitter(KVCacheHeadSpecific):
         if attn.ndim == 4:
             attn = attn.squeeze(0).sum(dim=1) / (seq_len - input_pos)
         attn = attn.reshape(1, self.n_heads, -1, 1)
+        if getattr(self, "attn_thresholding", False):
+            attn = attn >= 1 / self.cache_cts      # indicator of above-uniform attention (cache.py:708)
         n = attn.shape[2]
         slot = int(self.attn_counter.item()) % self.history_window_size if self.history_window_size > 1 else 0
         col = self.attn_history_num[:, :, :, slot]
@@ -376,6 +390,7 @@ class KVCacheHeavyHitter(KVCacheHeadSpecific):
             col[:, :, :n] = attn[..., 0].to(col.dtype)
         self.attn_history_denom += 1
         self.attn_counter += 1
+        self.resync_history()
 
 
 class KVCacheHybrid(KVCacheHeavyHitter):
@@ -436,13 +451,8 @@ class KVCacheHybrid(KVCacheHeavyHitter):
         names = [self.hybrid_strategies[int(i)]["strategy"] for i in ids]
         self.requires_heavy_hitter = any("heavy_hitter" in n for n in names)
 
-    def resync_history(self):
-        """Recompute the running ring sums from the ring (after the ring was written from outside)."""
-        self.attn_history_sum.copy_(self.attn_history_num.to(torch.float64).sum(dim=-1))
-
     def reset(self):
         super().reset()
-        self.attn_history_sum.zero_()
         names = [s["strategy"] for s in self.hybrid_strategies]
         self.requires_heavy_hitter = any("heavy_hitter" in n for n in names)
         for n in ("special_mask", "num_special", "punc_mask", "num_punc"):
@@ -572,7 +582,6 @@ class KVCacheHybrid(KVCacheHeavyHitter):
             self.punc_mask[0, :, :S] = punc.view(1, -1).expand(H, -1).gather(1, order)
         if self.requires_heavy_hitter:
             self._seed_history(input_pos, cum_attn.gather(1, order).unsqueeze(0))
-            self.resync_history()
 
     def update_state(self, input_pos, k_val, v_val, is_prefill, attn, **kwargs):
         if is_prefill:

@@ -182,8 +182,10 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
                do_score = phases & CC_PHASE_SCORE;
     const int NS = p.n_stages, stride = p.lg_stride;
     // shared (cross-head) state is read by every cluster and written by one: order with an epoch barrier
+    // heavy hitter with a history window (W > 1): the shared step counter selects the ring column every head writes
+    const bool hh_ring = POLICY == CC_POLICY_HEAVY_HITTER && st.history_window > 1;
     const bool needs_epoch = (do_evict && (POLICY == CC_POLICY_RECENT_GLOBAL || POLICY == CC_POLICY_L2)) ||
-                             (hybrid && (do_evict || do_score));
+                             ((hybrid || hh_ring) && (do_evict || do_score));
 
     // chunk-cyclic ownership: local chunk j <-> global chunk rank + j*C; local row lr = j*CH + r
     const int n_chunks_total = (L + CH - 1) >> chs;
@@ -247,6 +249,11 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             }
         }
         live_limit = min(L, hyb_cts + ((do_evict && hyb_mode == kHybAppend) ? 1 : 0));
+    }
+    int32_t hh_cts = 0;   // cache_cts before this step (thresholded history compares against 1 / cache_cts)
+    if (hh_ring) {
+        hyb_counter = st.attn_counter[0];
+        hh_cts = st.cache_cts[0];
     }
     const int live_chunks_total = (live_limit + CH - 1) >> chs;
     const int nlc_live = do_attend ? (live_chunks_total > rank ? (live_chunks_total - rank + C - 1) >> csh : 0) : 0;
@@ -327,7 +334,15 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
                 if (s >= L) continue;
                 const int ps = posp[s];
                 // cache.py:727-749: mean accumulated attention; globals & recent -> 1.0; unfilled -> 0.0
-                float avg = __fdiv_rn(__double2float_rn(num[s]), (float)max(den[s], 1));
+                float avg;
+                if (!hh_ring) {
+                    avg = __fdiv_rn(__double2float_rn(num[s]), (float)max(den[s], 1));
+                } else {
+                    // sum of the slot's ring (kept as an exact fp64 running sum): bf16 ring -> bf16(fp32 sum),
+                    // thresholded (bool) ring -> integer count; / clamp(denom, 1, W)   (cache.py:727-738)
+                    const float hs = __double2float_rn(st.attn_history_sum[(size_t)h * L + s]);
+                    avg = __fdiv_rn(st.attn_thresholding ? hs : bf16_round(hs), (float)min(max(den[s], 1), st.history_window));
+                }
                 if (ps < st.global_tokens || ps >= ipos - st.recent_window) avg = 1.0f;
                 if (ps == -1) avg = 0.0f;
                 const uint64_t k = ((uint64_t)float_order_key(avg) << 32) | (uint32_t)s;
@@ -732,7 +747,8 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             if (!hybrid || hyb_mode == kHybAppend) st.mask[(size_t)h * L + widx] = 1;
             if (p.a.fill_idx && POLICY != CC_POLICY_EXTERNAL) p.a.fill_idx[h] = widx;
             if (POLICY == CC_POLICY_HEAVY_HITTER && !do_score) {
-                reinterpret_cast<double*>(st.attn_history_num)[(size_t)h * L + widx] = 0.0;  // cache.py:753-763
+                if (hh_ring) st.attn_history_sum[(size_t)h * L + widx] = 0.0;   // the ring row is cleared below
+                else reinterpret_cast<double*>(st.attn_history_num)[(size_t)h * L + widx] = 0.0;  // cache.py:753-763
                 st.attn_history_denom[(size_t)h * L + widx] = 0;
             }
             if (hybrid && is_punc && st.punc_mask) st.punc_mask[(size_t)h * L + widx] = 1;  // cache.py:1011-1016
@@ -751,23 +767,40 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
             }
         }
     }
+    if (hh_ring && i_own) {
+        // the evicted slot's history restarts (cache.py:753-763): clear its ring row, except the column this very
+        // step writes when the score update is fused into the same launch
+        const int W = st.history_window;
+        const int keep = (do_score && NAIVE) ? (int)(hyb_counter % W) : -1;
+        if (st.attn_thresholding) {
+            uint8_t* rowp = reinterpret_cast<uint8_t*>(st.attn_history_num) + ((size_t)h * L + widx) * W;
+            for (int w = tid; w < W; w += kThreads) if (w != keep) rowp[w] = 0;
+        } else {
+            uint16_t* rowp = reinterpret_cast<uint16_t*>(st.attn_history_num) + ((size_t)h * L + widx) * W;
+            for (int w = tid; w < W; w += kThreads) if (w != keep) rowp[w] = 0;
+        }
+    }
     if (needs_epoch && h == 0 && rank == 0 && tid == 32) {
         // generation bump (and the shared step counter): only after every cluster has arrived
         const int32_t g0 = ld_acquire_gpu(&st.sync_words[1]);
         const int32_t target = (g0 + 1) * H;
         while (ld_acquire_gpu(&st.sync_words[0]) - target < 0) {}
-        if (hybrid && do_score && NAIVE) st.attn_counter[0] = hyb_counter + 1;
+        if ((hybrid || hh_ring) && do_score && NAIVE) st.attn_counter[0] = hyb_counter + 1;
         st_release_gpu(&st.sync_words[1], g0 + 1);
     }
 
     // ---- 9b. GQA pooling (model.py:413-418) and the score update (cache.py:716-723)
     {
-        const bool hh_score = do_score && NAIVE && POLICY == CC_POLICY_HEAVY_HITTER;
+        const bool hh_score = do_score && NAIVE && POLICY == CC_POLICY_HEAVY_HITTER && !hh_ring;
+        const bool hhr_score = do_score && NAIVE && hh_ring;
         const bool ring_score = do_score && NAIVE && hybrid;
         const int W = st.history_window;
-        const int wslot = ring_score ? (int)(hyb_counter % W) : 0;
+        const int wslot = (ring_score || hhr_score) ? (int)(hyb_counter % W) : 0;
+        // thresholded history: indicator p >= 1 / cache_cts with cache_cts AFTER this step's insertion (cache.py:330,
+        // 708).  While the cache is filling the inserted slot is an unfilled one (score 0.0, first index): + 1.
+        const float thr = hhr_score ? __fdiv_rn(1.0f, (float)(hh_cts + ((do_evict && has_slot && hh_cts < L) ? 1 : 0))) : 0.f;
         __nv_bfloat16* probs = reinterpret_cast<__nv_bfloat16*>(p.a.probs);
-        if (NAIVE && (hh_score || ring_score || (do_attend && probs))) {
+        if (NAIVE && (hh_score || hhr_score || ring_score || (do_attend && probs))) {
             for (int lr = tid; lr < local_rows; lr += kThreads) {
                 const int s = slot_of(lr);
                 if (s >= L) continue;
@@ -789,6 +822,25 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
                     const bool fresh = has_slot && s == widx;  // evicted slot's history restarts (cache.py:753-763)
                     num[s] = (fresh ? 0.0 : num[s]) + (double)pooled;
                     den[s] = (fresh ? 0 : den[s]) + 1;
+                } else if (hhr_score) {
+                    // ring[s][counter % W] = pooled (or its indicator), denominators + 1; the evicted slot starts
+                    // from a cleared ring (cache.py:716-723, 753-763).  hsum = exact running sum of the ring.
+                    int32_t* den = st.attn_history_denom + (size_t)h * L;
+                    double* hs = st.attn_history_sum + (size_t)h * L + s;
+                    const bool fresh = has_slot && s == widx;
+                    den[s] = (fresh ? 0 : den[s]) + 1;
+                    if (st.attn_thresholding) {
+                        uint8_t* cell = reinterpret_cast<uint8_t*>(st.attn_history_num) + ((size_t)h * L + s) * W + wslot;
+                        const float v = pooled >= thr ? 1.f : 0.f;
+                        const float old = fresh ? 0.f : (float)(*cell != 0);
+                        *hs = ((fresh ? 0.0 : *hs) - (double)old) + (double)v;
+                        *cell = (uint8_t)(v != 0.f);
+                    } else {
+                        __nv_bfloat16* cell = reinterpret_cast<__nv_bfloat16*>(st.attn_history_num) + ((size_t)h * L + s) * W + wslot;
+                        const float old = fresh ? 0.f : __bfloat162float(*cell);
+                        *hs = ((fresh ? 0.0 : *hs) - (double)old) + (double)pooled;
+                        *cell = __float2bfloat16_rn(pooled);
+                    }
                 } else if (ring_score) {
                     // ring[s][counter % W] = pooled; the evicted slot keeps its ring (the reference's reset is a
                     // silent no-op, cache.py:993-996).  Only live slots can hold non-zero history.
@@ -963,8 +1015,12 @@ static int validate(const CcCacheState* st, const CcDecodeArgs* a) {
     if (naive && (phases & CC_PHASE_SCORE) && !(phases & CC_PHASE_ATTEND) && !a->probs)
         return set_error(CC_ERR_INVALID_ARG, "score-only phase needs probs");
     if (st->policy == CC_POLICY_HEAVY_HITTER) {
-        if (st->history_window != 1) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "heavy_hitter kernel needs history_window_size == 1");
+        if (st->history_window < 1) return set_error(CC_ERR_INVALID_ARG, "history_window must be >= 1");
         if (!st->attn_history_num || !st->attn_history_denom || !st->attn_counter) return set_error(CC_ERR_INVALID_ARG, "null heavy_hitter state");
+        if (st->history_window > 1 && !st->attn_history_sum)
+            return set_error(CC_ERR_INVALID_ARG, "heavy_hitter with a history window needs the running ring sums (attn_history_sum)");
+        if (st->attn_thresholding && st->history_window == 1)
+            return set_error(CC_ERR_INVALID_ARG, "attn_thresholding needs history_window_size > 1 (the reference cannot add into a bool history)");
         if (!naive) return set_error(CC_ERR_INVALID_ARG, "heavy_hitter needs the naive (probability-returning) attention mode");
     }
     if (st->policy == CC_POLICY_HYBRID) {
@@ -988,7 +1044,8 @@ static int validate(const CcCacheState* st, const CcDecodeArgs* a) {
 }
 
 static bool plan_needs_epoch(const CcCacheState* st) {
-    return st->policy == CC_POLICY_RECENT_GLOBAL || st->policy == CC_POLICY_L2 || st->policy == CC_POLICY_HYBRID;
+    return st->policy == CC_POLICY_RECENT_GLOBAL || st->policy == CC_POLICY_L2 || st->policy == CC_POLICY_HYBRID ||
+           (st->policy == CC_POLICY_HEAVY_HITTER && st->history_window > 1);
 }
 
 int decode_step_impl(const CcCacheState* st, const CcDecodeArgs* a, cudaStream_t stream) {

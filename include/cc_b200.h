@@ -85,7 +85,7 @@ typedef struct CcCacheState {
     int32_t history_window;    /* W: 1 => fp64 running sum, >1 => bf16 ring (cache.py:661-667)   */
     int32_t pos_heads;         /* rows of `pos`: 1 (head-constant) or Hkv (head-specific)        */
     int32_t cts_heads;         /* rows of `cache_cts`: 1, or Hkv for variable_length (hybrid)    */
-    int32_t reserved0;
+    int32_t attn_thresholding; /* heavy_hitter, W > 1: history holds bool indicators p >= 1 / cache_cts (cache.py:708) */
 
     void*    k_cache;          /* bf16 [Hkv, L, D]   cache.py:185,200                    */
     void*    v_cache;          /* bf16 [Hkv, L, D]   cache.py:186,201                    */
@@ -94,10 +94,11 @@ typedef struct CcCacheState {
     int32_t* cache_cts;        /* i32  [cts_heads]   cache.py:219-222                    */
 
     /* heavy_hitter / hybrid (cache.py:646-679) */
-    void*    attn_history_num;   /* f64 [Hkv, L] when W == 1; bf16 [Hkv, L, W] otherwise */
+    void*    attn_history_num;   /* f64 [Hkv, L] when W == 1; bf16 [Hkv, L, W] otherwise (bool [Hkv, L, W] with
+                                    attn_thresholding)                                     */
     int32_t* attn_history_denom; /* i32 [Hkv, L]                                          */
     int64_t* attn_counter;       /* i64 [1]                                               */
-    double*  attn_history_sum;   /* hybrid (W > 1) only: f64 [Hkv, L] running sum of each slot's ring,
+    double*  attn_history_sum;   /* W > 1 (hybrid, windowed heavy_hitter): f64 [Hkv, L] running sum of each slot's ring,
                                     kept by the kernel so the ring is not re-summed every step (the
                                     reference re-sums it, cache.py:855-859); NULL otherwise            */
 

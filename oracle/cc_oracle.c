@@ -143,28 +143,6 @@ static void evict_l2(const CcCacheState* st, int32_t input_pos, int64_t* idx) {
     }
 }
 
-/* KVCacheHeavyHitter._eviction_idx, W == 1 (cache.py:725-765) */
-static void evict_heavy_hitter(const CcCacheState* st, int32_t input_pos, int64_t* idx) {
-    int H = st->n_kv_heads, L = st->max_cache_length;
-    double* num = (double*)st->attn_history_num;
-    for (int h = 0; h < H; ++h) {
-        const int32_t* pos = st->pos + (size_t)h * L;
-        int32_t* den = st->attn_history_denom + (size_t)h * L;
-        float best = 0;
-        int64_t bi = -1;
-        for (int s = 0; s < L; ++s) {
-            int32_t d = den[s] < 1 ? 1 : den[s];
-            float avg = (float)num[(size_t)h * L + s] / (float)d;
-            if (pos[s] < st->global_tokens || pos[s] >= input_pos - st->recent_window) avg = 1.0f;
-            if (pos[s] == -1) avg = 0.0f;
-            if (bi < 0 || avg < best) { best = avg; bi = s; }
-        }
-        idx[h] = bi;
-        num[(size_t)h * L + bi] = 0.0; /* history of the evicted slot restarts (cache.py:753-763) */
-        den[bi] = 0;
-    }
-}
-
 /* bf16 ring sum (cache.py:855-859): torch accumulates the W bf16 values in fp32 in an
  * unspecified vectorised order and rounds the result to bf16.  Here the sum is taken in fp64
  * (exact for any realistic dynamic range, hence order independent), rounded to fp32, then to
@@ -174,6 +152,47 @@ static float ring_sum_bf16(const uint16_t* ring, int W) {
     double acc = 0.0;
     for (int w = 0; w < W; ++w) acc += (double)bf2f(ring[w]);
     return bfround((float)acc);
+}
+
+/* KVCacheHeavyHitter._eviction_idx (cache.py:725-765).  W == 1: fp64 running sum / max(denom, 1).
+ * W > 1: sum of the slot's ring of the last W pooled probabilities (bf16 ring: cache.py:646-667; with
+ * attn_thresholding a bool ring of "p >= 1 / cache_cts" indicators, whose sum is an integer count)
+ * / clamp(denom, 1, W).  The evicted slot's ring and denominator are zeroed (753-763). */
+static void evict_heavy_hitter(const CcCacheState* st, int32_t input_pos, int64_t* idx) {
+    int H = st->n_kv_heads, L = st->max_cache_length, W = st->history_window;
+    int thresh = st->attn_thresholding != 0;
+    for (int h = 0; h < H; ++h) {
+        const int32_t* pos = st->pos + (size_t)h * L;
+        int32_t* den = st->attn_history_denom + (size_t)h * L;
+        float best = 0;
+        int64_t bi = -1;
+        for (int s = 0; s < L; ++s) {
+            float num;
+            int32_t d = den[s] < 1 ? 1 : den[s];
+            if (W == 1) {
+                num = (float)((double*)st->attn_history_num)[(size_t)h * L + s];
+            } else if (thresh) {
+                const uint8_t* ring = (const uint8_t*)st->attn_history_num + ((size_t)h * L + s) * W;
+                int cnt = 0;
+                for (int w = 0; w < W; ++w) cnt += ring[w] != 0;
+                num = (float)cnt;
+                if (d > W) d = W;
+            } else {
+                num = ring_sum_bf16((const uint16_t*)st->attn_history_num + ((size_t)h * L + s) * W, W);
+                if (d > W) d = W;
+            }
+            float avg = num / (float)d;
+            if (pos[s] < st->global_tokens || pos[s] >= input_pos - st->recent_window) avg = 1.0f;
+            if (pos[s] == -1) avg = 0.0f;
+            if (bi < 0 || avg < best) { best = avg; bi = s; }
+        }
+        idx[h] = bi;
+        /* history of the evicted slot restarts (cache.py:753-763) */
+        if (W == 1) ((double*)st->attn_history_num)[(size_t)h * L + bi] = 0.0;
+        else if (thresh) memset((uint8_t*)st->attn_history_num + ((size_t)h * L + bi) * W, 0, (size_t)W);
+        else memset((uint16_t*)st->attn_history_num + ((size_t)h * L + bi) * W, 0, (size_t)W * 2);
+        den[bi] = 0;
+    }
 }
 
 /* KVCacheHybrid._select_fill_idx / _eviction_idx_for_head (cache.py:844-950).
@@ -321,7 +340,6 @@ int cc_oracle_decode_step(const CcCacheState* st, const CcDecodeArgs* a) {
         }
         case CC_POLICY_L2: evict_l2(st, input_pos, idx); break;
         case CC_POLICY_HEAVY_HITTER:
-            if (st->history_window != 1) return fail(CC_ERR_UNSUPPORTED_SHAPE, "heavy_hitter needs W == 1");
             evict_heavy_hitter(st, input_pos, idx);
             break;
         case CC_POLICY_HYBRID:
@@ -391,6 +409,12 @@ int cc_oracle_decode_step(const CcCacheState* st, const CcDecodeArgs* a) {
         if (W == 1) {
             double* num = (double*)st->attn_history_num;
             for (size_t i = 0; i < (size_t)H * L; ++i) num[i] += (double)bf2f(probs[i]);
+        } else if (st->policy == CC_POLICY_HEAVY_HITTER && st->attn_thresholding) {
+            /* (attn >= 1 / cache_cts).int() stored into a bool ring (cache.py:708-709, 719): bf16 vs fp32 compare */
+            uint8_t* ring = (uint8_t*)st->attn_history_num;
+            int64_t w = st->attn_counter[0] % W;
+            float thr = 1.0f / (float)st->cache_cts[0];
+            for (size_t i = 0; i < (size_t)H * L; ++i) ring[i * W + w] = bf2f(probs[i]) >= thr;
         } else {
             uint16_t* ring = (uint16_t*)st->attn_history_num;
             int64_t w = st->attn_counter[0] % W;

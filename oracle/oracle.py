@@ -26,7 +26,7 @@ class CacheState(C.Structure):
 
     _fields_ = [(n, C.c_int32) for n in (
         "policy", "attn_mode", "n_kv_heads", "q_per_kv", "head_dim", "max_cache_length",
-        "global_tokens", "recent_window", "history_window", "pos_heads", "cts_heads", "reserved0")] + [
+        "global_tokens", "recent_window", "history_window", "pos_heads", "cts_heads", "attn_thresholding")] + [
         (n, C.c_void_p) for n in (
             "k_cache", "v_cache", "pos", "mask", "cache_cts", "attn_history_num",
             "attn_history_denom", "attn_counter", "attn_history_sum", "key_norm", "hyb_strategy_bits",
@@ -87,7 +87,7 @@ class OracleCache:
 
     def __init__(self, policy: str, n_kv_heads: int, q_per_kv: int, head_dim: int, max_cache_length: int,
                  global_tokens: int = 4, recent_window: int = 10, history_window: int = 1,
-                 hybrid_strategies=None, attn_mode: int | None = None):
+                 hybrid_strategies=None, attn_mode: int | None = None, attn_thresholding: bool = False):
         H, L, D = n_kv_heads, max_cache_length, head_dim
         self.policy, self.H, self.G, self.D, self.L = policy, H, q_per_kv, D, L
         self.global_tokens, self.recent_window = global_tokens, recent_window
@@ -95,6 +95,7 @@ class OracleCache:
         self.pos_heads = H if head_specific else 1
         self.cts_heads = H if policy == "hybrid" else 1
         self.W = 400 if policy == "hybrid" else history_window
+        self.attn_thresholding = bool(attn_thresholding) and policy == "heavy_hitter"
         self.attn_mode = attn_mode if attn_mode is not None else (
             ATTN_NAIVE if policy in ("heavy_hitter", "hybrid") else ATTN_MATH)
         self.k_cache = torch.zeros(H, L, D, dtype=torch.bfloat16)
@@ -108,7 +109,8 @@ class OracleCache:
         self.special_mask = self.punc_mask = self.num_special = self.num_punc = None
         if policy in ("heavy_hitter", "hybrid"):
             self.attn_history_num = (torch.zeros(H, L, dtype=torch.float64) if self.W == 1
-                                     else torch.zeros(H, L, self.W, dtype=torch.bfloat16))
+                                     else torch.zeros(H, L, self.W, dtype=torch.bool if self.attn_thresholding
+                                                      else torch.bfloat16))
             self.attn_history_denom = torch.zeros(H, L, dtype=torch.int32)
             self.attn_counter = torch.zeros(1, dtype=torch.int64)
         if policy == "l2":
@@ -137,6 +139,7 @@ class OracleCache:
         st.n_kv_heads, st.q_per_kv, st.head_dim, st.max_cache_length = self.H, self.G, self.D, self.L
         st.global_tokens, st.recent_window, st.history_window = self.global_tokens, self.recent_window, self.W
         st.pos_heads, st.cts_heads = self.pos_heads, self.cts_heads
+        st.attn_thresholding = int(self.attn_thresholding)
         for name, t in (("k_cache", self.k_cache), ("v_cache", self.v_cache), ("pos", self.pos),
                         ("mask", self.mask), ("cache_cts", self.cache_cts),
                         ("attn_history_num", self.attn_history_num),

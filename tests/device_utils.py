@@ -11,9 +11,10 @@ STATE_NAMES = ("k_cache", "v_cache", "pos", "mask", "cache_cts", "attn_history_n
                "attn_counter", "key_norm", "special_mask", "punc_mask", "num_special", "num_punc")
 
 
-def cache_kwargs(strategy, L, g=4, rw=10, hybrid_strategies=None, token_ids=None, min_recovery_frac=0.9):
+def cache_kwargs(strategy, L, g=4, rw=10, hybrid_strategies=None, token_ids=None, min_recovery_frac=0.9, W=1,
+                 thresholding=False):
     kw = dict(max_cache_length=L, global_tokens=g, max_seq_length=1 << 20, cache_bits=None, recent_window=rw,
-              history_window_size=1, attn_thresholding=False)
+              history_window_size=W, attn_thresholding=thresholding)
     if strategy == "hybrid":
         kw.update(hybrid_strategies=hybrid_strategies, min_recovery_frac=min_recovery_frac,
                   token_ids=token_ids or {"special": [[0], [1]], "punctuation": [5]})
@@ -40,6 +41,7 @@ def load_state(cache, tensors: dict):
 def device_cache_from_golden(g: Golden, device="cuda"):
     m = g.meta
     cache = make_device_cache(m["strategy"], g.Hkv, g.D, g.L, device, g=m["global_tokens"], rw=m["recent_window"],
+                              W=m.get("history_window_size", 1), thresholding=m.get("attn_thresholding", False),
                               hybrid_strategies=m.get("hybrid_strategies"),
                               token_ids={"special": m.get("special", [[0], [1]]),
                                          "punctuation": m.get("punctuation", [5])})
@@ -51,8 +53,9 @@ def device_cache_from_golden(g: Golden, device="cuda"):
 
 def oracle_from_golden(g: Golden) -> OracleCache:
     m = g.meta
-    oc = OracleCache(g.policy, g.Hkv, g.G, g.D, g.L, m["global_tokens"], m["recent_window"], 1,
-                     hybrid_strategies=m.get("hybrid_strategies"))
+    oc = OracleCache(g.policy, g.Hkv, g.G, g.D, g.L, m["global_tokens"], m["recent_window"],
+                     m.get("history_window_size", 1), hybrid_strategies=m.get("hybrid_strategies"),
+                     attn_thresholding=m.get("attn_thresholding", False))
     oc.load_state(g.state("init"))
     if g.policy == "hybrid":
         oc.set_head_strategies(g.z["init_cache_strategies"])
@@ -65,8 +68,9 @@ def oracle_like(cache, G) -> OracleCache:
     """An oracle cache holding a copy of a product cache's current state."""
     pol = {0: "external", 1: "recent_global", 2: "l2", 3: "heavy_hitter", 4: "hybrid"}[cache.policy]
     oc = OracleCache(pol, cache.n_heads, G, cache.head_dim, cache.max_cache_length, int(cache.global_tokens),
-                     int(getattr(cache, "recent_window", 0) or 0), 1,
-                     hybrid_strategies=getattr(cache, "hybrid_strategies", None))
+                     int(getattr(cache, "recent_window", 0) or 0), int(getattr(cache, "history_window_size", 1)),
+                     hybrid_strategies=getattr(cache, "hybrid_strategies", None),
+                     attn_thresholding=bool(getattr(cache, "attn_thresholding", False)))
     oc.load_state({n: getattr(cache, n).detach().cpu() for n in STATE_NAMES
                    if torch.is_tensor(getattr(cache, n, None))})
     if pol == "hybrid":

@@ -50,6 +50,11 @@ FIXTURES = {
     "hh_snapkv": dict(strategy="heavy_hitter", Hkv=4, G=4, D=128, L=128, S=300, T=100),
     "hh_g7_bias": dict(strategy="heavy_hitter", Hkv=2, G=7, D=128, L=96, S=40, T=120, bias=True),
     "hh_d64_ragged": dict(strategy="heavy_hitter", Hkv=2, G=2, D=64, L=40, S=25, T=100),
+    # heavy hitter with a bounded history window (bf16 ring, cache.py:661-667) and with thresholded (bool) history
+    "hh_window4": dict(strategy="heavy_hitter", Hkv=2, G=4, D=128, L=64, S=100, T=120, history_window_size=4),
+    # attn_thresholding=True cannot be recorded: the unmodified reference raises in update_state on this image's
+    # torch 2.11 ("Index put requires the source and destination dtypes match, got Bool ... Int", cache.py:708-721),
+    # so the thresholded variant is pinned on the oracle's reading of the code only (tests/test_gpu_parity.py).
     "rg_compress": dict(strategy="recent_global", Hkv=2, G=4, D=128, L=64, S=128, T=100),
     "l2_compress": dict(strategy="l2", Hkv=4, G=2, D=128, L=64, S=100, T=120),
     "l2_fill": dict(strategy="l2", Hkv=2, G=4, D=64, L=48, S=20, T=80),
@@ -122,7 +127,8 @@ def make(name: str, spec: dict, seed: int = 1234) -> dict:
     prompt_strategy = {"heavy_hitter": "heavy_hitter", "l2": "l2", "recent_global": "recent_global",
                        "full": "full", "hybrid": "full"}[strategy]
     kwargs = dict(max_cache_length=L, global_tokens=4, max_seq_length=S + T, cache_bits=None,
-                  recent_window=10, history_window_size=1, attn_thresholding=False,
+                  recent_window=10, history_window_size=spec.get("history_window_size", 1),
+                  attn_thresholding=spec.get("attn_thresholding", False),
                   prompt_compression_strategy=prompt_strategy)
     if strategy == "hybrid":
         kwargs.update(hybrid_strategies=spec["hybrid_strategies"], min_recovery_frac=spec["min_recovery_frac"],

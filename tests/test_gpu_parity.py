@@ -91,6 +91,9 @@ SHAPES = [
     ("heavy_hitter", 4, 7, 128, 556, 556, 40),     # Qwen2-7B grouping, ragged length
     ("heavy_hitter", 1, 4, 128, 1024, 1024, 24),   # one local head (tp.py world size 8)
     ("heavy_hitter", 2, 8, 64, 300, 120, 40),      # D=64, G=8
+    ("heavy_hitter:w16", 8, 4, 128, 1024, 1000, 60),  # bounded history window (bf16 ring), fill then evict
+    ("heavy_hitter:w4", 2, 2, 64, 200, 60, 80),
+    ("heavy_hitter:w8t", 4, 4, 128, 256, 200, 120),    # thresholded (bool) history; oracle-pinned only (the reference raises)
     ("l2", 8, 4, 128, 512, 512, 48),               # BASELINE config 3 shape
     ("l2", 2, 6, 128, 200, 64, 40),
     ("recent_global", 8, 4, 128, 64, 64, 40),      # BASELINE config 1 shape
@@ -103,7 +106,9 @@ SHAPES = [
 @pytest.mark.parametrize("strategy,Hkv,G,D,L,n_filled,steps", SHAPES)
 def test_decode_matches_oracle_on_seeded_state(strategy, Hkv, G, D, L, n_filled, steps):
     from device_utils import make_device_cache, oracle_like, synthetic_fill
-    cache = make_device_cache(strategy, Hkv, D, L)
+    strategy, _, opt = strategy.partition(":")
+    extra = dict(W=int(opt.strip("wt")), thresholding=opt.endswith("t")) if opt else {}
+    cache = make_device_cache(strategy, Hkv, D, L, **extra)
     next_pos = synthetic_fill(cache, n_filled, seed=L + Hkv, first_pos=0)
     cache._q_per_kv = G
     oc = oracle_like(cache, G)
@@ -131,14 +136,17 @@ def test_decode_matches_oracle_on_seeded_state(strategy, Hkv, G, D, L, n_filled,
         a, b = getattr(cache, n, None), getattr(oc, n, None)
         if torch.is_tensor(a) and torch.is_tensor(b):
             assert torch.equal(a.cpu().reshape(b.shape).to(b.dtype), b), f"final {n} differs"
+    if hasattr(cache, "attn_history_sum"):  # the kernel's running ring sums stay exact
+        assert torch.equal(cache.attn_history_sum.cpu(), cache.attn_history_num.double().sum(-1).cpu())
 
 
-def test_three_call_surface_equals_fused_step():
+@pytest.mark.parametrize("W", [1, 6])
+def test_three_call_surface_equals_fused_step(W):
     """update_kv -> attend -> update_state (three launches, phase masks) == decode_step (one launch)."""
     from device_utils import make_device_cache, synthetic_fill
     Hkv, G, D, L = 4, 4, 128, 256
-    a = make_device_cache("heavy_hitter", Hkv, D, L)
-    b = make_device_cache("heavy_hitter", Hkv, D, L)
+    a = make_device_cache("heavy_hitter", Hkv, D, L, W=W)
+    b = make_device_cache("heavy_hitter", Hkv, D, L, W=W)
     for c in (a, b):
         synthetic_fill(c, L, seed=7)
         c._q_per_kv = G

@@ -22,8 +22,9 @@ from oracle.oracle import ATTN_MATH, OracleCache
 
 def make_oracle(g: Golden) -> OracleCache:
     m = g.meta
-    oc = OracleCache(g.policy, g.Hkv, g.G, g.D, g.L, m["global_tokens"], m["recent_window"], 1,
-                     hybrid_strategies=m.get("hybrid_strategies"))
+    oc = OracleCache(g.policy, g.Hkv, g.G, g.D, g.L, m["global_tokens"], m["recent_window"],
+                     m.get("history_window_size", 1), hybrid_strategies=m.get("hybrid_strategies"),
+                     attn_thresholding=m.get("attn_thresholding", False))
     oc.load_state(g.state("init"))
     if g.policy == "hybrid":
         oc.set_head_strategies(g.z["init_cache_strategies"])
@@ -74,6 +75,9 @@ def test_oracle_reproduces_reference_trace(name):
         if oc.W == 1:
             # fp64 sums of bf16 probabilities: equal up to the (rare) 1-ulp probability differences
             assert torch.allclose(oc.attn_history_num, num_ref, rtol=0, atol=4e-3 * max(1, prob_mismatch))
+        elif oc.attn_history_num.dtype == torch.bool:
+            # indicators p >= 1 / cache_cts: a 1-ulp probability difference can flip one that sits on the threshold
+            assert int((oc.attn_history_num != num_ref.bool()).sum()) <= max(2, prob_mismatch)
         else:
             ring_diff = (bits(oc.attn_history_num).astype(np.int32) - bits(num_ref).astype(np.int32))
             assert np.abs(ring_diff).max() <= 2 and (ring_diff != 0).sum() <= max(2, prob_mismatch)
