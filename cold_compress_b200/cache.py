@@ -599,6 +599,98 @@ class KVCacheHybrid(KVCacheHeavyHitter):
         return stats
 
 
+
+class KVCacheAnalysis(KVCacheFull):
+    """`debug_<strategy>`: a full cache that also drives a shadow cache with the compression strategy and records the
+    attention mass the strategy would have lost at every decode step (reference cache.py:1291-1420).
+
+    Decode = the same kernel three times: the full cache appends and attends (returning the pooled probabilities),
+    the shadow cache takes its eviction decision + overwrite (phase EVICT_FILL) and its score update (phase SCORE)
+    from the full cache's probabilities gathered at the positions the shadow still holds."""
+    relevant_kwargs = ["max_cache_length", "max_seq_length", "cache_bits", "history_window_size", "recent_window",
+                       "attn_thresholding", "global_tokens", "prompt_compression_strategy"]
+
+    def __init__(self, max_batch_size, n_heads, head_dim, dtype=torch.bfloat16, cache_strategy="heavy_hitter", **kwargs):
+        full_kwargs = {"global_tokens": 0, "max_cache_length": kwargs["max_seq_length"],
+                       "prompt_compression_strategy": kwargs["prompt_compression_strategy"]}
+        super().__init__(max_batch_size, n_heads, head_dim, dtype, **full_kwargs)
+        self.compressed = get_cache_constructor(cache_strategy)[0](max_batch_size, n_heads, head_dim, dtype, **kwargs)
+        if not self.compressed.return_attn():
+            # the reference's update_state dereferences attn (None for strategies that return no attention)
+            raise ValueError(f"debug_{cache_strategy}: the attention-loss analysis needs a strategy that returns attention")
+        self.register_buffer("attention_losses", torch.full((self.max_cache_length,), -1, dtype=dtype))
+        self.register_buffer("attention_loss_ctr", torch.zeros((1,), dtype=torch.int))
+        self.prompt_compressor = get_prompt_compressor_constructor(self.prompt_compression_strategy)(
+            head_specific=self.compressed.head_specific, **kwargs)
+        self.head_specific = self.compressed.head_specific
+
+    def return_attn(self):
+        return self.compressed.return_attn()
+
+    def reset(self):
+        super().reset()
+        self.compressed.reset()
+        self.attention_losses.fill_(-1)
+        self.attention_loss_ctr.zero_()
+
+    def memory_usage(self):
+        return super().memory_usage() + self.compressed.memory_usage()
+
+    # ---- reference surface -----------------------------------------------------------------
+    def update_kv(self, input_pos, k_val, v_val, is_prefill, **kwargs):
+        out = super().update_kv(input_pos, k_val, v_val, is_prefill, **kwargs)
+        if input_pos.shape[-1] < self.compressed.max_cache_length:   # else: compressed in update_state (needs attention)
+            self.compressed.update_kv(input_pos, k_val, v_val, is_prefill, **kwargs)
+        return out
+
+    def _cum_attn(self, input_pos, attn):
+        from .prompt_compression import PrefillAttnStats
+        if isinstance(attn, PrefillAttnStats):
+            return attn.col_sum / (attn.col_sum.shape[-1] - input_pos)
+        return attn
+
+    def update_state(self, input_pos, k_val, v_val, is_prefill, attn, **kwargs):
+        comp = self.compressed
+        if is_prefill and input_pos.shape[-1] > comp.max_cache_length:
+            keep, k_c, v_c, cum = self.prompt_compressor(input_pos, k_val, v_val, attn=attn)
+            comp.update_kv(keep, k_c, v_c, True)
+            comp.update_state(keep, k_c, v_c, True, cum)
+        elif is_prefill:
+            comp.update_state(input_pos, k_val, v_val, True, self._cum_attn(input_pos, attn))
+        else:
+            self._shadow_score(input_pos, k_val, v_val, attn)
+
+    def _shadow_score(self, input_pos, k_val, v_val, attn):
+        """attn [1, H, (1,) Lfull]: pooled probabilities over the full cache (slot == position)."""
+        comp = self.compressed
+        attn = attn.reshape(1, self.n_heads, -1)
+        idx = comp.pos.long().expand(1, self.n_heads, -1)
+        idx = idx.masked_fill(idx < 0, attn.shape[-1] - 1)   # unfilled shadow slots read the last (still empty, 0.0) position
+        attn_c = attn.gather(2, idx)
+        comp.update_state(input_pos, k_val, v_val, False, attn_c)
+        loss = (1 - attn_c.sum(dim=-1)).mean()         # attention mass of the evicted tokens
+        self.attention_losses.index_put_((self.attention_loss_ctr.long(),), loss.to(self.attention_losses.dtype))
+        self.attention_loss_ctr += 1
+
+    # ---- decode: full-cache step, then the shadow's two phases ---------------------------------
+    def decode_step(self, q, k_val, v_val, input_pos, **kwargs):
+        kw = {k: v for k, v in kwargs.items() if k in ("overlap_predecessor", "input_ids")}
+        y = self._launch(_lib.PHASE_EVICT_FILL | _lib.PHASE_ATTEND, q, k_val, v_val, input_pos, **kw)
+        self.compressed._q_per_kv = self._q_per_kv
+        self.compressed.update_kv(input_pos, k_val, v_val, False, input_ids=kwargs.get("input_ids"))
+        self._shadow_score(input_pos, k_val, v_val, self._out["probs"])
+        return y
+
+    def compute_statistics(self, seq_len):
+        stats = super().compute_statistics(seq_len)
+        losses = self.attention_losses[: int(self.attention_loss_ctr)]
+        assert not torch.any(losses == -1)
+        for k in range(500, len(losses), 500):
+            stats[f"attention_loss@{k}"] = losses[:k].mean().item()
+        stats["attention_loss"] = losses.mean().item()
+        return stats
+
+
 # --------------------------------------------------------------------------- registry
 
 _REGISTRY = {
@@ -613,6 +705,11 @@ def get_cache_constructor(cache_strategy):
         cls = _REGISTRY[cache_strategy]
         return cls, cls.relevant_kwargs
     if cache_strategy.startswith("debug"):
-        raise NotImplementedError("debug_* (KVCacheAnalysis, reference cache.py:1291-1420) is out of the hot path; "
-                                  "listed as next in DESIGN.md")
+        import re
+        inner = re.sub(r"debug_+", "", cache_strategy).strip()
+        relevant = get_cache_constructor(inner)[1] + ["prompt_compression_strategy"]
+
+        def make(max_batch_size, n_heads, head_dim, dtype, **kwargs):
+            return KVCacheAnalysis(max_batch_size, n_heads, head_dim, dtype, cache_strategy=inner, **kwargs)
+        return make, relevant
     raise ValueError(f"Invalid cache strategy: {cache_strategy}")

@@ -353,7 +353,7 @@ class Attention(nn.Module):
             y, attn = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=True), None
         input_pos, k, v, attn = self.compress_prompt(input_pos, k, v, attn)
         cache.update_kv(input_pos, k, v, True, **kwargs)
-        if isinstance(attn, PrefillAttnStats) and not hasattr(cache, "profile_and_update"):
+        if isinstance(attn, PrefillAttnStats) and not hasattr(cache, "profile_and_update") and not hasattr(cache, "compressed"):
             # prompt fit the cache: seed with the column means directly
             seq_len = attn.col_sum.shape[-1]
             attn = attn.col_sum / (seq_len - input_pos)

@@ -55,6 +55,8 @@ FIXTURES = {
     # attn_thresholding=True cannot be recorded: the unmodified reference raises in update_state on this image's
     # torch 2.11 ("Index put requires the source and destination dtypes match, got Bool ... Int", cache.py:708-721),
     # so the thresholded variant is pinned on the oracle's reading of the code only (tests/test_gpu_parity.py).
+    # debug_<strategy> (KVCacheAnalysis, cache.py:1291-1420): full cache + shadow heavy-hitter cache + attention loss
+    "debug_hh": dict(strategy="debug_heavy_hitter", Hkv=2, G=4, D=128, L=32, S=60, T=50),
     "rg_compress": dict(strategy="recent_global", Hkv=2, G=4, D=128, L=64, S=128, T=100),
     "l2_compress": dict(strategy="l2", Hkv=4, G=2, D=128, L=64, S=100, T=120),
     "l2_fill": dict(strategy="l2", Hkv=2, G=4, D=64, L=48, S=20, T=80),
@@ -125,7 +127,7 @@ def make(name: str, spec: dict, seed: int = 1234) -> dict:
     attn = attn.to(torch.bfloat16).eval()
 
     prompt_strategy = {"heavy_hitter": "heavy_hitter", "l2": "l2", "recent_global": "recent_global",
-                       "full": "full", "hybrid": "full"}[strategy]
+                       "full": "full", "hybrid": "full", "debug_heavy_hitter": "heavy_hitter"}[strategy]
     kwargs = dict(max_cache_length=L, global_tokens=4, max_seq_length=S + T, cache_bits=None,
                   recent_window=10, history_window_size=spec.get("history_window_size", 1),
                   attn_thresholding=spec.get("attn_thresholding", False),
@@ -135,13 +137,20 @@ def make(name: str, spec: dict, seed: int = 1234) -> dict:
                       token_ids={"special": spec.get("special", [[0], [1]]),
                                  "punctuation": spec.get("punctuation", [5])})
     cls, relevant = get_cache_constructor(strategy)
+    if strategy.startswith("debug"):
+        # the reference cannot construct KVCacheAnalysis as shipped: its full-cache kwargs omit cache_bits, which
+        # KVCache.__init__ reads (cache.py:181, 1317-1324).  A class attribute supplies the missing default; every
+        # line of reference code still runs unmodified.
+        import cache as ref_cache_mod
+        ref_cache_mod.KVCacheAnalysis.cache_bits = None
     cache = cls(1, Hkv, D, torch.bfloat16, **{k: kwargs[k] for k in relevant})
     attn.kv_cache = cache
     attn.prompt_compressor = get_prompt_compressor_constructor(prompt_strategy)(
         head_specific=cache.head_specific, **{k: kwargs[k] for k in relevant})
     freqs = ref_model.precompute_freqs_cis(cfg.block_size, D, cfg.rope_base, torch.bfloat16)
 
-    rec = {k: [] for k in ("q", "k_new", "v_new", "y", "probs", "fill_idx", "pos_after", "input_pos", "input_id")}
+    rec = {k: [] for k in ("q", "k_new", "v_new", "y", "probs", "fill_idx", "pos_after", "input_pos", "input_id",
+                           "cpos_after")}
     state = {"decode": False}
 
     real_sdpa = ref_model.scaled_dot_product_attention
@@ -200,6 +209,8 @@ def make(name: str, spec: dict, seed: int = 1234) -> dict:
             rec["input_pos"].append(int(pos_t))
             rec["input_id"].append(int(tok))
             rec["pos_after"].append(cache.pos[0].numpy().astype(np.int16).copy())
+            if hasattr(cache, "compressed"):
+                rec["cpos_after"].append(cache.compressed.pos[0].numpy().astype(np.int16).copy())
             pos_t += 1
         snapshot(cache, "final", out)
     ref_model.scaled_dot_product_attention = real_sdpa

@@ -22,8 +22,8 @@ def small_model(strategy="heavy_hitter", L=64, n_layer=2, seed=0, device="cuda")
                 p.normal_(0.0, 0.05)
     model = model.to(device=device, dtype=torch.bfloat16).eval()
     ck = dict(max_cache_length=[float(L)], cache_bits=None, cache_length_pattern="tile", cache_strategy=[strategy],
-              cache_strategy_pattern="tile", prompt_compression_strategy=[strategy], global_tokens=4, recent_window=10,
-              history_window_size=1, attn_thresholding=False, min_recovery_frac=0.9)
+              cache_strategy_pattern="tile", prompt_compression_strategy=[strategy.replace("debug_", "")],
+              global_tokens=4, recent_window=10, history_window_size=1, attn_thresholding=False, min_recovery_frac=0.9)
     gu.setup_caches(model, SyntheticTokenizer(), torch.device(device), 400, ck)
     return model
 
@@ -128,3 +128,30 @@ def test_hybrid_end_to_end_prefill_profile_and_graph_decode():
         assert int(ca.cache_cts.max()) <= 100 + 40 and int(ca.cache_cts.min()) >= 4
     stats = a.get_cache_stats(100, 40)
     assert "compression_ratio_avg" in stats and "avg_strategy_idx_avg" in stats
+
+
+def test_debug_cache_end_to_end_records_attention_loss():
+    """debug_heavy_hitter through setup_caches / generate: full-cache attention, shadow heavy-hitter cache, attention
+    loss per decode step; eager and CUDA-graph decode agree; a larger shadow cache loses less attention mass."""
+    from cold_compress_b200 import generation_utils as gu
+    torch.manual_seed(21)
+    prompt = torch.randint(0, 1000, (150,), dtype=torch.int32, device="cuda")
+    prefill, eager = gu.compile_funcs(False)
+    _, graphed = gu.compile_funcs(True)
+    losses = {}
+    for L in (32, 96):
+        a = small_model("debug_heavy_hitter", L=L, seed=6)
+        b = small_model("debug_heavy_hitter", L=L, seed=6)
+        seq_a, _, _ = gu.generate(a, prompt, prefill, eager, max_new_tokens=30)
+        seq_b, _, _ = gu.generate(b, prompt, prefill, graphed, max_new_tokens=30)
+        assert torch.equal(seq_a, seq_b)
+        ca, cb = a.layers[0].attention.kv_cache, b.layers[0].attention.kv_cache
+        assert type(ca).__name__ == "KVCacheAnalysis" and ca.compressed.max_cache_length == L
+        # generate() feeds the last sampled token back only as an output, so 29 decode steps touched the caches
+        n = int(ca.attention_loss_ctr)
+        assert n >= 29 and torch.equal(ca.attention_losses[:n], cb.attention_losses[:n])
+        assert int(ca.compressed.cache_cts) == L and int((ca.pos >= 0).sum()) == 150 + n
+        stats = a.get_cache_stats(150, 30)
+        assert 0.0 <= stats["attention_loss_avg"] <= 1.0
+        losses[L] = stats["attention_loss_avg"]
+    assert losses[96] < losses[32], losses
