@@ -882,7 +882,8 @@ using KernelFn = void (*)(const DecodeParams);
 template <int D, int G>
 static KernelFn pick_policy(int policy, bool naive) {
     switch (policy) {
-    case CC_POLICY_EXTERNAL: return naive ? nullptr : (KernelFn)cc_decode_kernel<D, G, CC_POLICY_EXTERNAL, false>;
+    case CC_POLICY_EXTERNAL: return naive ? (KernelFn)cc_decode_kernel<D, G, CC_POLICY_EXTERNAL, true>   // debug_* full cache
+                                          : (KernelFn)cc_decode_kernel<D, G, CC_POLICY_EXTERNAL, false>;
     case CC_POLICY_RECENT_GLOBAL: return naive ? nullptr : (KernelFn)cc_decode_kernel<D, G, CC_POLICY_RECENT_GLOBAL, false>;
     case CC_POLICY_L2: return naive ? nullptr : (KernelFn)cc_decode_kernel<D, G, CC_POLICY_L2, false>;
     case CC_POLICY_HEAVY_HITTER: return naive ? (KernelFn)cc_decode_kernel<D, G, CC_POLICY_HEAVY_HITTER, true> : nullptr;
