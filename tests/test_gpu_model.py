@@ -137,9 +137,9 @@ def test_debug_cache_end_to_end_records_attention_loss():
     torch.manual_seed(21)
     prompt = torch.randint(0, 1000, (150,), dtype=torch.int32, device="cuda")
     prefill, eager = gu.compile_funcs(False)
-    _, graphed = gu.compile_funcs(True)
     losses = {}
     for L in (32, 96):
+        _, graphed = gu.compile_funcs(True)   # a captured graph belongs to one model
         a = small_model("debug_heavy_hitter", L=L, seed=6)
         b = small_model("debug_heavy_hitter", L=L, seed=6)
         seq_a, _, _ = gu.generate(a, prompt, prefill, eager, max_new_tokens=30)
