@@ -295,6 +295,12 @@ def run_ours(args):
         os.dup2(real_stdout, 1)
     if rank == 0:
         out["roofline"] = roof
+        # context for tokens/s: one token streams every non-embedding weight of this rank plus the live K/V once
+        wbytes = sum(p.numel() * p.element_size() for n, p in model.named_parameters() if "tok_embeddings" not in n)
+        kvbytes = sum(2 * c.n_heads * c.max_cache_length * c.head_dim * 2 for c in (b.attention.kv_cache for b in model.layers))
+        peak, _src = peaks()
+        out["step_stream"] = {"bytes_per_token_per_gpu": wbytes + kvbytes, "achieved_gbs": round((wbytes + kvbytes) / (dev_s / args.steps) / 1e9, 1),
+                              "frac_of_hbm_peak": round((wbytes + kvbytes) / (dev_s / args.steps) / 1e9 / peak, 4)}
         out["cpu_baseline"] = (cpu_reference(sample_seconds=20.0, warmup=1)
                                if world == 1 and not os.environ.get("CC_BENCH_NCU") and not os.environ.get("CC_TP_FAKE") else None)
         print(json.dumps(out), flush=True)

@@ -179,6 +179,8 @@ struct WarpDots {
         float acc[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = 0.f;
+        // rolling refill: the moment slot u has been consumed its registers are re-armed with the loads of the next
+        // round, so (NV - 1) / NV of the warp's loads stay in flight instead of draining to zero once per round
         while (true) {
 #pragma unroll
             for (int u = 0; u < NV; ++u) {
@@ -193,14 +195,14 @@ struct WarpDots {
                         for (int j = 0; j < 8; ++j) acc[r] = fmaf(f[j], x[j], acc[r]);
                     }
                 }
+                const int kn = k + (NV + u) * 256;
+                if (kn < k1) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) w[u][r] = ldg_stream(rows[r] + kn);
+                }
             }
             k += NV * 256;
             if (k >= k1) break;
-#pragma unroll
-            for (int u = 0; u < NV; ++u)
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if (k + u * 256 < k1) w[u][r] = ldg_stream(rows[r] + k + u * 256);
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) out[r] = warp_sum(acc[r]);
@@ -261,7 +263,7 @@ struct QkvParams {
 };
 
 template <int KS>
-__global__ void __launch_bounds__(kGemvThreads) rmsnorm_qkv_rope_kernel(const __grid_constant__ QkvParams p) {
+__global__ void __launch_bounds__(kGemvThreads, 3) rmsnorm_qkv_rope_kernel(const __grid_constant__ QkvParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem_raw);
     __shared__ float scratch[kGemvWarps];
@@ -314,7 +316,7 @@ struct GemvParams {
 };
 
 template <int KS>
-__global__ void __launch_bounds__(kGemvThreads) gemv_residual_kernel(const __grid_constant__ GemvParams p) {
+__global__ void __launch_bounds__(kGemvThreads, 3) gemv_residual_kernel(const __grid_constant__ GemvParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem_raw);
     __shared__ float scratch[kGemvWarps];
@@ -356,7 +358,7 @@ struct GateParams {
 };
 
 template <int KS>
-__global__ void __launch_bounds__(kGemvThreads) rmsnorm_ffn_gate_kernel(const __grid_constant__ GateParams p) {
+__global__ void __launch_bounds__(kGemvThreads, 3) rmsnorm_ffn_gate_kernel(const __grid_constant__ GateParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem_raw);
     __shared__ float scratch[kGemvWarps];
