@@ -68,6 +68,7 @@ EXPORTS = {
     "cc_key_norms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "cc_prefill_gather": (C.c_int, [C.POINTER(CcCacheState), C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "cc_requantize_cache": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 7),
     "cc_prefill_attention_workspace": (C.c_uint64, [C.c_int32] * 5),
     "cc_prefill_attention": (C.c_int, [C.POINTER(CcPrefillAttnArgs), C.c_void_p]),
     "cc_rmsnorm_qkv_rope": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -33,7 +33,7 @@ _STRATEGIES = ["full", "random", "recent_global", "heavy_hitter", "l2", "hybrid"
 _CACHE_FLAGS = [
     ("--max_cache_length", dict(type=float, default=[1.0], nargs="+",
                                 help="Cache size per layer: 0<x<=1 is a fraction of |prompt|+max_new_tokens, >1 absolute. Tiled over layers."), True),
-    ("--cache_bits", dict(default=None, type=int, choices=[2, 4, 8], help="KV quantisation bits (not in this build)."), True),
+    ("--cache_bits", dict(default=None, type=int, choices=[2, 4, 8], help="Quantise the KV cache to this many bits."), True),
     ("--cache_length_pattern", dict(default="tile", choices=["tile", "repeat", "funnel", "pyramid"]), True),
     ("--cache_strategy", dict(default=["full"], nargs="+",
                               choices=_STRATEGIES + [f"debug_{s}" for s in _STRATEGIES]), True),
@@ -91,10 +91,10 @@ class KVCache(nn.Module):
             setattr(self, key, value)
         if max_batch_size != 1:
             raise NotImplementedError("batch size is fixed to 1 (reference model.py:188-189)")
-        if getattr(self, "cache_bits", None) is not None:
-            raise NotImplementedError("--cache_bits (quantised KV) is not built yet; see DESIGN.md (next)")
-        self.cache_bits = None
-        self.quantize, self.n_bit = False, None
+        self.cache_bits = getattr(self, "cache_bits", None)
+        self.quantize, self.n_bit = self.cache_bits is not None, self.cache_bits
+        if self.quantize and self.cache_bits not in (2, 4, 8):
+            raise ValueError("Only 2-bit, 4-bit, and 8-bit quantization are supported")
         if not hasattr(self, "global_tokens"):
             self.global_tokens = 0
         self.n_heads, self.head_dim = n_heads, head_dim
@@ -106,6 +106,15 @@ class KVCache(nn.Module):
         self.register_buffer("pos", torch.full((max_batch_size, n_heads if head_specific else 1, L), -1, dtype=torch.int))
         self.register_buffer("cache_cts", torch.zeros(n_heads if variable_length else 1, dtype=torch.int))
         self.register_buffer("mask", torch.zeros((max_batch_size, n_heads, 1, L), dtype=torch.bool))
+        if self.quantize:
+            # --cache_bits: k_cache / v_cache above are the de-quantised WORKING copies the kernels read; after every
+            # step they go through the reference's quantise -> de-quantise round trip (cc_requantize_cache), which
+            # also leaves the packed codes and per-slot statistics the reference would hold (cache.py:176-200, 283-309)
+            nbytes = n_heads * L * head_dim * self.n_bit // 8
+            self.register_buffer("k_codes", torch.zeros(nbytes, dtype=torch.uint8))
+            self.register_buffer("v_codes", torch.zeros(nbytes, dtype=torch.uint8))
+            for name in ("k_scales", "v_scales", "k_zero_points", "v_zero_points"):
+                self.register_buffer(name, torch.zeros(L, dtype=dtype))
         # kernel-side scratch (not part of the reference state)
         self.register_buffer("_sync_words", torch.zeros(8, dtype=torch.int32), persistent=False)
         self.register_buffer("_fill_idx", torch.zeros(n_heads, dtype=torch.int64), persistent=False)
@@ -133,7 +142,16 @@ class KVCache(nn.Module):
     def compression_ratio(self, seq_len):
         n = seq_len - 1  # the final token is never passed to the cache
         assert torch.all(self.cache_cts <= self.max_cache_length)
-        return ((n - self.cache_cts.float()) / n).mean()
+        size = self.cache_cts.float()
+        if self.n_bit is not None:
+            size = size * (self.n_bit / 16.0)
+        return ((n - size) / n).mean()
+
+    def requantize(self):
+        """End of a cache update with --cache_bits: the whole cache through quantise -> de-quantise (cache.py:338)."""
+        if self.quantize:
+            ops.requantize_cache(self.k_cache, self.v_cache, self.n_bit, self.k_codes, self.v_codes, self.k_scales,
+                                 self.k_zero_points, self.v_scales, self.v_zero_points)
 
     def compute_statistics(self, seq_len):
         return {"compression_ratio": self.compression_ratio(seq_len).item(), "cache_memory_gb": self.memory_usage()}
@@ -151,7 +169,10 @@ class KVCache(nn.Module):
         return self.return_kv_cache()
 
     def update_state(self, input_pos, k_val, v_val, is_prefill, attn, **kwargs):
-        """No-op for caches that keep no score state (reference cache.py:342-346)."""
+        """No-op for caches that keep no score state (reference cache.py:342-346).  With --cache_bits the step ends
+        here: the reference re-quantises at the end of update_kv but hands attention the un-quantised tensors, so in
+        the three-call surface the round trip has to wait until attention has read the cache."""
+        self.requantize()
         return None
 
     # ---- fused / phased decode step -----------------------------------------------------
@@ -163,7 +184,9 @@ class KVCache(nn.Module):
         overlap_predecessor=True promises that the kernel launched just before on this stream does not
         write this cache (CC_FLAG_OVERLAP_PREDECESSOR): the step then starts fetching early.
         warm_l2=[tensors]: read-only tensors (up to 3) the step pulls into L2 while HBM is idle."""
-        return self._launch(_lib.PHASE_ALL, q, k_val, v_val, input_pos, **kwargs)
+        y = self._launch(_lib.PHASE_ALL, q, k_val, v_val, input_pos, **kwargs)
+        self.requantize()
+        return y
 
     def attend(self, q, input_pos):
         """Attention over the current cache content only (kernel phase ATTEND): (y, pooled probs or None)."""
@@ -316,6 +339,8 @@ class KVCacheL2(KVCacheHeadSpecific):
 
     def __init__(self, max_batch_size, n_heads, head_dim, dtype=torch.bfloat16, **kwargs):
         super().__init__(max_batch_size, n_heads, head_dim, dtype, **kwargs)
+        if self.quantize:   # the reference takes the norm of its int8 cache at prefill and raises (cache.py:611)
+            raise NotImplementedError("l2 cannot be combined with --cache_bits (nor can it in the reference)")
         self.register_buffer("key_norm", torch.zeros((max_batch_size, n_heads, self.max_cache_length), dtype=dtype))
 
     def reset(self):
@@ -370,8 +395,9 @@ class KVCacheHeavyHitter(KVCacheHeadSpecific):
         if not is_prefill:
             # kernel phase SCORE with the pooled probabilities the caller holds
             self._launch(_lib.PHASE_SCORE, None, None, None, input_pos, probs_in=attn.to(self.k_cache.dtype))
-            return
-        self._seed_history(input_pos, attn)
+        else:
+            self._seed_history(input_pos, attn)
+        self.requantize()
 
     def _seed_history(self, input_pos, attn):
         """Prefill seed of the score history (reference cache.py:697-723): attn is either the full
@@ -405,6 +431,8 @@ class KVCacheHybrid(KVCacheHeavyHitter):
     def __init__(self, max_batch_size, n_heads, head_dim, dtype=torch.bfloat16, **kwargs):
         self.attn_thresholding = False
         kwargs = dict(kwargs, history_window_size=400, recent_window=None, attn_thresholding=False)
+        if kwargs.get("cache_bits") is not None:
+            raise NotImplementedError("hybrid cannot be combined with --cache_bits")
         super().__init__(max_batch_size, n_heads, head_dim, dtype, variable_length=True, **kwargs)
         names = [s["strategy"] for s in self.hybrid_strategies]
         L = self.max_cache_length

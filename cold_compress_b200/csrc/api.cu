@@ -62,6 +62,13 @@ int cc_prefill_gather(const CcCacheState* state, const void* k_prompt, const voi
                                    (cudaStream_t)stream);
 }
 
+int cc_requantize_cache(void* k_cache, void* v_cache, int32_t n_kv_heads, int32_t max_cache_length, int32_t head_dim, int32_t n_bit,
+                        uint8_t* k_codes, uint8_t* v_codes, void* k_scales, void* k_zero_points, void* v_scales,
+                        void* v_zero_points, void* stream) {
+    return cc::requantize_cache_impl(k_cache, v_cache, n_kv_heads, max_cache_length, head_dim, n_bit, k_codes, v_codes, k_scales,
+                                     k_zero_points, v_scales, v_zero_points, (cudaStream_t)stream);
+}
+
 uint64_t cc_prefill_attention_workspace(int32_t seq_len, int32_t n_kv_heads, int32_t q_per_kv, int32_t obs_len,
                                         int32_t n_windows) {
     return cc::prefill_attention_workspace_impl(seq_len, n_kv_heads, q_per_kv, obs_len, n_windows);

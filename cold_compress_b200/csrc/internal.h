@@ -17,6 +17,8 @@ int prefill_gather_impl(const CcCacheState* st, const void* k_prompt, const void
                         cudaStream_t stream);
 int prefill_attention_impl(const CcPrefillAttnArgs* a, cudaStream_t stream);
 unsigned long long prefill_attention_workspace_impl(int S, int Hkv, int G, int obs_len, int n_windows);
+int requantize_cache_impl(void* k_cache, void* v_cache, int H, int L, int D, int n_bit, uint8_t* k_codes, uint8_t* v_codes,
+                          void* k_scales, void* k_zeros, void* v_scales, void* v_zeros, cudaStream_t stream);
 int rmsnorm_qkv_rope_impl(const void* x, const void* norm_w, float eps, const void* wqkv, const void* bias,
                           const void* freqs, const int32_t* input_pos, void* q, void* k, void* v, int dim,
                           int n_q_heads, int n_kv_heads, int head_dim, const CcTpArgs* tp, cudaStream_t stream);

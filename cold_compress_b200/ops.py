@@ -26,6 +26,8 @@ _library.define(
 _library.define("key_norms(Tensor k, Tensor(a!) key_norm) -> ()")
 _library.define(
     "prefill_gather(Tensor(a!)[] state, int[] meta, Tensor k_prompt, Tensor v_prompt, Tensor keep_idx) -> ()")
+_library.define("requantize_cache(Tensor(a!) k_cache, Tensor(b!) v_cache, int n_bit, Tensor(c!) k_codes, Tensor(d!) v_codes, "
+                "Tensor(e!) k_scales, Tensor(f!) k_zero_points, Tensor(g!) v_scales, Tensor(h!) v_zero_points) -> ()")
 _library.define(
     "prefill_attention(Tensor q, Tensor k, Tensor v, Tensor(a!) y, int attn_mode, int obs_len, int[] windows, "
     "Tensor(b!)? col_sum, Tensor(c!)? obs_sum, Tensor(d!)? band_sum, Tensor(e!)? workspace) -> ()")
@@ -107,6 +109,15 @@ def _prefill_gather(state, meta, k_prompt, v_prompt, keep_idx):
                                      n_keep, prompt_len, _stream()), "cc_prefill_gather")
 
 
+def _requantize_cache(k_cache, v_cache, n_bit, k_codes, v_codes, k_scales, k_zero_points, v_scales, v_zero_points):
+    """k_cache / v_cache bf16 [1, H, L, D] (or [H, L, D]) contiguous, re-quantised in place."""
+    _require_cuda(k_cache, v_cache, k_codes, v_codes, k_scales, k_zero_points, v_scales, v_zero_points)
+    H, L, D = k_cache.shape[-3:]
+    _lib.check(_lib.load().cc_requantize_cache(k_cache.data_ptr(), v_cache.data_ptr(), H, L, D, int(n_bit), _ptr(k_codes),
+                                               _ptr(v_codes), _ptr(k_scales), _ptr(k_zero_points), _ptr(v_scales),
+                                               _ptr(v_zero_points), _stream()), "cc_requantize_cache")
+
+
 def prefill_attention_workspace(seq_len, n_kv_heads, q_per_kv, obs_len, n_windows) -> int:
     return int(_lib.load().cc_prefill_attention_workspace(seq_len, n_kv_heads, q_per_kv, obs_len, n_windows))
 
@@ -186,19 +197,21 @@ _library.impl("rmsnorm_ffn_gate", _rmsnorm_ffn_gate, "CUDA")
 _library.impl("key_norms", _key_norms, "CUDA")
 _library.impl("prefill_gather", _prefill_gather, "CUDA")
 _library.impl("prefill_attention", _prefill_attention, "CUDA")
+_library.impl("requantize_cache", _requantize_cache, "CUDA")
 
 
 def _no_cpu(*_a, **_k):
     raise _lib.CcError("cold_compress_b200 ops have no CPU implementation: the decode path is CUDA (sm_100a) only")
 
 
-for _name in ("decode_step", "key_norms", "prefill_gather", "prefill_attention", "rmsnorm_qkv_rope", "gemv_residual", "rmsnorm_ffn_gate"):
+for _name in ("decode_step", "key_norms", "prefill_gather", "prefill_attention", "requantize_cache", "rmsnorm_qkv_rope", "gemv_residual", "rmsnorm_ffn_gate"):
     _library.impl(_name, _no_cpu, "CPU")
 
 decode_step = torch.ops.cold_compress_b200.decode_step
 key_norms = torch.ops.cold_compress_b200.key_norms
 prefill_gather = torch.ops.cold_compress_b200.prefill_gather
 prefill_attention = torch.ops.cold_compress_b200.prefill_attention
+requantize_cache = torch.ops.cold_compress_b200.requantize_cache
 rmsnorm_qkv_rope = torch.ops.cold_compress_b200.rmsnorm_qkv_rope
 gemv_residual = torch.ops.cold_compress_b200.gemv_residual
 rmsnorm_ffn_gate = torch.ops.cold_compress_b200.rmsnorm_ffn_gate

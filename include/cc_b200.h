@@ -182,6 +182,18 @@ int cc_prefill_gather(const CcCacheState* state, const void* k_prompt, const voi
                       int32_t prompt_len, void* stream);
 
 /*
+ * Quantised KV cache (--cache_bits 2 / 4 / 8): the round trip dequantize(quantize(cache)) the reference applies to
+ * the WHOLE cache in every update_kv (cache.py:283-338; quantization_utils.py:4-46), in place on the bf16 working
+ * cache [Hkv, L, D].  Groups are one slot across all heads and channels (axis=2); min/max, scale = (max - min)
+ * .clamp(1e-6) / (2^n - 1), zero point = min + scale * 2^(n-1), code = round((x - min) / scale) clamped, value =
+ * (code - 2^(n-1)) * scale + zero point, every step a bf16 op as in the reference.  Optional outputs: the packed codes
+ * (Hkv*L*D*n_bit/8 bytes, quantization_utils.pack_low_bit_tensor order) and the per-slot statistics (bf16 [L]).
+ */
+int cc_requantize_cache(void* k_cache, void* v_cache, int32_t n_kv_heads, int32_t max_cache_length, int32_t head_dim,
+                        int32_t n_bit, uint8_t* k_codes, uint8_t* v_codes, void* k_scales, void* k_zero_points,
+                        void* v_scales, void* v_zero_points, void* stream);
+
+/*
  * Causal prompt attention on the tensor cores (tcgen05) with the reductions of the GQA-pooled
  * probability map that prompt compression and the score-keeping caches consume, in one pass:
  * the [Hq, S, S] attention map of the reference is never materialised.

@@ -12,8 +12,8 @@ STATE_NAMES = ("k_cache", "v_cache", "pos", "mask", "cache_cts", "attn_history_n
 
 
 def cache_kwargs(strategy, L, g=4, rw=10, hybrid_strategies=None, token_ids=None, min_recovery_frac=0.9, W=1,
-                 thresholding=False):
-    kw = dict(max_cache_length=L, global_tokens=g, max_seq_length=1 << 20, cache_bits=None, recent_window=rw,
+                 thresholding=False, bits=None):
+    kw = dict(max_cache_length=L, global_tokens=g, max_seq_length=1 << 20, cache_bits=bits, recent_window=rw,
               history_window_size=W, attn_thresholding=thresholding)
     if strategy == "hybrid":
         kw.update(hybrid_strategies=hybrid_strategies, min_recovery_frac=min_recovery_frac,
@@ -42,10 +42,13 @@ def device_cache_from_golden(g: Golden, device="cuda"):
     m = g.meta
     cache = make_device_cache(m["strategy"], g.Hkv, g.D, g.L, device, g=m["global_tokens"], rw=m["recent_window"],
                               W=m.get("history_window_size", 1), thresholding=m.get("attn_thresholding", False),
-                              hybrid_strategies=m.get("hybrid_strategies"),
+                              bits=m.get("cache_bits"), hybrid_strategies=m.get("hybrid_strategies"),
                               token_ids={"special": m.get("special", [[0], [1]]),
                                          "punctuation": m.get("punctuation", [5])})
-    load_state(cache, g.state("init"))
+    init = dict(g.state("init"))
+    if m.get("cache_bits"):   # the reference holds integer codes between steps; the product holds the de-quantised view
+        init["k_cache"], init["v_cache"] = init.pop("k_cache_dq"), init.pop("v_cache_dq")
+    load_state(cache, init)
     if m["strategy"] == "hybrid":
         cache.set_head_strategies(g.z["init_cache_strategies"])
     return cache

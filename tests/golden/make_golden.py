@@ -57,6 +57,11 @@ FIXTURES = {
     # so the thresholded variant is pinned on the oracle's reading of the code only (tests/test_gpu_parity.py).
     # debug_<strategy> (KVCacheAnalysis, cache.py:1291-1420): full cache + shadow heavy-hitter cache + attention loss
     "debug_hh": dict(strategy="debug_heavy_hitter", Hkv=2, G=4, D=128, L=32, S=60, T=50),
+    # quantised KV (--cache_bits): the whole cache is de-quantised, updated and re-quantised every step
+    # (cache.py:283-338, quantization_utils.py), groups = one slot across all heads
+    "hh_bits8": dict(strategy="heavy_hitter", Hkv=2, G=4, D=128, L=48, S=80, T=80, cache_bits=8),
+    "hh_bits4": dict(strategy="heavy_hitter", Hkv=2, G=2, D=64, L=40, S=30, T=80, cache_bits=4),
+    "rg_bits2": dict(strategy="recent_global", Hkv=2, G=4, D=128, L=32, S=60, T=60, cache_bits=2),
     "rg_compress": dict(strategy="recent_global", Hkv=2, G=4, D=128, L=64, S=128, T=100),
     "l2_compress": dict(strategy="l2", Hkv=4, G=2, D=128, L=64, S=100, T=120),
     "l2_fill": dict(strategy="l2", Hkv=2, G=4, D=64, L=48, S=20, T=80),
@@ -98,6 +103,14 @@ def snapshot(cache, prefix: str, out: dict):
             out[key] = t.numpy().astype(np.uint8)
         else:
             out[key] = t.numpy().copy()
+    if getattr(cache, "quantize", False):
+        from quantization_utils import dequantize_tensor
+        for n in ("k", "v"):
+            dq = dequantize_tensor(getattr(cache, f"{n}_cache"), getattr(cache, f"{n}_scales"),
+                                   getattr(cache, f"{n}_zero_points"), cache.cache_shape, n_bit=cache.n_bit, axis=2)
+            out[f"{prefix}_{n}_cache_dq__bf16"] = u16(dq)
+            out[f"{prefix}_{n}_scales__bf16"] = u16(getattr(cache, f"{n}_scales"))
+            out[f"{prefix}_{n}_zero_points__bf16"] = u16(getattr(cache, f"{n}_zero_points"))
     # Hybrid replaces these buffers by plain attributes during profiling (cache.py:1147,1151,1240)
     for name in ("cache_cts", "num_special", "num_punc"):
         if hasattr(cache, name) and torch.is_tensor(getattr(cache, name)):
@@ -128,7 +141,7 @@ def make(name: str, spec: dict, seed: int = 1234) -> dict:
 
     prompt_strategy = {"heavy_hitter": "heavy_hitter", "l2": "l2", "recent_global": "recent_global",
                        "full": "full", "hybrid": "full", "debug_heavy_hitter": "heavy_hitter"}[strategy]
-    kwargs = dict(max_cache_length=L, global_tokens=4, max_seq_length=S + T, cache_bits=None,
+    kwargs = dict(max_cache_length=L, global_tokens=4, max_seq_length=S + T, cache_bits=spec.get("cache_bits"),
                   recent_window=10, history_window_size=spec.get("history_window_size", 1),
                   attn_thresholding=spec.get("attn_thresholding", False),
                   prompt_compression_strategy=prompt_strategy)

@@ -8,7 +8,8 @@ import numpy as np
 import torch
 
 GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
-ALL_FIXTURES = sorted(p.stem for p in GOLDEN_DIR.glob("*.npz") if not p.stem.startswith(("prefill_", "debug_")))
+ALL_FIXTURES = sorted(p.stem for p in GOLDEN_DIR.glob("*.npz")
+                      if not p.stem.startswith(("prefill_", "debug_")) and "_bits" not in p.stem)
 
 
 def bf(a: np.ndarray) -> torch.Tensor:
