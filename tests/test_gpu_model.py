@@ -8,7 +8,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def small_model(strategy="heavy_hitter", L=64, n_layer=2, seed=0, device="cuda"):
+def small_model(strategy="heavy_hitter", L=64, n_layer=2, seed=0, device="cuda", bits=None):
     from cold_compress_b200 import generation_utils as gu
     from cold_compress_b200.model import ModelArgs, Transformer
     from cold_compress_b200.tokenizer import SyntheticTokenizer
@@ -21,7 +21,7 @@ def small_model(strategy="heavy_hitter", L=64, n_layer=2, seed=0, device="cuda")
             if "norm" not in name:
                 p.normal_(0.0, 0.05)
     model = model.to(device=device, dtype=torch.bfloat16).eval()
-    ck = dict(max_cache_length=[float(L)], cache_bits=None, cache_length_pattern="tile", cache_strategy=[strategy],
+    ck = dict(max_cache_length=[float(L)], cache_bits=bits, cache_length_pattern="tile", cache_strategy=[strategy],
               cache_strategy_pattern="tile", prompt_compression_strategy=[strategy.replace("debug_", "")],
               global_tokens=4, recent_window=10, history_window_size=1, attn_thresholding=False, min_recovery_frac=0.9)
     gu.setup_caches(model, SyntheticTokenizer(), torch.device(device), 400, ck)
@@ -155,3 +155,32 @@ def test_debug_cache_end_to_end_records_attention_loss():
         assert 0.0 <= stats["attention_loss_avg"] <= 1.0
         losses[L] = stats["attention_loss_avg"]
     assert losses[96] < losses[32], losses
+
+
+@pytest.mark.parametrize("strategy,bits", [("heavy_hitter", 8), ("recent_global", 4)])
+def test_quantised_cache_end_to_end(strategy, bits):
+    """--cache_bits through setup_caches / generate: eager and CUDA-graph decode agree token for token, the cache the
+    kernels read is exactly dequantize(codes), and the statistics report the reduced footprint."""
+    from cold_compress_b200 import generation_utils as gu
+    from oracle import quant
+    torch.manual_seed(13)
+    prompt = torch.randint(0, 1000, (120,), dtype=torch.int32, device="cuda")
+    prefill, eager = gu.compile_funcs(False)
+    _, graphed = gu.compile_funcs(True)
+    a, b = small_model(strategy, seed=8, bits=bits), small_model(strategy, seed=8, bits=bits)
+    seq_a, _, _ = gu.generate(a, prompt, prefill, eager, max_new_tokens=24)
+    seq_b, _, _ = gu.generate(b, prompt, prefill, graphed, max_new_tokens=24)
+    assert torch.equal(seq_a, seq_b)
+    full = small_model(strategy, seed=8)
+    seq_f, _, _ = gu.generate(full, prompt, prefill, eager, max_new_tokens=24)
+    assert seq_f.numel() == seq_a.numel()
+    for la, lb in zip(a.layers, b.layers):
+        ca, cb = la.attention.kv_cache, lb.attention.kv_cache
+        assert torch.equal(ca.k_cache, cb.k_cache) and torch.equal(ca.k_codes, cb.k_codes)
+        H, L, D = ca.n_heads, ca.max_cache_length, ca.head_dim
+        per = 8 // bits
+        codes = ((ca.k_codes.cpu().to(torch.int32).view(-1, 1) >> torch.arange(0, 8, bits, dtype=torch.int32)) & (2 ** bits - 1))
+        codes = codes.reshape(-1)[: H * L * D].view(H, L, D) if per > 1 else ca.k_codes.cpu().to(torch.int32).view(H, L, D)
+        assert torch.equal(quant.dequantize(codes, ca.k_scales.cpu(), ca.k_zero_points.cpu(), bits), ca.k_cache[0].cpu())
+    stats = a.get_cache_stats(120, 24)
+    assert stats["compression_ratio_avg"] > full.get_cache_stats(120, 24)["compression_ratio_avg"]
