@@ -18,18 +18,19 @@ def _torchrun(n, *args, timeout=600):
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
 
 
-def test_tp_host_logic_gloo_world2():
+@pytest.mark.parametrize("world", [2, 4])
+def test_tp_host_logic_gloo(world):
     env_cuda = os.environ.get("CUDA_VISIBLE_DEVICES")
     os.environ["CUDA_VISIBLE_DEVICES"] = ""
     try:
-        r = _torchrun(2, "heavy_hitter")
+        r = _torchrun(world, "heavy_hitter")
     finally:
         if env_cuda is None:
             os.environ.pop("CUDA_VISIBLE_DEVICES", None)
         else:
             os.environ["CUDA_VISIBLE_DEVICES"] = env_cuda
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
-    assert r.stdout.count("tp host logic ok") == 2
+    assert r.stdout.count("tp host logic ok") == world
 
 
 @pytest.mark.gpu
