@@ -62,6 +62,11 @@ FIXTURES = {
     "hh_bits8": dict(strategy="heavy_hitter", Hkv=2, G=4, D=128, L=48, S=80, T=80, cache_bits=8),
     "hh_bits4": dict(strategy="heavy_hitter", Hkv=2, G=2, D=64, L=40, S=30, T=80, cache_bits=4),
     "rg_bits2": dict(strategy="recent_global", Hkv=2, G=4, D=128, L=32, S=60, T=60, cache_bits=2),
+    # BASELINE.json per-layer cache shapes (Llama-3-8B heads): config 1 exactly; configs 2 / 3 with a shorter prompt
+    # (the cache sees the same 1024 / 512 slots; the reference's CPU prefill materialises the S x S map)
+    "cfg1_rg_l64": dict(strategy="recent_global", Hkv=8, G=4, D=128, L=64, S=128, T=16),
+    "cfg2_hh_l1024": dict(strategy="heavy_hitter", Hkv=8, G=4, D=128, L=1024, S=1536, T=24),
+    "cfg3_l2_l512": dict(strategy="l2", Hkv=8, G=4, D=128, L=512, S=768, T=24),
     "rg_compress": dict(strategy="recent_global", Hkv=2, G=4, D=128, L=64, S=128, T=100),
     "l2_compress": dict(strategy="l2", Hkv=4, G=2, D=128, L=64, S=100, T=120),
     "l2_fill": dict(strategy="l2", Hkv=2, G=4, D=64, L=48, S=20, T=80),

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_utils import ALL_FIXTURES, Golden, bits, check_y
+from golden_utils import GPU_FIXTURES as ALL_FIXTURES, Golden, bits, check_y
 
 pytestmark = pytest.mark.gpu
 
