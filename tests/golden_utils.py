@@ -10,10 +10,7 @@ import torch
 GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
 ALL_FIXTURES = sorted(p.stem for p in GOLDEN_DIR.glob("*.npz")
                       if not p.stem.startswith(("prefill_", "debug_")) and "_bits" not in p.stem)
-# traces recorded after the round's GPU budget was spent: pinned on the oracle (CPU) now, on the GPU path once
-# CC_RUN_UNVERIFIED=1 has been run on a B200 (then drop the prefix filter)
-import os as _os
-GPU_FIXTURES = [n for n in ALL_FIXTURES if not n.startswith("cfg") or _os.environ.get("CC_RUN_UNVERIFIED") == "1"]
+GPU_FIXTURES = ALL_FIXTURES   # every decode trace, incl. the BASELINE cache shapes (cfg*), is verified on the B200
 
 
 def bf(a: np.ndarray) -> torch.Tensor:
