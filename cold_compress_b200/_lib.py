@@ -20,6 +20,7 @@ POLICY_EXTERNAL, POLICY_RECENT_GLOBAL, POLICY_L2, POLICY_HEAVY_HITTER, POLICY_HY
 ATTN_MATH_FP32, ATTN_NAIVE_BF16 = 0, 1
 PHASE_EVICT_FILL, PHASE_ATTEND, PHASE_SCORE, PHASE_ALL = 1, 2, 4, 7
 FLAG_OVERLAP_PREDECESSOR = 1
+FLAG_VIA_TOKEN_KERNEL = 2
 HYB_FULL, HYB_WINDOW, HYB_HEAVY_HITTER, HYB_SPECIAL, HYB_PUNC = 1, 2, 4, 8, 16
 
 _STATE_INTS = ("policy", "attn_mode", "n_kv_heads", "q_per_kv", "head_dim", "max_cache_length",
@@ -56,6 +57,19 @@ class CcPrefillAttnArgs(C.Structure):
         (n, C.c_void_p) for n in ("col_sum", "obs_sum", "band_sum", "workspace")] + [("workspace_bytes", C.c_uint64)]
 
 
+class CcTokenLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("attention_norm", "wqkv", "bqkv", "wo", "ffn_norm", "w1", "w3", "w2")] + [
+        ("attention_norm_eps", C.c_float), ("ffn_norm_eps", C.c_float), ("cache", CcCacheState),
+        ("fill_idx", C.c_void_p), ("probs", C.c_void_p)]
+
+
+class CcTokenModel(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_layers", "dim", "n_q_heads", "n_kv_heads", "head_dim", "intermediate", "vocab")] + [
+        ("norm_eps", C.c_float), ("layers", C.POINTER(CcTokenLayer))] + [
+        (n, C.c_void_p) for n in ("tok_embeddings", "norm", "output", "freqs_cis")] + [
+        ("world", C.c_int32), ("rank", C.c_int32), ("scratch_peers", C.POINTER(C.c_uint64)), ("scratch_bytes", C.c_uint64)]
+
+
 # every symbol include/cc_b200.h declares: name -> (restype, argtypes)
 EXPORTS = {
     "cc_abi_version": (C.c_int, []),
@@ -71,6 +85,13 @@ EXPORTS = {
     "cc_requantize_cache": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 7),
     "cc_prefill_attention_workspace": (C.c_uint64, [C.c_int32] * 5),
     "cc_prefill_attention": (C.c_int, [C.POINTER(CcPrefillAttnArgs), C.c_void_p]),
+    "cc_token_scratch_bytes": (C.c_uint64, [C.POINTER(CcTokenModel)]),
+    "cc_token_plan_create": (C.c_int, [C.POINTER(CcTokenModel), C.POINTER(C.c_void_p)]),
+    "cc_token_plan_destroy": (C.c_int, [C.c_void_p]),
+    "cc_decode_token": (C.c_int, [C.c_void_p] * 7),
+    "cc_token_buffer": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
+    "cc_token_set_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cc_token_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int32)] * 4),
     "cc_rmsnorm_qkv_rope": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32, C.POINTER(CcTpArgs), C.c_void_p]),

@@ -248,7 +248,8 @@ class KVCache(nn.Module):
             bool(kwargs.get("is_punc", False)),
             # a caller-chosen slot (EXTERNAL) is written to `fill_idx` by the kernel launched just before this one,
             # so the step must not start reading ahead of its predecessor
-            _lib.FLAG_OVERLAP_PREDECESSOR if kwargs.get("overlap_predecessor") and self.policy != _lib.POLICY_EXTERNAL else 0,
+            (_lib.FLAG_OVERLAP_PREDECESSOR if kwargs.get("overlap_predecessor") and self.policy != _lib.POLICY_EXTERNAL else 0)
+            | (_lib.FLAG_VIA_TOKEN_KERNEL if kwargs.get("via_token_kernel") else 0),
             list(kwargs.get("warm_l2", ())), kwargs.get("is_punc_dev"))
         return out["y"].view(1, self.n_heads * G, 1, self.head_dim) if q is not None else None
 

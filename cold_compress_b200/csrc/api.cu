@@ -96,4 +96,19 @@ int cc_rmsnorm_ffn_gate(const void* x, const void* norm_w, float eps, const void
     return cc::rmsnorm_ffn_gate_impl(x, norm_w, eps, w1, w3, out, K, N, tp, (cudaStream_t)stream);
 }
 
+uint64_t cc_token_scratch_bytes(const CcTokenModel* model) { return cc::token_scratch_bytes_impl(model); }
+int cc_token_plan_create(const CcTokenModel* model, void** plan) { return cc::token_plan_create_impl(model, plan); }
+int cc_token_plan_destroy(void* plan) { return cc::token_plan_destroy_impl(plan); }
+int cc_decode_token(void* plan, const int32_t* token_in, const int32_t* input_pos, int32_t* token_out, void* logits_out,
+                    void* probs_out, void* stream) {
+    return cc::decode_token_impl(plan, token_in, input_pos, token_out, logits_out, probs_out, (cudaStream_t)stream);
+}
+int cc_token_buffer(void* plan, int32_t layer, int32_t which, uint64_t* offset_bytes, int32_t* n_words) {
+    return cc::token_buffer_impl(plan, layer, which, offset_bytes, n_words);
+}
+int cc_token_set_trace(void* plan, void* device_buffer) { return cc::token_set_trace_impl(plan, device_buffer); }
+int cc_token_info(void* plan, int32_t* n_ctas, int32_t* n_stages_program, int32_t* ring_stages, int32_t* smem_bytes) {
+    return cc::token_info_impl(plan, n_ctas, n_stages_program, ring_stages, smem_bytes);
+}
+
 }  // extern "C"

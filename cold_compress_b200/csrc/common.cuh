@@ -171,4 +171,58 @@ __device__ __forceinline__ void st_release_gpu(int32_t* p, int32_t v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
+// ------------------------------------------------------------------ warp-level reductions shared by the decode kernels
+template <int LPR>
+__device__ __forceinline__ float group_butterfly(float v) {
+#pragma unroll
+    for (int d = LPR / 2; d >= 1; d >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, d));
+    return v;
+}
+
+// Reduce G per-lane partial sums over the LPR lanes of a row group with the SAME addition tree as
+// group_butterfly (pairs at lane distance LPR/2, ..., 1) but exchanging halves of the value set while
+// more than one value is held: 5 shuffles instead of 16 for G = 4.  On return lane `li` holds the
+// full sum of query head `*g_out` (replicated over the lanes that share it); fp add is commutative,
+// so the bits equal the plain butterfly's.
+template <int LPR, int G>
+__device__ __forceinline__ float group_reduce_multi(const float (&v)[G], int li, int* g_out) {
+    constexpr int P0 = G <= 1 ? 1 : G <= 2 ? 2 : G <= 4 ? 4 : 8;
+    static_assert(P0 <= LPR, "more query heads than lanes per row");
+    float w[P0];
+#pragma unroll
+    for (int i = 0; i < P0; ++i) w[i] = i < G ? v[i] : 0.f;
+    int g = 0;
+    int held = P0;
+#pragma unroll
+    for (int d = LPR / 2; d >= 1; d >>= 1) {
+        if (held > 1) {
+            const int half = held / 2;
+            const bool upper = (li & d) != 0;  // upper lanes keep the upper half of the values
+#pragma unroll
+            for (int i = 0; i < P0 / 2; ++i) {
+                if (i < half) {
+                    const float send = upper ? w[i] : w[i + half];
+                    const float keep = upper ? w[i + half] : w[i];
+                    w[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, d));
+                }
+            }
+            if (upper) g += half;
+            held = half;
+        } else {
+            w[0] = __fadd_rn(w[0], __shfl_xor_sync(0xffffffffu, w[0], d));
+        }
+    }
+    *g_out = g;
+    return w[0];
+}
+
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t k) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        uint64_t o = __shfl_xor_sync(0xffffffffu, k, d);
+        k = o < k ? o : k;
+    }
+    return k;
+}
+
 }  // namespace cc

@@ -106,59 +106,6 @@ __device__ __forceinline__ void stamp(const DecodeParams& p, int k) {
     }
 }
 
-template <int LPR>
-__device__ __forceinline__ float group_butterfly(float v) {
-#pragma unroll
-    for (int d = LPR / 2; d >= 1; d >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, d));
-    return v;
-}
-
-// Reduce G per-lane partial sums over the LPR lanes of a row group with the SAME addition tree as
-// group_butterfly (pairs at lane distance LPR/2, ..., 1) but exchanging halves of the value set while
-// more than one value is held: 5 shuffles instead of 16 for G = 4.  On return lane `li` holds the
-// full sum of query head `*g_out` (replicated over the lanes that share it); fp add is commutative,
-// so the bits equal the plain butterfly's.
-template <int LPR, int G>
-__device__ __forceinline__ float group_reduce_multi(const float (&v)[G], int li, int* g_out) {
-    constexpr int P0 = G <= 1 ? 1 : G <= 2 ? 2 : G <= 4 ? 4 : 8;
-    static_assert(P0 <= LPR, "more query heads than lanes per row");
-    float w[P0];
-#pragma unroll
-    for (int i = 0; i < P0; ++i) w[i] = i < G ? v[i] : 0.f;
-    int g = 0;
-    int held = P0;
-#pragma unroll
-    for (int d = LPR / 2; d >= 1; d >>= 1) {
-        if (held > 1) {
-            const int half = held / 2;
-            const bool upper = (li & d) != 0;  // upper lanes keep the upper half of the values
-#pragma unroll
-            for (int i = 0; i < P0 / 2; ++i) {
-                if (i < half) {
-                    const float send = upper ? w[i] : w[i + half];
-                    const float keep = upper ? w[i + half] : w[i];
-                    w[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, d));
-                }
-            }
-            if (upper) g += half;
-            held = half;
-        } else {
-            w[0] = __fadd_rn(w[0], __shfl_xor_sync(0xffffffffu, w[0], d));
-        }
-    }
-    *g_out = g;
-    return w[0];
-}
-
-__device__ __forceinline__ uint64_t warp_min_u64(uint64_t k) {
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        uint64_t o = __shfl_xor_sync(0xffffffffu, k, d);
-        k = o < k ? o : k;
-    }
-    return k;
-}
-
 template <int D, int G, int POLICY, bool NAIVE>
 __global__ void __launch_bounds__(kThreads, 1)
 cc_decode_kernel(const __grid_constant__ DecodeParams p) {
@@ -216,10 +163,13 @@ cc_decode_kernel(const __grid_constant__ DecodeParams p) {
         for (int s = 0; s < 2 * NS + 4; ++s) mbar_init(&kbar[s], 1);
         mbar_fence_init();
         // every exchange delivers a known number of bytes into this CTA: arm the barriers right away
-        mbar_expect_tx(&xbar[0], (uint32_t)C * 4);
+        // (only the exchanges this launch performs: an armed barrier nobody completes is a synccheck finding)
+        if (POLICY == CC_POLICY_L2 && do_evict) mbar_expect_tx(&xbar[0], (uint32_t)C * 4);
         mbar_expect_tx(&xbar[1], (uint32_t)C * NW * 4);
-        mbar_expect_tx(&xbar[2], (uint32_t)C * G * 8);
-        mbar_expect_tx(&xbar[3], (uint32_t)G * D * 4);
+        if (do_attend) {
+            mbar_expect_tx(&xbar[2], (uint32_t)C * G * 8);
+            mbar_expect_tx(&xbar[3], (uint32_t)G * D * 4);
+        }
     }
     // B0: this CTA has started and its exchange barriers exist; peers wait for this before they send
     cluster_arrive_release();
@@ -1052,6 +1002,7 @@ static bool plan_needs_epoch(const CcCacheState* st) {
 int decode_step_impl(const CcCacheState* st, const CcDecodeArgs* a, cudaStream_t stream) {
     int rc = validate(st, a);
     if (rc) return rc;
+    if (a->flags & CC_FLAG_VIA_TOKEN_KERNEL) return decode_step_via_token_impl(st, a, stream);
     LaunchPlan plan;
     rc = make_plan(st, plan_needs_epoch(st), &plan);
     if (rc) return rc;

@@ -1,0 +1,1484 @@
+// decode_token.cu -- one decoded token as ONE persistent sm_100a kernel.
+//
+// Replaces the per-token launch chain of the reference's decode_one_token (generation_utils.py:163-178 ->
+// Transformer.forward model.py:268-292 -> 32 x TransformerBlock.forward model.py:307-327 -> greedy sampling
+// generation_utils.py:136-142), which round 1 ran as 5 launches per layer.  A decoded token streams 15 GB of bf16
+// weights plus the live K/V rows exactly once; the only way to keep HBM busy across the ~160 dependent stages of a
+// token is to never stop the stream at a stage boundary.  Design:
+//
+//   * one CTA per SM (cooperative launch: all co-resident), 8 warps; the rows of every stage are dealt to CTAs and,
+//     inside a CTA, to warps, statically;
+//   * every warp owns a private ring of 8 KiB shared-memory stages fed by the TMA engine (cp.async.bulk, UBLKCP):
+//     the moment a warp has consumed a stage it re-arms it with the NEXT tile of its own static tile sequence --
+//     the sequence runs across stage boundaries (weights of wo / w1 / w3 / w2 / the next layer, this layer's K/V
+//     rows), so up to ~190 KiB per SM are in flight or resident while the warp waits for a predecessor stage;
+//   * stages hand vectors to each other through flag-in-data words in global memory (u64 = {payload, token tag},
+//     8-byte single-copy atomic): a consumer spins on the tag of the words it needs.  No grid barrier, no fence, no
+//     kernel boundary; every stage output has its own buffer, so nothing is overwritten within a token;
+//   * the attention stage is the cc_decode_step algorithm (decode_step.cu: eviction decision -> overwrite ->
+//     masked attention -> GQA pooling -> score update, same bit-reproducible arithmetic) with the three cluster
+//     exchanges replaced by flag-in-data exchanges between the CTAs of a KV head;
+//   * with tensor parallelism the row-parallel stages (wo, w2) store their partial vectors into EVERY rank's
+//     scratch (peer-mapped NVLink memory) and the consuming stage sums the `world` partial vectors: the all-reduce
+//     of tp.py:134-160 costs one NVLink write latency and is hidden behind the weight stream like any other stage
+//     hand-over.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/cc_b200.h"
+#include "common.cuh"
+#include "internal.h"
+
+namespace cc {
+
+constexpr int kTW = 8;                 // warps per CTA
+constexpr int kTT = kTW * 32;          // threads per CTA
+constexpr uint32_t kStage = 8192;      // bytes per ring stage
+constexpr int kTokMaxWorld = 8;
+constexpr int kTokMaxG = 8;
+constexpr int kOutStage = 64;          // row pairs a CTA can stage for a coalesced peer push
+constexpr uint64_t kNoKey64 = ~0ull;
+
+enum : int { TOK_QKV = 0, TOK_ATTN = 1, TOK_GEMV = 2, TOK_GATE = 3, TOK_HEAD = 4 };
+enum : int { IN_TOKEN = 0, IN_LL = 1 };
+enum : int { RES_NONE = 0, RES_TOKEN = 1, RES_LL = 2 };
+
+// One stage of the token program (device memory, read-only during the kernel).
+struct TokOp {
+    int32_t type;         // TOK_*
+    int32_t K, N;         // matrix-vector stages: input length, output rows
+    int32_t n_groups;     // row groups (a group = 2 output rows; the FFN gate reads 2 rows of w1 and 2 of w3)
+    int32_t seg_len;      // elements of a row per ring stage (multiple of 256)
+    int32_t n_seg;        // ceil(K / seg_len)
+    int32_t rot;          // rotation of the CTA dealing (spreads the +1 row groups over CTAs from stage to stage)
+    int32_t layer;
+    int32_t in_kind;      // IN_TOKEN: embedding row of the input token; IN_LL: in_world partial vectors at in_off
+    int32_t in_world;
+    int32_t res_kind;     // residual added to the (summed) input: none / embedding row / flag-in-data vector at res_off
+    int32_t publish_cta;  // the CTA that also writes the staged input vector to sum_off (-1: nobody)
+    int32_t out_world;    // TOK_GEMV: ranks the partial output is stored to (1 = this rank only)
+    int32_t attn;         // TOK_ATTN: index into the attention table
+    float eps;
+    int32_t pad;
+    uint64_t in_off, res_off, sum_off, out_off;   // byte offsets inside the scratch (identical on every rank)
+    const __nv_bfloat16 *norm_w, *w, *w3, *bias;
+};
+
+struct TokAttn {
+    CcCacheState st;
+    int32_t c_shift;      // log2(CTAs per KV head)
+    int32_t ch_shift;     // log2(rows per chunk)
+    int32_t rot;
+    int32_t lg_stride;    // floats per query head in the logit / probability array
+    float scale;
+    int32_t pad;
+    uint64_t qkv_off, y_off, x1_off, x2_off, x3_off;
+    int64_t* fill_idx;
+    __nv_bfloat16* probs;
+};
+
+struct TokParams {
+    const TokOp* ops;
+    const TokAttn* attns;
+    int32_t n_ops, world, rank, vocab;
+    uint8_t* scratch;             // this rank's scratch
+    const uint64_t* peers;        // device array [world]: scratch base address of every rank
+    const int32_t* token_in;
+    const int32_t* input_pos;
+    int32_t* token_out;
+    __nv_bfloat16* logits_out;
+    __nv_bfloat16* probs_out;
+    const __nv_bfloat16* emb;
+    const __nv_bfloat16* freqs;
+    int32_t dim, n_q_rows, n_kv_rows, head_dim;
+    uint32_t xs_bytes;            // staging area at the start of shared memory (input vector / attention scratch)
+    int32_t n_stages;             // ring stages per warp
+    uint64_t rec1_off, rec2_off;  // arg-max / softmax-sum records, one per CTA
+    unsigned long long* trace;
+};
+
+// scratch header
+struct TokHeader { uint32_t gen; uint32_t done; };
+
+// ------------------------------------------------------------------ flag-in-data words
+__device__ __forceinline__ void ll_store(uint64_t* p, uint32_t data, uint32_t tag) {
+    const uint64_t v = ((uint64_t)tag << 32) | data;
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ll_load(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ll_load2(const uint64_t* p, uint64_t& a, uint64_t& b) {
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ uint32_t ll_wait(const uint64_t* p, uint32_t tag) {
+    uint64_t v;
+    do { v = ll_load(p); } while ((uint32_t)(v >> 32) != tag);
+    return (uint32_t)v;
+}
+// four consecutive words (p 16-byte aligned) = 8 bf16 values
+__device__ __forceinline__ uint4 ll_wait4(const uint64_t* p, uint32_t tag) {
+    uint64_t a, b, c, d;
+    while (true) {
+        ll_load2(p, a, b);
+        ll_load2(p + 2, c, d);
+        const uint32_t bad = ((uint32_t)(a >> 32) ^ tag) | ((uint32_t)(b >> 32) ^ tag) | ((uint32_t)(c >> 32) ^ tag) |
+                             ((uint32_t)(d >> 32) ^ tag);
+        if (!bad) break;
+    }
+    return make_uint4((uint32_t)a, (uint32_t)b, (uint32_t)c, (uint32_t)d);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// ------------------------------------------------------------------ dealing of work to CTAs and warps
+// matrix-vector stage: CTA c owns row groups [g0, g0 + n); warp w of the CTA owns local groups w, w + 8, ...
+__device__ __forceinline__ void deal_groups(int n_groups, int rot, int* g0, int* n) {
+    const int nc = (int)gridDim.x;
+    int c = (int)blockIdx.x + rot;
+    if (c >= nc) c -= nc;
+    const int base = n_groups / nc, rem = n_groups - base * nc;
+    *g0 = c * base + min(c, rem);
+    *n = base + (c < rem ? 1 : 0);
+}
+// attention stage: CTA unit u < H * C works on KV head u / C as rank u % C of that head; chunk j of rank r is
+// global chunk r + j * C; warp w owns rows [w * RW, (w + 1) * RW) of every chunk
+struct AttnDeal {
+    int active, h, rank, nlc;   // nlc: chunks of this rank
+};
+__device__ __forceinline__ AttnDeal deal_attn(const TokAttn& A) {
+    AttnDeal d;
+    const int nc = (int)gridDim.x;
+    int u = (int)blockIdx.x + A.rot;
+    if (u >= nc) u -= nc;
+    const int C = 1 << A.c_shift;
+    d.active = u < A.st.n_kv_heads * C;
+    d.h = u >> A.c_shift;
+    d.rank = u & (C - 1);
+    const int n_chunks = (A.st.max_cache_length + (1 << A.ch_shift) - 1) >> A.ch_shift;
+    d.nlc = (d.active && n_chunks > d.rank) ? (n_chunks - d.rank + C - 1) >> A.c_shift : 0;
+    return d;
+}
+// first slot and number of valid rows of warp `w` in local chunk `jj`
+__device__ __forceinline__ void attn_warp_rows(const TokAttn& A, int rank, int jj, int w, int* first, int* nvalid) {
+    const int RW = (1 << A.ch_shift) / kTW;
+    const int f = ((((jj << A.c_shift) + rank)) << A.ch_shift) + w * RW;
+    *first = f;
+    *nvalid = max(0, min(RW, A.st.max_cache_length - f));
+}
+
+// ------------------------------------------------------------------ per-warp tile sequence (the fetch cursor)
+struct TileIter {
+    int op;         // current stage index (>= n_ops: exhausted)
+    int j, nj;      // matrix-vector: local group index / count; attention: tile index / 2 * nlc
+    int s, ns;      // segment index / count
+    int type, K, seg_len, g0, rank, h;
+    const TokOp* o;
+    const TokAttn* a;
+};
+
+__device__ __forceinline__ bool iter_tile_valid(const TileIter& it, int warp) {
+    if (it.type != TOK_ATTN) return true;
+    const int nlc = it.nj >> 1;
+    int first, nv;
+    attn_warp_rows(*it.a, it.rank, it.j < nlc ? it.j : it.j - nlc, warp, &first, &nv);
+    return nv > 0;
+}
+// position the cursor on the first tile of stage it.op or of the first later stage in which this warp has work
+__device__ __forceinline__ void iter_enter(TileIter& it, const TokParams& P, int warp) {
+    for (; it.op < P.n_ops; ++it.op) {
+        const TokOp* o = P.ops + it.op;
+        it.o = o;
+        it.type = o->type;
+        if (o->type == TOK_ATTN) {
+            const TokAttn* a = P.attns + o->attn;
+            const AttnDeal d = deal_attn(*a);
+            if (d.nlc == 0) continue;
+            it.a = a; it.rank = d.rank; it.h = d.h;
+            it.nj = 2 * d.nlc; it.s = 0; it.ns = 1;
+            for (it.j = 0; it.j < it.nj && !iter_tile_valid(it, warp); ++it.j) {}
+            if (it.j < it.nj) return;
+        } else {
+            int g0, n;
+            deal_groups(o->n_groups, o->rot, &g0, &n);
+            if (warp >= n) continue;
+            it.g0 = g0; it.nj = n; it.j = warp; it.s = 0; it.ns = o->n_seg; it.K = o->K; it.seg_len = o->seg_len;
+            return;
+        }
+    }
+}
+__device__ __forceinline__ void iter_advance(TileIter& it, const TokParams& P, int warp) {
+    if (it.type == TOK_ATTN) {
+        for (++it.j; it.j < it.nj && !iter_tile_valid(it, warp); ++it.j) {}
+        if (it.j < it.nj) return;
+    } else {
+        if (++it.s < it.ns) return;
+        it.s = 0;
+        it.j += kTW;
+        if (it.j < it.nj) return;
+    }
+    ++it.op;
+    iter_enter(it, P, warp);
+}
+// issue the TMA copies of the cursor's tile into a ring stage (one lane)
+__device__ __forceinline__ void iter_issue(const TileIter& it, int warp, uint8_t* stage, uint64_t* bar) {
+    if (it.type == TOK_ATTN) {
+        const TokAttn& A = *it.a;
+        const int nlc = it.nj >> 1;
+        const bool is_v = it.j >= nlc;
+        int first, nv;
+        attn_warp_rows(A, it.rank, is_v ? it.j - nlc : it.j, warp, &first, &nv);
+        const uint32_t row_bytes = (uint32_t)A.st.head_dim * 2;
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(is_v ? A.st.v_cache : A.st.k_cache);
+        const uint32_t bytes = (uint32_t)nv * row_bytes;
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(stage, base + ((size_t)it.h * A.st.max_cache_length + first) * row_bytes, bytes, bar);
+        return;
+    }
+    const int off = it.s * it.seg_len;
+    const int len = min(it.seg_len, it.K - off);
+    const uint32_t bytes = (uint32_t)len * 2;
+    const size_t r0 = 2 * (size_t)(it.g0 + it.j);
+    const __nv_bfloat16* w = it.o->w;
+    if (it.type == TOK_GATE) {
+        const __nv_bfloat16* w3 = it.o->w3;
+        mbar_expect_tx(bar, 4 * bytes);
+        tma_load_1d(stage, w + r0 * it.K + off, bytes, bar);
+        tma_load_1d(stage + bytes, w + (r0 + 1) * it.K + off, bytes, bar);
+        tma_load_1d(stage + 2 * bytes, w3 + r0 * it.K + off, bytes, bar);
+        tma_load_1d(stage + 3 * bytes, w3 + (r0 + 1) * it.K + off, bytes, bar);
+    } else {
+        mbar_expect_tx(bar, 2 * bytes);
+        tma_load_1d(stage, w + r0 * it.K + off, bytes, bar);
+        tma_load_1d(stage + bytes, w + (r0 + 1) * it.K + off, bytes, bar);
+    }
+}
+
+// ------------------------------------------------------------------ the per-warp ring
+struct Ring {
+    uint8_t* stages;      // this warp's stages
+    uint64_t* bars;       // this warp's mbarriers
+    int ns, cs;           // number of stages, stage the consumer reads next
+    uint32_t phases;      // parity of the next completion of each stage's barrier
+    TileIter it;          // fetch cursor; only lane 0's copy is meaningful
+};
+__device__ __forceinline__ const uint8_t* ring_wait(Ring& r) {
+    mbar_wait(&r.bars[r.cs], (r.phases >> r.cs) & 1u);
+    return r.stages + (size_t)r.cs * kStage;
+}
+// the warp is done with the current stage: re-arm it with the next tile of the warp's sequence
+__device__ __forceinline__ void ring_release(Ring& r, const TokParams& P, int warp, int lane) {
+    __syncwarp();
+    if (lane == 0 && r.it.op < P.n_ops) {
+        fence_proxy_async();
+        iter_issue(r.it, warp, r.stages + (size_t)r.cs * kStage, &r.bars[r.cs]);
+        iter_advance(r.it, P, warp);
+    }
+    r.phases ^= 1u << r.cs;
+    r.cs = r.cs + 1 == r.ns ? 0 : r.cs + 1;
+}
+
+// ------------------------------------------------------------------ input staging of a matrix-vector stage
+// x = [residual +] sum over ranks of the predecessor's partial vectors  ->  shared memory (bf16), optionally
+// RMS-normalised the way the reference's RMSNorm does it (model.py:452-457).
+__device__ void stage_input(const TokParams& P, const TokOp& op, __nv_bfloat16* xs, float* scratch, uint32_t tag) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = op.K;
+    const int token = (op.in_kind == IN_TOKEN || op.res_kind == RES_TOKEN) ? P.token_in[0] : 0;
+    if (op.in_kind == IN_TOKEN) {
+        const __nv_bfloat16* src = P.emb + (size_t)token * K;
+        for (int i = tid * 8; i < K; i += kTT * 8)
+            *reinterpret_cast<uint4*>(xs + i) = __ldg(reinterpret_cast<const uint4*>(src + i));
+    } else {
+        const int nw = K >> 1;
+        const uint64_t* in = reinterpret_cast<const uint64_t*>(P.scratch + op.in_off);
+        // cheap gate: one warp samples 32 words per source with a back-off, so that a CTA that arrives early does
+        // not hammer L2 with 256 spinning threads while the weight stream needs the bandwidth
+        if (warp == 0) {
+            for (int s = 0; s < op.in_world; ++s) {
+                const uint64_t* p = in + (size_t)s * nw + (size_t)lane * (nw >> 5);
+                while ((uint32_t)(ll_load(p) >> 32) != tag) __nanosleep(64);
+            }
+        }
+        __syncthreads();
+        const uint64_t* res = op.res_kind == RES_LL ? reinterpret_cast<const uint64_t*>(P.scratch + op.res_off) : nullptr;
+        const __nv_bfloat16* rest = op.res_kind == RES_TOKEN ? P.emb + (size_t)token * K : nullptr;
+        uint64_t* sum_out = op.publish_cta == (int)blockIdx.x ? reinterpret_cast<uint64_t*>(P.scratch + op.sum_off) : nullptr;
+        for (int i = tid * 8; i < K; i += kTT * 8) {
+            uint4 o = ll_wait4(in + (i >> 1), tag);
+            if (op.in_world > 1 || op.res_kind != RES_NONE) {
+                float acc[8], f[8];
+                unpack8(o, acc);
+                for (int s = 1; s < op.in_world; ++s) {   // rank order: the same bits on every rank
+                    unpack8(ll_wait4(in + (size_t)s * nw + (i >> 1), tag), f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] += f[j];
+                }
+                if (op.res_kind != RES_NONE) {
+                    // h = x + attention(...) / out = h + feed_forward(...): bf16 + bf16 -> bf16 (model.py:317, 326)
+                    unpack8(res ? ll_wait4(res + (i >> 1), tag) : __ldg(reinterpret_cast<const uint4*>(rest + i)), f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = __fadd_rn(f[j], bf16_round(acc[j]));
+                }
+                o = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                               pack_bf16x2(acc[6], acc[7]));
+            }
+            *reinterpret_cast<uint4*>(xs + i) = o;
+            if (sum_out) {
+                ll_store(sum_out + (i >> 1) + 0, o.x, tag);
+                ll_store(sum_out + (i >> 1) + 1, o.y, tag);
+                ll_store(sum_out + (i >> 1) + 2, o.z, tag);
+                ll_store(sum_out + (i >> 1) + 3, o.w, tag);
+            }
+        }
+    }
+    __syncthreads();
+    if (op.norm_w == nullptr) return;
+    float ss = 0.f;
+    for (int i = tid * 8; i < K; i += kTT * 8) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(xs + i), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+    }
+    ss = warp_sum_f(ss);
+    if (lane == 0) scratch[warp] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < kTW; ++w) tot += scratch[w];
+    const float rstd = rsqrtf(tot / (float)K + op.eps);
+    for (int i = tid * 8; i < K; i += kTT * 8) {
+        float f[8], wv[8];
+        unpack8(*reinterpret_cast<const uint4*>(xs + i), f);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(op.norm_w + i)), wv);
+        *reinterpret_cast<uint4*>(xs + i) =
+            make_uint4(pack_bf16x2(__fmul_rn(bf16_round(__fmul_rn(f[0], rstd)), wv[0]), __fmul_rn(bf16_round(__fmul_rn(f[1], rstd)), wv[1])),
+                       pack_bf16x2(__fmul_rn(bf16_round(__fmul_rn(f[2], rstd)), wv[2]), __fmul_rn(bf16_round(__fmul_rn(f[3], rstd)), wv[3])),
+                       pack_bf16x2(__fmul_rn(bf16_round(__fmul_rn(f[4], rstd)), wv[4]), __fmul_rn(bf16_round(__fmul_rn(f[5], rstd)), wv[5])),
+                       pack_bf16x2(__fmul_rn(bf16_round(__fmul_rn(f[6], rstd)), wv[6]), __fmul_rn(bf16_round(__fmul_rn(f[7], rstd)), wv[7])));
+    }
+    __syncthreads();
+}
+
+// RG weight-row segments of `len` elements (a multiple of 256) in a ring stage against the staged input
+template <int RG>
+__device__ __forceinline__ void consume_tile(const uint8_t* stage, const __nv_bfloat16* xseg, int len, float (&acc)[RG], int lane) {
+    const int nb = len >> 8;
+    const uint32_t row_bytes = (uint32_t)len * 2;
+#pragma unroll 4
+    for (int b = 0; b < nb; ++b) {
+        float x[8];
+        unpack8(*reinterpret_cast<const uint4*>(xseg + b * 256 + lane * 8), x);
+#pragma unroll
+        for (int r = 0; r < RG; ++r) {
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(stage + r * row_bytes + b * 512 + lane * 16), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[r] = fmaf(f[j], x[j], acc[r]);
+        }
+    }
+}
+
+// deferred writes of cross-head cache state (see attn_stage): performed by thread 0 once every head has read it
+struct Pending {
+    int32_t active;
+    int32_t pos_val;
+    int32_t* pos_ptr;
+    uint16_t* kn_ptr;
+    uint32_t kn_val;
+};
+
+struct HeadBest { float v; int idx; };
+
+// ------------------------------------------------------------------ a matrix-vector stage
+__device__ void gemv_stage(const TokParams& P, const TokOp& op, int oi, uint8_t* smem, Ring& ring, uint32_t tag,
+                           float* scratch, uint32_t* outw, Pending* pend, HeadBest* best) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem);
+    __syncthreads();   // every warp is done with the staging area of the previous stage
+    if (P.trace && tid == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.trace[((size_t)oi * gridDim.x + blockIdx.x) * 2] = t;
+    }
+    stage_input(P, op, xs, scratch, tag);
+    if (P.trace && tid == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.trace[((size_t)oi * gridDim.x + blockIdx.x) * 2 + 1] = t;
+    }
+    // cross-head cache state of the attention stage just before this one: its input being complete means every
+    // head's CTAs have finished reading the old state
+    if (tid == 0 && pend->active) {
+        if (pend->pos_ptr) *pend->pos_ptr = pend->pos_val;
+        if (pend->kn_ptr) *pend->kn_ptr = (uint16_t)pend->kn_val;
+        pend->active = 0;
+    }
+    int g0, nloc;
+    deal_groups(op.n_groups, op.rot, &g0, &nloc);
+    const int type = op.type, K = op.K;
+    const int pos = type == TOK_QKV ? P.input_pos[0] : 0;
+    const bool push = type == TOK_GEMV && op.out_world > 1 && nloc <= kOutStage;
+    for (int j = warp; j < nloc; j += kTW) {
+        const int g = g0 + j, r0 = 2 * g;
+        // operands of the epilogue, requested before the dot products
+        float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+        if (lane == 0 && type == TOK_QKV) {
+            if (op.bias) { e0 = __bfloat162float(op.bias[r0]); e1 = __bfloat162float(op.bias[r0 + 1]); }
+            if (r0 < P.n_q_rows + P.n_kv_rows) {
+                const int half = P.head_dim >> 1, i = (r0 % P.head_dim) >> 1;
+                e2 = __bfloat162float(P.freqs[((size_t)pos * half + i) * 2]);
+                e3 = __bfloat162float(P.freqs[((size_t)pos * half + i) * 2 + 1]);
+            }
+        }
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int s = 0; s < op.n_seg; ++s) {
+            const int off = s * op.seg_len, len = min(op.seg_len, K - off);
+            const uint8_t* st = ring_wait(ring);
+            if (type == TOK_GATE) {
+                consume_tile<4>(st, xs + off, len, acc, lane);
+            } else {
+                float a2[2] = {acc[0], acc[1]};
+                consume_tile<2>(st, xs + off, len, a2, lane);
+                acc[0] = a2[0]; acc[1] = a2[1];
+            }
+            ring_release(ring, P, warp, lane);
+        }
+        acc[0] = warp_sum_f(acc[0]);
+        acc[1] = warp_sum_f(acc[1]);
+        if (type == TOK_GATE) { acc[2] = warp_sum_f(acc[2]); acc[3] = warp_sum_f(acc[3]); }
+        if (lane != 0) continue;
+        uint64_t* out = reinterpret_cast<uint64_t*>(P.scratch + op.out_off);
+        if (type == TOK_QKV) {
+            // nn.Linear (+bias) output is a bf16 tensor; q and k rows rotate in fp32 (model.py:507-519), v rows do not
+            float a = bf16_round(acc[0] + e0), b = bf16_round(acc[1] + e1);
+            if (r0 < P.n_q_rows + P.n_kv_rows) {
+                const float ra = __fsub_rn(__fmul_rn(a, e2), __fmul_rn(b, e3));
+                const float rb = __fadd_rn(__fmul_rn(b, e2), __fmul_rn(a, e3));
+                a = ra; b = rb;
+            }
+            ll_store(out + g, pack_bf16x2(a, b), tag);
+        } else if (type == TOK_GEMV) {
+            const uint32_t d = pack_bf16x2(bf16_round(acc[0]), bf16_round(acc[1]));
+            if (push) {
+                outw[j] = d;
+            } else {
+                const size_t word = (size_t)P.rank * (op.N >> 1) + g;
+                for (int p = 0; p < op.out_world; ++p)
+                    ll_store(reinterpret_cast<uint64_t*>(P.peers[p] + op.out_off) + word, d, tag);
+            }
+        } else if (type == TOK_GATE) {
+            float o[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float gt = bf16_round(acc[q]);                      // w1(x), bf16 tensor
+                const float sg = bf16_round(gt / (1.0f + expf(-gt)));     // F.silu in fp32, bf16 out
+                o[q] = __fmul_rn(sg, bf16_round(acc[2 + q]));             // * w3(x)
+            }
+            ll_store(out + g, pack_bf16x2(o[0], o[1]), tag);
+        } else {  // TOK_HEAD: logits (model.py:291), running arg-max with torch.argmax's first-index rule
+            const float a = bf16_round(acc[0]), b = bf16_round(acc[1]);
+            if (P.logits_out) *reinterpret_cast<uint32_t*>(P.logits_out + r0) = pack_bf16x2(a, b);
+            if (a > best->v || (a == best->v && r0 < best->idx)) { best->v = a; best->idx = r0; }
+            if (b > best->v || (b == best->v && r0 + 1 < best->idx)) { best->v = b; best->idx = r0 + 1; }
+        }
+    }
+    if (push) {
+        // row-parallel partial outputs of this CTA are contiguous words: store them to every rank as whole lines
+        __syncthreads();
+        const size_t word0 = (size_t)P.rank * (op.N >> 1) + g0;
+        for (int t = tid; t < nloc * op.out_world; t += kTT) {
+            const int p = t / nloc, i = t - p * nloc;
+            ll_store(reinterpret_cast<uint64_t*>(P.peers[p] + op.out_off) + word0 + i, outw[i], tag);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ the attention stage
+// The cc_decode_step algorithm (decode_step.cu) for policies recent_global / l2 / heavy_hitter (full history), with
+// C CTAs per KV head exchanging {candidate, row max}, {softmax sums} and {P.V partials} through flag-in-data words.
+// attention scratch inside the staging area, in 4-byte words / bytes as noted
+struct AttnSmem {
+    float* lg; float* red; uint32_t* rec; uint32_t* sums; float* yx; unsigned long long* ssum; uint8_t* maskb; float* misc;
+};
+__host__ __device__ inline uint32_t attn_smem_bytes(int D, int G, int C, int stride, int local_rows) {
+    uint32_t off = 0;
+    off += (uint32_t)G * stride * 4;            // lg
+    off += (uint32_t)kTW * G * D * 4;           // red
+    off += (uint32_t)C * (2 + 2 * G) * 4;       // rec
+    off += (uint32_t)C * 2 * G * 4;             // sums (lo, hi)
+    off += (uint32_t)G * D * 4;                 // yx
+    off += kTokMaxG * 8;                        // ssum
+    off += ((uint32_t)local_rows + 15) / 16 * 16;  // maskb
+    off += 128 * 4;                             // misc
+    return off;
+}
+enum : int { kTmNewLg = 0, kTmMyRec = 16, kTmWarpKey = 48, kTmWarpMax = 80, kTmWords = 128 };
+
+template <int D, int G>
+__device__ void attn_stage(const TokParams& P, const TokAttn& A, int oi, uint8_t* smem, Ring& ring, uint32_t tag, Pending* pend) {
+    constexpr int LPR = D / 8;           // lanes per cache row
+    constexpr int RPI = 32 / LPR;        // rows per warp iteration
+    constexpr uint32_t kRowBytes = D * 2;
+    constexpr int NWR = 2 + 2 * G;       // words of an X1 record: key lo, key hi, lmax[G], candidate logits[G]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int li = lane % LPR, sub = lane / LPR;
+    const AttnDeal dl = deal_attn(A);
+    __syncthreads();   // the staging area of the previous stage is free
+    if (P.trace && tid == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.trace[((size_t)oi * gridDim.x + blockIdx.x) * 2] = t;
+    }
+    if (!dl.active) return;
+    const CcCacheState& st = A.st;
+    const int csh = A.c_shift, C = 1 << csh, chs = A.ch_shift, CH = 1 << chs, RW = CH / kTW;
+    const int h = dl.h, rank = dl.rank, nlc = dl.nlc;
+    const int H = st.n_kv_heads, L = st.max_cache_length;
+    const int policy = st.policy;
+    const bool naive = st.attn_mode == CC_ATTN_NAIVE_BF16;
+    const int local_rows = nlc << chs, stride = A.lg_stride;
+    auto slot_of = [&](int lr) { return ((((lr >> chs) << csh) + rank) << chs) + (lr & (CH - 1)); };
+
+    AttnSmem sm;
+    {
+        uint8_t* p = smem;
+        sm.lg = reinterpret_cast<float*>(p);    p += (size_t)G * stride * 4;
+        sm.red = reinterpret_cast<float*>(p);   p += (size_t)kTW * G * D * 4;
+        sm.rec = reinterpret_cast<uint32_t*>(p); p += (size_t)C * NWR * 4;
+        sm.sums = reinterpret_cast<uint32_t*>(p); p += (size_t)C * 2 * G * 4;
+        sm.yx = reinterpret_cast<float*>(p);    p += (size_t)G * D * 4;
+        sm.ssum = reinterpret_cast<unsigned long long*>(p); p += kTokMaxG * 8;
+        sm.maskb = p;                           p += ((size_t)local_rows + 15) / 16 * 16;
+        sm.misc = reinterpret_cast<float*>(p);
+    }
+    float* lg = sm.lg;
+    float* misc = sm.misc;
+    uint32_t* miscu = reinterpret_cast<uint32_t*>(misc);
+
+    uint64_t* x1 = reinterpret_cast<uint64_t*>(P.scratch + A.x1_off) + (size_t)h * C * NWR;
+    uint64_t* x2 = reinterpret_cast<uint64_t*>(P.scratch + A.x2_off) + (size_t)h * C * 2 * G;
+    uint64_t* x3 = reinterpret_cast<uint64_t*>(P.scratch + A.x3_off) + (size_t)h * C * G * D;
+    const uint64_t* qkv = reinterpret_cast<const uint64_t*>(P.scratch + A.qkv_off);
+
+    // ---- A. everything that does not need this token's q / k / v: mask bytes, arg-min candidate
+    const int ipos = P.input_pos[0];
+    const int pos_row = st.pos_heads == 1 ? 0 : h;
+    const int32_t* posp = st.pos + (size_t)pos_row * L;
+    for (int lr = tid; lr < local_rows; lr += kTT) {
+        const int s = slot_of(lr);
+        sm.maskb[lr] = s < L ? st.mask[(size_t)h * L + s] : 0;
+    }
+    if (tid < kTokMaxG) sm.ssum[tid] = 0ull;
+    float l2_max = 0.f;
+    if (policy == CC_POLICY_L2) {
+        // key_norm.max() over every head and slot (cache.py:602): 2 * H * L bytes from L2, every CTA for itself
+        const uint16_t* kn = reinterpret_cast<const uint16_t*>(st.key_norm);
+        float m = -CUDART_INF_F;
+        for (int i = tid; i < H * L; i += kTT) m = fmaxf(m, bf16_bits_to_float(kn[i]));
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+        if (lane == 0) misc[kTmWarpMax + warp] = m;
+        __syncthreads();
+        l2_max = misc[kTmWarpMax];
+        for (int w = 1; w < kTW; ++w) l2_max = fmaxf(l2_max, misc[kTmWarpMax + w]);
+    }
+    uint64_t ckey = kNoKey64;
+    if (policy == CC_POLICY_HEAVY_HITTER) {
+        const double* num = reinterpret_cast<const double*>(st.attn_history_num) + (size_t)h * L;
+        const int32_t* den = st.attn_history_denom + (size_t)h * L;
+        for (int lr = tid; lr < local_rows; lr += kTT) {
+            const int s = slot_of(lr);
+            if (s >= L) continue;
+            const int ps = posp[s];
+            // cache.py:727-749: mean accumulated attention; globals & recent -> 1.0; unfilled -> 0.0
+            float avg = __fdiv_rn(__double2float_rn(num[s]), (float)max(den[s], 1));
+            if (ps < st.global_tokens || ps >= ipos - st.recent_window) avg = 1.0f;
+            if (ps == -1) avg = 0.0f;
+            const uint64_t k = ((uint64_t)float_order_key(avg) << 32) | (uint32_t)s;
+            ckey = k < ckey ? k : ckey;
+        }
+    } else if (policy == CC_POLICY_L2) {
+        const uint16_t* kn = reinterpret_cast<const uint16_t*>(st.key_norm) + (size_t)h * L;
+        for (int lr = tid; lr < local_rows; lr += kTT) {
+            const int s = slot_of(lr);
+            if (s >= L) continue;
+            const int ps = posp[s];
+            // cache.py:597-605 then 366-379: bf16(max - norm); recent -> +inf; first g slots -> +inf; unfilled -> -inf
+            float sc = bf16_round(__fsub_rn(l2_max, bf16_bits_to_float(kn[s])));
+            if (ps >= ipos - st.recent_window) sc = CUDART_INF_F;
+            if (s < st.global_tokens) sc = CUDART_INF_F;
+            if (ps == -1) sc = -CUDART_INF_F;
+            const uint64_t k = ((uint64_t)float_order_key(sc) << 32) | (uint32_t)s;
+            ckey = k < ckey ? k : ckey;
+        }
+    } else {  // CC_POLICY_RECENT_GLOBAL, cache.py:552-556: oldest position among slots >= g (unfilled = -1 first)
+        for (int lr = tid; lr < local_rows; lr += kTT) {
+            const int s = slot_of(lr);
+            if (s >= L || s < st.global_tokens) continue;
+            const uint64_t k = ((uint64_t)((uint32_t)posp[s] ^ 0x80000000u) << 32) | (uint32_t)s;
+            ckey = k < ckey ? k : ckey;
+        }
+    }
+    ckey = warp_min_u64(ckey);
+    if (lane == 0) reinterpret_cast<unsigned long long*>(miscu + kTmWarpKey)[warp] = ckey;
+    __syncthreads();
+    ckey = lane < kTW ? reinterpret_cast<unsigned long long*>(miscu + kTmWarpKey)[lane] : kNoKey64;
+    ckey = warp_min_u64(ckey);
+    int cand_local = -1;
+    if (ckey != kNoKey64) {
+        const int s = (int)(uint32_t)(ckey & 0xffffffffu);
+        cand_local = (((s >> chs) >> csh) << chs) + (s & (CH - 1));
+    }
+
+    // ---- B. this token's query rows of the KV group, the new key and value slices (flag-in-data words of the
+    // projection stage): 4 words per 8 elements
+    float q[G][8];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+        unpack8(ll_wait4(qkv + (((size_t)(h * G + g) * D + li * 8) >> 1), tag), q[g]);
+    const uint4 knew8 = ll_wait4(qkv + (((size_t)P.n_q_rows + (size_t)h * D + li * 8) >> 1), tag);
+    const uint4 vnew8 = ll_wait4(qkv + (((size_t)P.n_q_rows + P.n_kv_rows + (size_t)h * D + li * 8) >> 1), tag);
+    if (P.trace && tid == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.trace[((size_t)oi * gridDim.x + blockIdx.x) * 2 + 1] = t;
+    }
+    if (warp == kTW - 1) {   // logits of the new token (it attends to itself, model.py:392 then 402)
+        float kf[8], part[G];
+        unpack8(knew8, kf);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc = __fmaf_rn(q[g][i], kf[i], acc);
+            part[g] = acc;
+        }
+        int gsel;
+        const float dot = group_reduce_multi<LPR, G>(part, li, &gsel);
+        const float v = naive ? bf16_round(__fmul_rn(bf16_round(dot), A.scale)) : __fmul_rn(dot, A.scale);
+        if (sub == 0 && gsel < G) misc[kTmNewLg + gsel] = v;
+    }
+    // ---- logits of this warp's rows of every local chunk (canonical dot tree), K tiles from the ring
+    for (int jj = 0; jj < nlc; ++jj) {
+        int first, nv;
+        attn_warp_rows(A, rank, jj, warp, &first, &nv);
+        const uint8_t* kt = nv > 0 ? ring_wait(ring) : nullptr;
+        const int lr0 = (jj << chs) + warp * RW;
+        for (int rb = 0; rb < RW; rb += RPI) {   // warp-uniform trip count: the dot tree shuffles over all lanes
+            const int r = rb + sub;
+            const uint4 kv = r < nv ? *reinterpret_cast<const uint4*>(kt + r * kRowBytes + li * 16) : make_uint4(0, 0, 0, 0);
+            float kf[8], part[G];
+            unpack8(kv, kf);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc = __fmaf_rn(q[g][i], kf[i], acc);
+                part[g] = acc;
+            }
+            int gsel;
+            const float dot = group_reduce_multi<LPR, G>(part, li, &gsel);
+            // naive path rounds q@k^T to bf16, then * scale to bf16 (attention_utils.py:37)
+            const float v = naive ? bf16_round(__fmul_rn(bf16_round(dot), A.scale)) : __fmul_rn(dot, A.scale);
+            const int lr = lr0 + r;
+            if (gsel < G && r < RW) lg[gsel * stride + lr] = (r < nv && sm.maskb[lr]) ? v : -CUDART_INF_F;
+        }
+        if (nv > 0) ring_release(ring, P, warp, lane);
+    }
+    __syncthreads();
+    // ---- row max without the local candidate, and the candidate's own logits -> this CTA's X1 record
+    for (int g = warp; g < G; g += kTW) {
+        float m = -CUDART_INF_F;
+        for (int lr = lane; lr < local_rows; lr += 32)
+            if (lr != cand_local) m = fmaxf(m, lg[g * stride + lr]);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+        if (lane == 0) {
+            misc[kTmMyRec + 2 + g] = m;
+            misc[kTmMyRec + 2 + G + g] = cand_local >= 0 ? lg[g * stride + cand_local] : -CUDART_INF_F;
+        }
+    }
+    if (tid == 0) {
+        miscu[kTmMyRec + 0] = (uint32_t)(ckey & 0xffffffffu);
+        miscu[kTmMyRec + 1] = (uint32_t)(ckey >> 32);
+    }
+    __syncthreads();
+    // ---- X1: every CTA of the head learns every candidate and every partial max
+    if (tid < NWR) ll_store(x1 + (size_t)rank * NWR + tid, miscu[kTmMyRec + tid], tag);
+    for (int idx = tid; idx < C * NWR; idx += kTT) sm.rec[idx] = ll_wait(x1 + idx, tag);
+    __syncthreads();
+    // winner + global max per query head (every warp redundantly)
+    uint64_t wkey = kNoKey64;
+    for (int r = lane; r < C; r += 32) {
+        const uint64_t k = (uint64_t)sm.rec[r * NWR] | ((uint64_t)sm.rec[r * NWR + 1] << 32);
+        wkey = k < wkey ? k : wkey;
+    }
+    wkey = warp_min_u64(wkey);
+    const bool has_slot = wkey != kNoKey64;   // a slot is overwritten this step, and the new token attends to itself there
+    const int widx = has_slot ? (int)(uint32_t)(wkey & 0xffffffffu) : -1;
+    const int owner = has_slot ? (widx >> chs) & (C - 1) : -1;
+    const bool i_own = has_slot && owner == rank;
+    const int widx_local = has_slot ? (((widx >> chs) >> csh) << chs) + (widx & (CH - 1)) : -1;
+    float gmax[G], newlg[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        float m = -CUDART_INF_F;
+        for (int r = lane; r < C; r += 32) {
+            m = fmaxf(m, __uint_as_float(sm.rec[r * NWR + 2 + g]));
+            const bool r_has_cand = (sm.rec[r * NWR] & sm.rec[r * NWR + 1]) != 0xffffffffu;
+            // a candidate that is not overwritten keeps its logit
+            if (r_has_cand && r != owner) m = fmaxf(m, __uint_as_float(sm.rec[r * NWR + 2 + G + g]));
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+        newlg[g] = has_slot ? misc[kTmNewLg + g] : -CUDART_INF_F;
+        gmax[g] = fmaxf(m, newlg[g]);
+    }
+    const int patch_row = i_own ? widx_local : -1;  // this row now holds the new token
+
+    // ---- exp and the exact fixed-point softmax denominator = X2
+    {
+        const int rows_pad = (local_rows + 31) & ~31;
+        for (int it = tid; it < G * rows_pad; it += kTT) {
+            const int g = it / rows_pad, lr = it - g * rows_pad;
+            long long part = 0;
+            if (lr < local_rows) {
+                float gm = gmax[0], nl = newlg[0];
+#pragma unroll
+                for (int gg = 1; gg < G; ++gg) if (g == gg) { gm = gmax[gg]; nl = newlg[gg]; }
+                const float l = lr == patch_row ? nl : lg[g * stride + lr];
+                const float e = det_expf(__fsub_rn(l, gm));
+                lg[g * stride + lr] = e;
+                part = __float2ll_rz(__fmul_rn(e, 1099511627776.0f));
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+            if (lane == 0 && part) atomicAdd(&sm.ssum[g], (unsigned long long)part);  // integers: order independent
+        }
+    }
+    __syncthreads();
+    if (tid < 2 * G) ll_store(x2 + (size_t)rank * 2 * G + tid, (uint32_t)(sm.ssum[tid >> 1] >> (32 * (tid & 1))), tag);
+    for (int idx = tid; idx < C * 2 * G; idx += kTT) sm.sums[idx] = ll_wait(x2 + idx, tag);
+    __syncthreads();
+    float sumf[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        long long t = 0;
+        for (int r = lane; r < C; r += 32)
+            t += (long long)((unsigned long long)sm.sums[(r * G + g) * 2] | ((unsigned long long)sm.sums[(r * G + g) * 2 + 1] << 32));
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+        sumf[g] = __fmul_rn(__ll2float_rn(t), 9.094947017729282e-13f);  // 2^-40
+    }
+    for (int it = tid; it < G * local_rows; it += kTT) {
+        const int g = it / local_rows, lr = it - g * local_rows;
+        float sf = sumf[0];
+#pragma unroll
+        for (int gg = 1; gg < G; ++gg) if (g == gg) sf = sumf[gg];
+        float pr = __fdiv_rn(lg[g * stride + lr], sf);
+        if (naive) pr = bf16_round(pr);
+        lg[g * stride + lr] = pr;
+    }
+    __syncthreads();
+
+    // ---- y = P.V over this warp's V tiles, warp -> CTA -> head reduction = X3
+    {
+        float acc[G][8];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[g][i] = 0.f;
+        for (int jj = 0; jj < nlc; ++jj) {
+            int first, nv;
+            attn_warp_rows(A, rank, jj, warp, &first, &nv);
+            if (nv <= 0) continue;
+            const uint8_t* vt = ring_wait(ring);
+            const int lr0 = (jj << chs) + warp * RW;
+            for (int r = sub; r < nv; r += RPI) {
+                const int lr = lr0 + r;
+                uint4 vv = *reinterpret_cast<const uint4*>(vt + r * kRowBytes + li * 16);
+                if (lr == patch_row) vv = vnew8;
+                float vf[8];
+                unpack8(vv, vf);
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const float pr = lg[g * stride + lr];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[g][i] = fmaf(pr, vf[i], acc[g][i]);
+                }
+            }
+            ring_release(ring, P, warp, lane);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float v = acc[g][i];
+#pragma unroll
+                for (int d = 16; d >= LPR; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                acc[g][i] = v;
+            }
+        if (lane < LPR) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float4* dst = reinterpret_cast<float4*>(&sm.red[warp * G * D + g * D + lane * 8]);
+                dst[0] = make_float4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]);
+                dst[1] = make_float4(acc[g][4], acc[g][5], acc[g][6], acc[g][7]);
+            }
+        }
+    }
+    __syncthreads();
+    const int SL = (G * D) >> csh;  // outputs reduced by each CTA of the head (a multiple of 4)
+    for (int o = tid; o < G * D; o += kTT) {
+        float s = sm.red[o];
+#pragma unroll
+        for (int w = 1; w < kTW; ++w) s += sm.red[w * G * D + o];
+        const int dest = o / SL, off = o - dest * SL;
+        ll_store(x3 + ((size_t)dest * C + rank) * SL + off, __float_as_uint(s), tag);
+    }
+
+    // ======== while the partial sums travel: global state writes ========
+    // owner CTA: in-place slot overwrite (cache.py:390-401 / 460-490) + policy state
+    if (i_own && warp == kTW - 1) {
+        if (lane < LPR) {
+            uint16_t* kd = reinterpret_cast<uint16_t*>(st.k_cache) + ((size_t)h * L + widx) * D + lane * 8;
+            uint16_t* vd = reinterpret_cast<uint16_t*>(st.v_cache) + ((size_t)h * L + widx) * D + lane * 8;
+            *reinterpret_cast<uint4*>(kd) = knew8;   // lanes < LPR have sub == 0, li == lane
+            *reinterpret_cast<uint4*>(vd) = vnew8;
+        }
+        float knorm = 0.f;
+        if (policy == CC_POLICY_L2) {
+            // key_norm[idx] = ||k_new||_2 (cache.py:592-593), canonical tree, correctly rounded sqrt
+            float kf[8];
+            unpack8(knew8, kf);
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc = __fmaf_rn(kf[i], kf[i], acc);
+            knorm = __fsqrt_rn(group_butterfly<LPR>(acc));
+        }
+        if (lane == 0) {
+            const int32_t pos_old = posp[widx];
+            st.mask[(size_t)h * L + widx] = 1;
+            if (A.fill_idx) A.fill_idx[h] = widx;
+            // cross-head state (head-constant pos, key_norm: read by the CTAs of every head above) is written once
+            // the NEXT stage's input is complete, i.e. when all heads are past their reads
+            pend->pos_ptr = nullptr; pend->kn_ptr = nullptr;
+            if (st.pos_heads != 1) st.pos[(size_t)pos_row * L + widx] = ipos;
+            else if (h == 0) { pend->pos_ptr = st.pos + widx; pend->pos_val = ipos; }
+            if (policy == CC_POLICY_L2) {
+                pend->kn_ptr = reinterpret_cast<uint16_t*>(st.key_norm) + (size_t)h * L + widx;
+                const __nv_bfloat16 kb = __float2bfloat16_rn(knorm);
+                pend->kn_val = *reinterpret_cast<const uint16_t*>(&kb);
+            }
+            pend->active = (pend->pos_ptr || pend->kn_ptr) ? 1 : 0;
+            if (h == 0) st.cache_cts[0] += (pos_old == -1) ? 1 : 0;  // cache.py:330, 356-360
+        }
+    }
+    // GQA pooling (model.py:413-418) and the score update (cache.py:716-723)
+    if (naive) {
+        const bool hh = policy == CC_POLICY_HEAVY_HITTER;
+        for (int lr = tid; lr < local_rows; lr += kTT) {
+            const int s = slot_of(lr);
+            if (s >= L) continue;
+            float acc = lg[lr];
+#pragma unroll
+            for (int g = 1; g < G; ++g) acc = __fadd_rn(acc, lg[g * stride + lr]);
+            const float pooled = bf16_round(__fdiv_rn(acc, (float)G));  // torch mean: fp32 sum / G, then bf16
+            if (A.probs) A.probs[(size_t)h * L + s] = __float2bfloat16_rn(pooled);
+            if (hh) {
+                double* num = reinterpret_cast<double*>(st.attn_history_num) + (size_t)h * L;
+                int32_t* den = st.attn_history_denom + (size_t)h * L;
+                const bool fresh = has_slot && s == widx;  // evicted slot's history restarts (cache.py:753-763)
+                num[s] = (fresh ? 0.0 : num[s]) + (double)pooled;
+                den[s] = (fresh ? 0 : den[s]) + 1;
+            }
+        }
+        if (hh && h == 0 && rank == 0 && tid == 0) st.attn_counter[0] += 1;
+    }
+    // ---- X3 arrives: this CTA's slice of y
+    {
+        uint64_t* yout = reinterpret_cast<uint64_t*>(P.scratch + A.y_off) + (((size_t)h * G * D + (size_t)rank * SL) >> 1);
+        const uint64_t* mine = x3 + (size_t)rank * C * SL;
+        for (int t = tid; t < (SL >> 1); t += kTT) {
+            float s0 = 0.f, s1 = 0.f;
+            for (int r = 0; r < C; ++r) {
+                s0 += __uint_as_float(ll_wait(mine + (size_t)r * SL + 2 * t, tag));
+                s1 += __uint_as_float(ll_wait(mine + (size_t)r * SL + 2 * t + 1, tag));
+            }
+            ll_store(yout + t, pack_bf16x2(s0, s1), tag);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int D, int G>
+__global__ void __launch_bounds__(kTT, 1) cc_token_kernel(const __grid_constant__ TokParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ float scratch[kTW];
+    __shared__ uint32_t outw[kOutStage];
+    __shared__ Pending pend;
+    __shared__ HeadBest wbest[kTW];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t ring_off = (P.xs_bytes + 127u) & ~127u;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ring_off + (size_t)kTW * P.n_stages * kStage);
+
+    Ring ring;
+    ring.ns = P.n_stages;
+    ring.cs = 0;
+    ring.phases = 0;
+    ring.stages = smem + ring_off + (size_t)warp * P.n_stages * kStage;
+    ring.bars = bars + warp * P.n_stages;
+    if (lane == 0) {
+        for (int s = 0; s < P.n_stages; ++s) mbar_init(&ring.bars[s], 1);
+        mbar_fence_init();
+    }
+    if (tid == 0) pend.active = 0;
+    __syncwarp();
+    // the weight / cache stream starts before anything else: fill the whole ring
+    ring.it.op = 0;
+    if (lane == 0) {
+        iter_enter(ring.it, P, warp);
+        for (int s = 0; s < P.n_stages && ring.it.op < P.n_ops; ++s) {
+            iter_issue(ring.it, warp, ring.stages + (size_t)s * kStage, &ring.bars[s]);
+            iter_advance(ring.it, P, warp);
+        }
+    }
+    __syncwarp();
+    TokHeader* hdr = reinterpret_cast<TokHeader*>(P.scratch);
+    const uint32_t tag = *reinterpret_cast<volatile uint32_t*>(&hdr->gen) + 1u;
+    HeadBest best = {-CUDART_INF_F, 0x7fffffff};
+    bool has_head = false;
+
+    for (int oi = 0; oi < P.n_ops; ++oi) {
+        const TokOp& op = P.ops[oi];
+        if (op.type == TOK_ATTN) {
+            attn_stage<D, G>(P, P.attns[op.attn], oi, smem, ring, tag, &pend);
+        } else {
+            gemv_stage(P, op, oi, smem, ring, tag, scratch, outw, &pend, &best);
+            has_head |= op.type == TOK_HEAD;
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && pend.active) {   // a program that ends with an attention stage (tests)
+        if (pend.pos_ptr) *pend.pos_ptr = pend.pos_val;
+        if (pend.kn_ptr) *pend.kn_ptr = (uint16_t)pend.kn_val;
+        pend.active = 0;
+    }
+
+    // ---- greedy sampling (generation_utils.py:136-142): arg-max over all CTAs' rows, optional softmax
+    if (has_head) {
+        if (lane == 0) wbest[warp] = best;
+        __syncthreads();
+        HeadBest cb = wbest[0];
+        for (int w = 1; w < kTW; ++w)
+            if (wbest[w].v > cb.v || (wbest[w].v == cb.v && wbest[w].idx < cb.idx)) cb = wbest[w];
+        uint64_t* rec1 = reinterpret_cast<uint64_t*>(P.scratch + P.rec1_off);
+        const int nc = (int)gridDim.x;
+        if (tid == 0) {
+            ll_store(rec1 + 2 * blockIdx.x, __float_as_uint(cb.v), tag);
+            ll_store(rec1 + 2 * blockIdx.x + 1, (uint32_t)cb.idx, tag);
+        }
+        // every CTA reduces all records (it needs the global max for the softmax anyway)
+        HeadBest gb = {-CUDART_INF_F, 0x7fffffff};
+        for (int c = lane; c < nc; c += 32) {
+            const float v = __uint_as_float(ll_wait(rec1 + 2 * c, tag));
+            const int idx = (int)ll_wait(rec1 + 2 * c + 1, tag);
+            if (v > gb.v || (v == gb.v && idx < gb.idx)) { gb.v = v; gb.idx = idx; }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, gb.v, d);
+            const int oidx = __shfl_xor_sync(0xffffffffu, gb.idx, d);
+            if (ov > gb.v || (ov == gb.v && oidx < gb.idx)) { gb.v = ov; gb.idx = oidx; }
+        }
+        if (blockIdx.x == 0 && tid == 0 && P.token_out) P.token_out[0] = gb.idx;
+        if (P.probs_out && P.logits_out) {
+            // softmax over the bf16 logits in fp32 (torch.softmax on a bf16 tensor), one bf16 rounding
+            const TokOp& hop = P.ops[P.n_ops - 1];
+            int g0, nloc;
+            deal_groups(hop.n_groups, hop.rot, &g0, &nloc);
+            float part = 0.f;
+            for (int i = tid; i < 2 * nloc; i += kTT)
+                part += expf(__bfloat162float(P.logits_out[2 * g0 + i]) - gb.v);
+            part = warp_sum_f(part);
+            if (lane == 0) scratch[warp] = part;
+            __syncthreads();
+            uint64_t* rec2 = reinterpret_cast<uint64_t*>(P.scratch + P.rec2_off);
+            if (tid == 0) {
+                float tot = 0.f;
+                for (int w = 0; w < kTW; ++w) tot += scratch[w];
+                ll_store(rec2 + blockIdx.x, __float_as_uint(tot), tag);
+            }
+            float tot = 0.f;
+            for (int c = 0; c < nc; ++c) tot += __uint_as_float(ll_wait(rec2 + c, tag));  // CTA order: deterministic
+            for (int i = tid; i < 2 * nloc; i += kTT) {
+                const float l = __bfloat162float(P.logits_out[2 * g0 + i]);
+                P.probs_out[2 * g0 + i] = __float2bfloat16_rn(__fdiv_rn(expf(l - gb.v), tot));
+            }
+        }
+    }
+    // ---- the last CTA to finish advances the token tag
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const uint32_t prev = atomicAdd(&hdr->done, 1u);
+        if (prev == gridDim.x - 1) {
+            hdr->done = 0;
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t*>(&hdr->gen) = tag;
+        }
+    }
+}
+
+// pack / unpack between plain bf16 vectors and flag-in-data words (tests: CC_FLAG_VIA_TOKEN_KERNEL)
+__global__ void tok_pack_kernel(const uint32_t* __restrict__ src, uint64_t* dst, int n_words, const TokHeader* hdr) {
+    const uint32_t tag = hdr->gen + 1u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x)
+        dst[i] = ((uint64_t)tag << 32) | src[i];
+}
+__global__ void tok_unpack_kernel(const uint64_t* __restrict__ src, uint32_t* dst, int n_words) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x)
+        dst[i] = (uint32_t)src[i];
+}
+
+// --------------------------------------------------------------------------- host side
+using TokKernelFn = void (*)(const TokParams);
+
+template <int D>
+static TokKernelFn pick_tok_group(int G) {
+    switch (G) {
+    case 1: return cc_token_kernel<D, 1>;
+    case 2: return cc_token_kernel<D, 2>;
+    case 4: return cc_token_kernel<D, 4>;
+    case 7: return cc_token_kernel<D, 7>;
+    case 8: return cc_token_kernel<D, 8>;
+    default: return nullptr;
+    }
+}
+static TokKernelFn pick_tok_kernel(int D, int G) {
+    if (D == 128) return pick_tok_group<128>(G);
+    if (D == 64) return pick_tok_group<64>(G);
+    return nullptr;
+}
+
+struct BufMap { uint64_t off; int32_t words; };
+
+struct TokenPlan {
+    TokParams p;
+    TokKernelFn fn;
+    TokOp* d_ops;
+    TokAttn* d_attns;
+    uint64_t* d_peers;
+    int n_ctas;
+    uint32_t smem;
+    int n_layers;
+    std::vector<BufMap> bufs;   // [layer][7]
+    uint64_t scratch_bytes;
+};
+
+static uint64_t align_up64(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+struct AttnShape { int c_shift, ch_shift, stride, local_rows; uint32_t smem; };
+
+static int attn_shape(const CcCacheState& st, int n_ctas, AttnShape* out) {
+    const int H = st.n_kv_heads, L = st.max_cache_length, G = st.q_per_kv, D = st.head_dim;
+    if (H > n_ctas) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "more KV heads than SMs");
+    int csh = 0;
+    while ((2 << csh) * H <= n_ctas && (2 << csh) <= 128) ++csh;
+    while (csh > 0 && (1 << csh) > (G * D) / 4) --csh;                 // every CTA reduces >= 4 outputs of y
+    while (csh > 0 && (1 << csh) > (L + 15) / 16) --csh;               // every CTA gets >= 1 chunk of >= 16 rows
+    int chs = 7;
+    while (chs > 4 && ((L + (1 << chs) - 1) >> chs) < (1 << csh)) --chs;
+    const int C = 1 << csh, n_chunks = (L + (1 << chs) - 1) >> chs;
+    const int mlc = (n_chunks + C - 1) / C;
+    out->c_shift = csh; out->ch_shift = chs;
+    out->local_rows = mlc << chs;
+    out->stride = (out->local_rows + 31) / 32 * 32;
+    out->smem = attn_smem_bytes(D, G, C, out->stride, out->local_rows);
+    return CC_OK;
+}
+
+struct Layout {
+    uint64_t total;
+    std::vector<BufMap> bufs;   // per layer 7 entries, then one extra layer entry for the head input
+    std::vector<uint64_t> x1, x2, x3;
+    uint64_t rec1, rec2;
+};
+
+static int token_policy_ok(const CcCacheState& st) {
+    if (st.policy == CC_POLICY_RECENT_GLOBAL || st.policy == CC_POLICY_L2) return st.attn_mode == CC_ATTN_MATH_FP32;
+    if (st.policy == CC_POLICY_HEAVY_HITTER)
+        return st.attn_mode == CC_ATTN_NAIVE_BF16 && st.history_window == 1 && !st.attn_thresholding;
+    return 0;
+}
+
+static int build_layout(const CcTokenModel* m, int n_ctas, Layout* lay) {
+    uint64_t off = 256;   // header
+    auto take = [&](uint64_t words) { const uint64_t o = off; off = align_up64(off + words * 8, 256); return o; };
+    const int D = m->head_dim, world = m->world;
+    const int qkv_rows = (m->n_q_heads + 2 * m->n_kv_heads) * D;
+    lay->bufs.assign((size_t)(m->n_layers + 1) * 7, BufMap{0, 0});
+    for (int l = 0; l < m->n_layers; ++l) {
+        BufMap* b = &lay->bufs[(size_t)l * 7];
+        b[0] = {take(qkv_rows / 2), qkv_rows / 2};
+        b[1] = {take(m->n_q_heads * D / 2), m->n_q_heads * D / 2};
+        b[2] = {take((uint64_t)world * m->dim / 2), world * m->dim / 2};
+        b[3] = {take(m->dim / 2), m->dim / 2};
+        b[4] = {take(m->intermediate / 2), m->intermediate / 2};
+        b[5] = {take((uint64_t)world * m->dim / 2), world * m->dim / 2};
+        if (l > 0) b[6] = {take(m->dim / 2), m->dim / 2};
+        const CcCacheState& st = m->layers[l].cache;
+        AttnShape sh;
+        if (int rc = attn_shape(st, n_ctas, &sh)) return rc;
+        const int C = 1 << sh.c_shift, G = st.q_per_kv;
+        lay->x1.push_back(take((uint64_t)st.n_kv_heads * C * (2 + 2 * G)));
+        lay->x2.push_back(take((uint64_t)st.n_kv_heads * C * 2 * G));
+        lay->x3.push_back(take((uint64_t)st.n_kv_heads * C * G * D));
+    }
+    lay->bufs[(size_t)m->n_layers * 7 + 6] = {take(m->dim / 2), m->dim / 2};
+    lay->rec1 = take(2 * (uint64_t)n_ctas);
+    lay->rec2 = take((uint64_t)n_ctas);
+    lay->total = off;
+    return CC_OK;
+}
+
+static int validate_model(const CcTokenModel* m) {
+    if (!m || !m->layers || m->n_layers < 1) return set_error(CC_ERR_INVALID_ARG, "cc_token: null model or no layers");
+    if (m->world < 1 || m->world > kTokMaxWorld || m->rank < 0 || m->rank >= m->world)
+        return set_error(CC_ERR_INVALID_ARG, "cc_token: bad world / rank");
+    const bool attn_only_prog = m->n_layers == 1 && m->layers[0].wqkv == nullptr;   // tests: one attention stage
+    if (!attn_only_prog && (m->dim % 256 || m->intermediate % 256 || (m->n_q_heads * m->head_dim) % 256))
+        return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_token: dim, intermediate size and n_q_heads * head_dim must be multiples of 256");
+    if ((m->n_q_heads * m->head_dim) % 8) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_token: n_q_heads * head_dim must be a multiple of 8");
+    if (m->head_dim != 64 && m->head_dim != 128) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_token: head_dim must be 64 or 128");
+    if (m->n_kv_heads < 1 || m->n_q_heads % m->n_kv_heads) return set_error(CC_ERR_INVALID_ARG, "cc_token: bad head counts");
+    if (m->vocab & 1) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_token: vocabulary rows must be even");
+    const int G = m->n_q_heads / m->n_kv_heads;
+    if (!pick_tok_kernel(m->head_dim, G)) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_token: unsupported q_per_kv (1, 2, 4, 7, 8)");
+    for (int l = 0; l < m->n_layers; ++l) {
+        const CcTokenLayer& y = m->layers[l];
+        const CcCacheState& st = y.cache;
+        if (!y.wqkv || !y.attention_norm) {   // attention-only program (tests)
+            if (m->n_layers != 1) return set_error(CC_ERR_INVALID_ARG, "cc_token: null layer weights");
+        } else if (!y.wo || !y.ffn_norm || !y.w1 || !y.w3 || !y.w2) {
+            return set_error(CC_ERR_INVALID_ARG, "cc_token: null layer weights");
+        }
+        if (st.n_kv_heads != m->n_kv_heads || st.q_per_kv != G || st.head_dim != m->head_dim)
+            return set_error(CC_ERR_INVALID_ARG, "cc_token: cache shape does not match the model");
+        if (!token_policy_ok(st))
+            return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_token: cache policy not supported by the whole-token kernel "
+                                                       "(recent_global, l2, heavy_hitter with full history)");
+        if (!st.k_cache || !st.v_cache || !st.pos || !st.mask || !st.cache_cts) return set_error(CC_ERR_INVALID_ARG, "cc_token: null cache buffer");
+        if (st.pos_heads != 1 && st.pos_heads != st.n_kv_heads) return set_error(CC_ERR_INVALID_ARG, "cc_token: pos_heads must be 1 or n_kv_heads");
+        if (st.policy == CC_POLICY_HEAVY_HITTER && (!st.attn_history_num || !st.attn_history_denom || !st.attn_counter))
+            return set_error(CC_ERR_INVALID_ARG, "cc_token: null heavy_hitter state");
+        if (st.policy == CC_POLICY_L2 && !st.key_norm) return set_error(CC_ERR_INVALID_ARG, "cc_token: null key_norm");
+        if (st.policy == CC_POLICY_RECENT_GLOBAL && st.global_tokens >= st.max_cache_length)
+            return set_error(CC_ERR_INVALID_ARG, "cc_token: global_tokens must be < max_cache_length");
+    }
+    return CC_OK;
+}
+
+static int token_device(int* n_sms, int* smem_optin) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return set_error(CC_ERR_NO_DEVICE, "no CUDA device");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return set_error(CC_ERR_NO_DEVICE, "cudaGetDeviceProperties failed");
+    if (prop.major != 10) return set_error(CC_ERR_NO_DEVICE, "this library is built for sm_100a (Blackwell B200) only");
+    if (!prop.cooperativeLaunch) return set_error(CC_ERR_NO_DEVICE, "device does not support cooperative launches");
+    *n_sms = prop.multiProcessorCount;
+    *smem_optin = (int)prop.sharedMemPerBlockOptin;
+    return CC_OK;
+}
+
+unsigned long long token_scratch_bytes_impl(const CcTokenModel* m) {
+    if (validate_model(m)) return 0;
+    int n_sms = 148, optin = 0;
+    if (const char* e = getenv("CC_B200_TOKEN_CTAS")) n_sms = atoi(e);
+    else if (token_device(&n_sms, &optin)) n_sms = 148;   // sizing without a device (tests of the host logic)
+    Layout lay;
+    if (build_layout(m, n_sms, &lay)) return 0;
+    return lay.total;
+}
+
+static void seg_plan(int K, int rg, int* seg_len, int* n_seg) {
+    const int cap = (int)(kStage / 2) / rg;   // elements per row per stage
+    int sl = K < cap ? K : cap;
+    sl = sl / 256 * 256;
+    *seg_len = sl;
+    *n_seg = (K + sl - 1) / sl;
+}
+
+int token_plan_create_impl(const CcTokenModel* m, void** out_plan) {
+    if (!out_plan) return set_error(CC_ERR_INVALID_ARG, "cc_token_plan_create: null out pointer");
+    if (int rc = validate_model(m)) return rc;
+    if (!m->scratch_peers) return set_error(CC_ERR_INVALID_ARG, "cc_token_plan_create: null scratch_peers");
+    int n_sms = 0, optin = 0;
+    if (int rc = token_device(&n_sms, &optin)) return rc;
+    int n_ctas = n_sms;
+    if (const char* e = getenv("CC_B200_TOKEN_CTAS")) n_ctas = atoi(e) > 0 ? atoi(e) : n_ctas;   // experiments only
+    Layout lay;
+    if (int rc = build_layout(m, n_ctas, &lay)) return rc;
+    if (m->scratch_bytes < lay.total) return set_error(CC_ERR_INVALID_ARG, "cc_token_plan_create: scratch smaller than cc_token_scratch_bytes()");
+    const int D = m->head_dim, G = m->n_q_heads / m->n_kv_heads, world = m->world;
+    const bool attn_only = m->layers[0].wqkv == nullptr;
+    std::vector<TokOp> ops;
+    std::vector<TokAttn> attns;
+    uint32_t xs_bytes = 1024;
+    int rot = 0;
+    auto next_rot = [&](int n_groups) { const int r = rot; rot = (rot + n_groups % n_ctas) % n_ctas; return r; };
+    auto base_op = [&](int type, int K, int N, int rg, int layer) {
+        TokOp o;
+        memset(&o, 0, sizeof(o));
+        o.type = type; o.K = K; o.N = N; o.n_groups = N / 2; o.layer = layer;
+        seg_plan(K, rg, &o.seg_len, &o.n_seg);
+        o.rot = next_rot(o.n_groups);
+        o.publish_cta = -1; o.in_world = 1; o.out_world = 1; o.attn = -1;
+        if ((uint32_t)K * 2 > xs_bytes) xs_bytes = (uint32_t)K * 2;
+        return o;
+    };
+    const int qkv_rows = (m->n_q_heads + 2 * m->n_kv_heads) * D;
+    for (int l = 0; l < m->n_layers; ++l) {
+        const CcTokenLayer& y = m->layers[l];
+        const BufMap* b = &lay.bufs[(size_t)l * 7];
+        if (!attn_only) {
+            TokOp o = base_op(TOK_QKV, m->dim, qkv_rows, 2, l);
+            if (l == 0) {
+                o.in_kind = IN_TOKEN;
+            } else {   // x_l = h_{l-1} + all-reduce(w2 partials of layer l-1)
+                const BufMap* pb = &lay.bufs[(size_t)(l - 1) * 7];
+                o.in_kind = IN_LL; o.in_world = world; o.in_off = pb[5].off;
+                o.res_kind = RES_LL; o.res_off = pb[3].off;
+                o.publish_cta = (2 * l) % n_ctas; o.sum_off = b[6].off;
+            }
+            o.norm_w = (const __nv_bfloat16*)y.attention_norm; o.eps = y.attention_norm_eps;
+            o.w = (const __nv_bfloat16*)y.wqkv; o.bias = (const __nv_bfloat16*)y.bqkv;
+            o.out_off = b[0].off;
+            ops.push_back(o);
+        }
+        {
+            TokOp o;
+            memset(&o, 0, sizeof(o));
+            o.type = TOK_ATTN; o.layer = l; o.attn = (int)attns.size(); o.publish_cta = -1;
+            TokAttn a;
+            memset(&a, 0, sizeof(a));
+            a.st = y.cache;
+            AttnShape sh;
+            if (int rc = attn_shape(a.st, n_ctas, &sh)) return rc;
+            a.c_shift = sh.c_shift; a.ch_shift = sh.ch_shift; a.lg_stride = sh.stride;
+            a.rot = (l * 37) % n_ctas;
+            a.scale = (float)(1.0 / sqrt((double)D));
+            a.qkv_off = b[0].off; a.y_off = b[1].off;
+            a.x1_off = lay.x1[l]; a.x2_off = lay.x2[l]; a.x3_off = lay.x3[l];
+            a.fill_idx = y.fill_idx; a.probs = (__nv_bfloat16*)y.probs;
+            if (sh.smem > xs_bytes) xs_bytes = sh.smem;
+            attns.push_back(a);
+            ops.push_back(o);
+        }
+        if (attn_only) continue;
+        {   // wo: row-parallel under tensor parallelism, partial sums to every rank
+            TokOp o = base_op(TOK_GEMV, m->n_q_heads * D, m->dim, 2, l);
+            o.in_kind = IN_LL; o.in_off = b[1].off;
+            o.w = (const __nv_bfloat16*)y.wo;
+            o.out_off = b[2].off; o.out_world = world;
+            ops.push_back(o);
+        }
+        {   // h = x + all-reduce(wo partials); ffn_norm; silu(w1 h) * w3 h
+            TokOp o = base_op(TOK_GATE, m->dim, m->intermediate, 4, l);
+            o.in_kind = IN_LL; o.in_world = world; o.in_off = b[2].off;
+            if (l == 0) o.res_kind = RES_TOKEN; else { o.res_kind = RES_LL; o.res_off = b[6].off; }
+            o.publish_cta = (2 * l + 1) % n_ctas; o.sum_off = b[3].off;
+            o.norm_w = (const __nv_bfloat16*)y.ffn_norm; o.eps = y.ffn_norm_eps;
+            o.w = (const __nv_bfloat16*)y.w1; o.w3 = (const __nv_bfloat16*)y.w3;
+            o.out_off = b[4].off;
+            ops.push_back(o);
+        }
+        {   // w2: row-parallel
+            TokOp o = base_op(TOK_GEMV, m->intermediate, m->dim, 2, l);
+            o.in_kind = IN_LL; o.in_off = b[4].off;
+            o.w = (const __nv_bfloat16*)y.w2;
+            o.out_off = b[5].off; o.out_world = world;
+            ops.push_back(o);
+        }
+    }
+    if (!attn_only) {
+        if (!m->output || !m->norm || !m->tok_embeddings || !m->freqs_cis)
+            return set_error(CC_ERR_INVALID_ARG, "cc_token_plan_create: null embedding / norm / output / freqs_cis");
+        const int l = m->n_layers;
+        const BufMap* pb = &lay.bufs[(size_t)(l - 1) * 7];
+        TokOp o = base_op(TOK_HEAD, m->dim, m->vocab, 2, l);
+        o.in_kind = IN_LL; o.in_world = world; o.in_off = pb[5].off;
+        o.res_kind = RES_LL; o.res_off = pb[3].off;
+        o.publish_cta = (2 * l) % n_ctas; o.sum_off = lay.bufs[(size_t)l * 7 + 6].off;
+        o.norm_w = (const __nv_bfloat16*)m->norm; o.eps = m->norm_eps;
+        o.w = (const __nv_bfloat16*)m->output;
+        ops.push_back(o);
+    }
+    xs_bytes = (xs_bytes + 1023u) & ~1023u;
+    TokKernelFn fn = pick_tok_kernel(D, G);
+    cudaFuncAttributes fattr;
+    if (cudaFuncGetAttributes(&fattr, fn) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(CC_ERR_NO_DEVICE, "cc_token: no kernel image for this device");
+    }
+    const int max_dyn = optin - (int)fattr.sharedSizeBytes;   // static shared memory counts against the same limit
+    // shared memory: staging area | ring (8 warps x n_stages x 8 KiB) | mbarriers
+    const int avail = max_dyn - (int)xs_bytes - 1024 /* barriers + slack */;
+    int n_stages = avail / (int)(kTW * kStage);
+    if (n_stages > 8) n_stages = 8;
+    if (const char* e = getenv("CC_B200_TOKEN_STAGES")) n_stages = atoi(e) < n_stages && atoi(e) > 0 ? atoi(e) : n_stages;
+    if (n_stages < 2) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_token: staging area leaves fewer than 2 ring stages per warp");
+    const uint32_t smem = ((xs_bytes + 127u) & ~127u) + (uint32_t)n_stages * kTW * kStage + (uint32_t)n_stages * kTW * 8 + 64;
+
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(CC_ERR_CUDA, "cc_token: cannot raise the dynamic shared memory limit");
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTT, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_token: the kernel does not fit an SM with this shared-memory plan");
+    }
+    if (n_ctas > n_sms * per_sm) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_token: more CTAs than can be co-resident");
+
+    TokenPlan* plan = new TokenPlan();
+    plan->fn = fn; plan->n_ctas = n_ctas; plan->smem = smem; plan->n_layers = m->n_layers;
+    plan->bufs = lay.bufs; plan->scratch_bytes = lay.total;
+    cudaError_t e = cudaMalloc(&plan->d_ops, ops.size() * sizeof(TokOp));
+    if (e == cudaSuccess) e = cudaMalloc(&plan->d_attns, attns.size() * sizeof(TokAttn));
+    if (e == cudaSuccess) e = cudaMalloc(&plan->d_peers, kTokMaxWorld * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMemcpy(plan->d_ops, ops.data(), ops.size() * sizeof(TokOp), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(plan->d_attns, attns.data(), attns.size() * sizeof(TokAttn), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(plan->d_peers, m->scratch_peers, world * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { delete plan; return set_cuda_error(e, "cc_token_plan_create"); }
+    TokParams& p = plan->p;
+    memset(&p, 0, sizeof(p));
+    p.ops = plan->d_ops; p.attns = plan->d_attns; p.n_ops = (int)ops.size();
+    p.world = world; p.rank = m->rank; p.vocab = m->vocab;
+    p.scratch = reinterpret_cast<uint8_t*>(m->scratch_peers[m->rank]);
+    p.peers = plan->d_peers;
+    p.emb = (const __nv_bfloat16*)m->tok_embeddings; p.freqs = (const __nv_bfloat16*)m->freqs_cis;
+    p.dim = m->dim; p.n_q_rows = m->n_q_heads * D; p.n_kv_rows = m->n_kv_heads * D; p.head_dim = D;
+    p.xs_bytes = xs_bytes; p.n_stages = n_stages;
+    p.rec1_off = lay.rec1; p.rec2_off = lay.rec2;
+    *out_plan = plan;
+    return CC_OK;
+}
+
+int token_plan_destroy_impl(void* vp) {
+    TokenPlan* plan = static_cast<TokenPlan*>(vp);
+    if (!plan) return CC_OK;
+    cudaFree(plan->d_ops); cudaFree(plan->d_attns); cudaFree(plan->d_peers);
+    delete plan;
+    return CC_OK;
+}
+
+int decode_token_impl(void* vp, const int32_t* token_in, const int32_t* input_pos, int32_t* token_out, void* logits_out,
+                      void* probs_out, cudaStream_t stream) {
+    TokenPlan* plan = static_cast<TokenPlan*>(vp);
+    if (!plan || !input_pos) return set_error(CC_ERR_INVALID_ARG, "cc_decode_token: null plan or input_pos");
+    if (probs_out && !logits_out) return set_error(CC_ERR_INVALID_ARG, "cc_decode_token: probs_out needs logits_out");
+    TokParams p = plan->p;
+    p.token_in = token_in; p.input_pos = input_pos; p.token_out = token_out;
+    p.logits_out = (__nv_bfloat16*)logits_out; p.probs_out = (__nv_bfloat16*)probs_out;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan->n_ctas);
+    cfg.blockDim = dim3(kTT);
+    cfg.dynamicSmemBytes = plan->smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeCooperative;   // the stages spin on each other's output: every CTA must be resident
+    attr.val.cooperative = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, plan->fn, p);
+    if (e != cudaSuccess) return set_cuda_error(e, "cc_decode_token launch");
+    return CC_OK;
+}
+
+int token_buffer_impl(void* vp, int layer, int which, uint64_t* off, int32_t* words) {
+    TokenPlan* plan = static_cast<TokenPlan*>(vp);
+    if (!plan || layer < 0 || layer > plan->n_layers || which < 0 || which > 6) return set_error(CC_ERR_INVALID_ARG, "cc_token_buffer: bad argument");
+    const BufMap& b = plan->bufs[(size_t)layer * 7 + which];
+    if (!b.words) return set_error(CC_ERR_INVALID_ARG, "cc_token_buffer: no such buffer");
+    if (off) *off = b.off;
+    if (words) *words = b.words;
+    return CC_OK;
+}
+
+int token_set_trace_impl(void* vp, void* buf) {
+    TokenPlan* plan = static_cast<TokenPlan*>(vp);
+    if (!plan) return set_error(CC_ERR_INVALID_ARG, "cc_token_set_trace: null plan");
+    plan->p.trace = static_cast<unsigned long long*>(buf);
+    return CC_OK;
+}
+
+int token_info_impl(void* vp, int32_t* n_ctas, int32_t* n_ops, int32_t* ring_stages, int32_t* smem) {
+    TokenPlan* plan = static_cast<TokenPlan*>(vp);
+    if (!plan) return set_error(CC_ERR_INVALID_ARG, "cc_token_info: null plan");
+    if (n_ctas) *n_ctas = plan->n_ctas;
+    if (n_ops) *n_ops = plan->p.n_ops;
+    if (ring_stages) *ring_stages = plan->p.n_stages;
+    if (smem) *smem = (int32_t)plan->smem;
+    return CC_OK;
+}
+
+// cc_decode_step with CC_FLAG_VIA_TOKEN_KERNEL: one attention stage of the whole-token kernel on caller-supplied
+// q / k / v (tests: the stage is held to the same bit-exact bar as the per-layer kernel).  Synchronous.
+int decode_step_via_token_impl(const CcCacheState* st, const CcDecodeArgs* a, cudaStream_t stream) {
+    if (a->phases != CC_PHASE_ALL) return set_error(CC_ERR_INVALID_ARG, "the whole-token kernel runs the fused step only (phases = ALL)");
+    CcTokenLayer layer;
+    memset(&layer, 0, sizeof(layer));
+    layer.cache = *st;
+    layer.fill_idx = a->fill_idx;
+    layer.probs = a->probs;
+    CcTokenModel m;
+    memset(&m, 0, sizeof(m));
+    m.n_layers = 1; m.dim = 256; m.intermediate = 256; m.vocab = 2;
+    m.n_kv_heads = st->n_kv_heads; m.n_q_heads = st->n_kv_heads * st->q_per_kv; m.head_dim = st->head_dim;
+    m.layers = &layer; m.world = 1; m.rank = 0;
+    if (int rc = validate_model(&m)) return rc;
+    const uint64_t bytes = token_scratch_bytes_impl(&m);
+    if (!bytes) return CC_ERR_INVALID_ARG;
+    uint8_t* scratch = nullptr;
+    cudaError_t e = cudaMalloc(&scratch, bytes);
+    if (e != cudaSuccess) return set_cuda_error(e, "cc_decode_step (token kernel) scratch");
+    cudaMemsetAsync(scratch, 0, bytes, stream);
+    uint64_t peer = reinterpret_cast<uint64_t>(scratch);
+    m.scratch_peers = &peer; m.scratch_bytes = bytes;
+    void* plan = nullptr;
+    int rc = token_plan_create_impl(&m, &plan);
+    if (rc == CC_OK) {
+        TokenPlan* tp = static_cast<TokenPlan*>(plan);
+        const int D = st->head_dim, nq = m.n_q_heads * D, nkv = m.n_kv_heads * D;
+        uint64_t* qkv = reinterpret_cast<uint64_t*>(scratch + tp->bufs[0].off);
+        const TokHeader* hdr = reinterpret_cast<const TokHeader*>(scratch);
+        tok_pack_kernel<<<8, 256, 0, stream>>>((const uint32_t*)a->q, qkv, nq / 2, hdr);
+        tok_pack_kernel<<<4, 256, 0, stream>>>((const uint32_t*)a->k_new, qkv + nq / 2, nkv / 2, hdr);
+        tok_pack_kernel<<<4, 256, 0, stream>>>((const uint32_t*)a->v_new, qkv + (nq + nkv) / 2, nkv / 2, hdr);
+        rc = decode_token_impl(plan, nullptr, a->input_pos, nullptr, nullptr, nullptr, stream);
+        if (rc == CC_OK) {
+            tok_unpack_kernel<<<8, 256, 0, stream>>>(reinterpret_cast<const uint64_t*>(scratch + tp->bufs[1].off), (uint32_t*)a->y, nq / 2);
+            e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) rc = set_cuda_error(e, "cc_decode_step (token kernel)");
+        }
+        token_plan_destroy_impl(plan);
+    }
+    cudaFree(scratch);
+    return rc;
+}
+
+}  // namespace cc

@@ -26,4 +26,14 @@ int gemv_residual_impl(const void* x, const void* norm_w, float eps, const void*
                        int K, int N, const CcTpArgs* tp, cudaStream_t stream);
 int rmsnorm_ffn_gate_impl(const void* x, const void* norm_w, float eps, const void* w1, const void* w3, void* out,
                           int K, int N, const CcTpArgs* tp, cudaStream_t stream);
+// whole-token persistent kernel (decode_token.cu)
+unsigned long long token_scratch_bytes_impl(const CcTokenModel* m);
+int token_plan_create_impl(const CcTokenModel* m, void** plan);
+int token_plan_destroy_impl(void* plan);
+int decode_token_impl(void* plan, const int32_t* token_in, const int32_t* input_pos, int32_t* token_out, void* logits_out,
+                      void* probs_out, cudaStream_t stream);
+int token_buffer_impl(void* plan, int layer, int which, uint64_t* off, int32_t* words);
+int token_set_trace_impl(void* plan, void* buf);
+int token_info_impl(void* plan, int32_t* n_ctas, int32_t* n_ops, int32_t* ring_stages, int32_t* smem);
+int decode_step_via_token_impl(const CcCacheState* st, const CcDecodeArgs* a, cudaStream_t stream);
 }  // namespace cc

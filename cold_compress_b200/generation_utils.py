@@ -103,6 +103,10 @@ def prefill(model: Transformer, x: torch.Tensor, input_pos: torch.Tensor, next_t
 
 def decode_one_token(model: Transformer, x: torch.Tensor, input_pos: torch.Tensor, next_token: torch.Tensor = None,
                      attn_top_k: float = 1, **sampling_kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
+    fused = model.decode_token_fused(x, input_pos) if attn_top_k in (None, 1, 1.0) and hasattr(model, "decode_token_fused") else None
+    if fused is not None:   # ONE kernel: the whole layer stack, the head, arg-max and softmax (csrc/decode_token.cu)
+        tok, probs = fused
+        return (tok if next_token is None else next_token), probs
     logits = model(x, input_pos, is_prefill=False, attn_top_k=attn_top_k)
     return greedy(logits, next_token=next_token)
 
@@ -128,10 +132,7 @@ class GraphedDecoder:
         with torch.cuda.stream(stream):
             # capture only records: the cache state is untouched until the first replay
             with torch.cuda.graph(self.graph, stream=stream):
-                logits = model(self.x, self.pos, is_prefill=False, attn_top_k=attn_top_k)
-                probs = torch.nn.functional.softmax(logits[0, -1], dim=-1)
-                self.tok = torch.argmax(probs, keepdim=True).to(dtype=torch.int)
-                self.probs = probs
+                self.tok, self.probs = decode_one_token(model, self.x, self.pos, attn_top_k=attn_top_k)
         torch.cuda.current_stream().wait_stream(stream)
 
     def __call__(self, model, x, input_pos, next_token=None, attn_top_k=1, **kw):

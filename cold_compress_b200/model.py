@@ -13,6 +13,7 @@ probability-consuming caches goes through `prefill_attention_stats` instead of a
 from __future__ import annotations
 
 import math
+import os
 from collections import defaultdict
 from dataclasses import dataclass
 from typing import Any, Dict, Optional
@@ -113,6 +114,11 @@ class Transformer(nn.Module):
         self.fused_decode = True
         self._bufs = None
         self.tp_link = None  # tp.enable_fused_exchange: all-reduces fused into the projection kernels
+        # decode a token as ONE persistent kernel (csrc/decode_token.cu) when the cache policies allow it;
+        # False = the 5-launches-per-layer path above (also the fallback for hybrid / quantised / debug caches)
+        self.token_kernel = os.environ.get("CC_TOKEN_KERNEL", "1") != "0"
+        self._tplan = None
+        self._tplan_why = None
 
     def setup_caches(self, **kwargs):
         """Per layer: cache + prompt compressor from the strategy names (reference model.py:191-233)."""
@@ -173,12 +179,53 @@ class Transformer(nn.Module):
                           "gate": mk(ffn.w1.out_features), "logits": mk(self.output.out_features)}
         return self._bufs
 
+    # ---- one token = one kernel ----------------------------------------------------------------
+    def token_plan(self):
+        """The whole-token kernel's plan for the current weights + caches, or None when some cache needs the
+        per-layer kernel (the reason is kept in `_tplan_why`).  Under tensor parallelism building the plan is a
+        collective (symmetric-memory rendezvous): every rank gets here in the same decode call."""
+        if not (self.token_kernel and self.fused_decode):
+            return None
+        from .token_kernel import TokenPlan, unsupported_reason
+        sig = TokenPlan.signature_of(self)
+        if self._tplan is not None and self._tplan.signature == sig:
+            return self._tplan
+        if self._tplan is None and self._tplan_why == sig:
+            return None
+        self._tplan = None
+        why = unsupported_reason(self)
+        if why is None and self.layers[0].attention.tp_group is not None and os.environ.get("CC_TP_NCCL") == "1":
+            why = "CC_TP_NCCL=1 selects NCCL all-reduces between the per-layer kernels"
+        if why is not None:
+            self._tplan_why = sig
+            self.token_kernel_reason = why
+            return None
+        self._tplan = TokenPlan(self)
+        return self._tplan
+
+    def decode_token_fused(self, idx: Tensor, input_pos: Tensor):
+        """(token int32 [1], probs bf16 [vocab]) of one greedy decode step through the whole-token kernel, or None
+        when that kernel cannot serve this model (reference generation_utils.py:163-178 + 136-142)."""
+        if idx.numel() != 1 or not idx.is_cuda:
+            return None
+        plan = self.token_plan()
+        if plan is None:
+            return None
+        tok = idx.view(-1) if idx.dtype == torch.int32 else idx.view(-1).int()
+        ip = input_pos if input_pos.dtype == torch.int32 else input_pos.int()
+        token, probs, _ = plan.decode(tok, ip)
+        return token, probs
+
     def _decode_fused(self, idx: Tensor, input_pos: Tensor) -> Tensor:
         """embedding -> per layer [norm+wqkv+RoPE | cache step | wo+residual | norm+gate | w2+residual] -> head.
         Same bf16 rounding points as the tensor-op path; every kernel takes `input_pos` from device
         memory, so the whole step is capturable in one CUDA graph."""
-        b = self._decode_buffers(idx.device)
         ip = input_pos if input_pos.dtype == torch.int32 else input_pos.int()
+        plan = self.token_plan()
+        if plan is not None:
+            _, _, logits = plan.decode(idx.view(-1) if idx.dtype == torch.int32 else idx.view(-1).int(), ip)
+            return logits.view(1, 1, -1)
+        b = self._decode_buffers(idx.device)
         eps = self.norm.eps
         b["x"].copy_(self.tok_embeddings(idx).view(-1))
         x, h = b["x"], b["h"]
@@ -258,6 +305,8 @@ class Transformer(nn.Module):
 
     def kernels_per_token(self) -> int:
         """Launches of this repo's kernels in one fused decode step (bench.py: gpu_launches)."""
+        if self._tplan is not None:
+            return 1
         return 5 * len(self.layers) + 1
 
     def forward(self, idx: Tensor, input_pos: Tensor, is_prefill, mask: Optional[Tensor] = None,

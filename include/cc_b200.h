@@ -61,6 +61,10 @@ extern "C" {
                                           start early (programmatic dependent launch) and fetch K/V and
                                           policy state while that kernel is still running               */
 
+#define CC_FLAG_VIA_TOKEN_KERNEL     2  /* tests: run this step through the attention stage of the whole-token
+                                          kernel (cc_decode_token) instead of the per-layer kernel: same results,
+                                          synchronous, not capturable                                            */
+
 /* ---- hybrid per-head strategy bits (cache.py:896-950 substrings of the name) */
 #define CC_HYB_FULL          1
 #define CC_HYB_WINDOW        2
@@ -281,6 +285,70 @@ int cc_gemv_residual(const void* x, const void* norm_w, float eps, const void* w
                      void* out, int32_t K, int32_t N, const CcTpArgs* tp, void* stream);
 int cc_rmsnorm_ffn_gate(const void* x, const void* norm_w, float eps, const void* w1, const void* w3,
                         void* out, int32_t K, int32_t N, const CcTpArgs* tp, void* stream);
+
+/*
+ * One decoded token as ONE persistent kernel (generation_utils.py:163-178 decode_one_token = Transformer.forward
+ * model.py:268-292 with is_prefill=False, followed by greedy sampling generation_utils.py:136-142):
+ * embedding row -> per layer [attention_norm + wqkv (+bias) + RoPE | eviction + overwrite + attention + pooling +
+ * score update (the cc_decode_step stage) | wo + residual | ffn_norm + silu(w1 x) * w3 x | w2 + residual] -> norm ->
+ * output head -> arg-max token (+ softmax probabilities).  One CTA per SM stays resident for the whole token; every
+ * warp streams its share of the weight rows (and of the K/V rows) through a private TMA-fed shared-memory ring that
+ * runs ahead across stage boundaries, and the stages hand vectors to each other through flag-in-data words
+ * (u64 = {payload, token tag}) in `scratch`, so there is no grid barrier and no kernel boundary inside a token.
+ * With world > 1 (tp.py head / column sharding) the row-parallel wo / w2 stages store their partial vectors into
+ * every rank's scratch over NVLink and the consumer stage sums them: the all-reduces of tp.py:134-160 are part of
+ * the same kernel.  Policies: recent_global, l2, heavy_hitter (full history); other caches use cc_decode_step.
+ */
+typedef struct CcTokenLayer {
+    const void* attention_norm;   /* bf16 [dim]                          model.py:310-313 */
+    const void* wqkv;             /* bf16 [(Hq + 2 Hkv) * D, dim]        model.py:339     */
+    const void* bqkv;             /* bf16 [(Hq + 2 Hkv) * D] or NULL     (Qwen2)          */
+    const void* wo;               /* bf16 [dim, Hq * D]                  model.py:340     */
+    const void* ffn_norm;         /* bf16 [dim]                                          */
+    const void* w1;               /* bf16 [intermediate, dim]            model.py:438-440 */
+    const void* w3;               /* bf16 [intermediate, dim]                             */
+    const void* w2;               /* bf16 [dim, intermediate]                             */
+    float attention_norm_eps, ffn_norm_eps;
+    CcCacheState cache;           /* this layer's KV cache                                */
+    int64_t* fill_idx;            /* optional out i64 [Hkv]: the eviction trace           */
+    void*    probs;               /* optional out bf16 [Hkv, L]: GQA-pooled probabilities */
+} CcTokenLayer;
+
+typedef struct CcTokenModel {
+    int32_t n_layers;
+    int32_t dim;                  /* model width (never sharded)                          */
+    int32_t n_q_heads, n_kv_heads;/* LOCAL heads of this rank (tp.py:163-168)             */
+    int32_t head_dim;
+    int32_t intermediate;         /* LOCAL rows of w1 / w3                                */
+    int32_t vocab;                /* rows of `output`                                     */
+    float   norm_eps;
+    const CcTokenLayer* layers;   /* HOST array [n_layers]                                */
+    const void* tok_embeddings;   /* bf16 [vocab, dim]                                    */
+    const void* norm;             /* bf16 [dim]                                           */
+    const void* output;           /* bf16 [vocab, dim]                                    */
+    const void* freqs_cis;        /* bf16 [max_pos, D/2, 2]                               */
+    int32_t world, rank;          /* tensor-parallel ranks (1, 0 without)                 */
+    const uint64_t* scratch_peers;/* HOST array [world]: device address of every rank's scratch (peer-mapped);
+                                     entry [rank] is the local one                         */
+    uint64_t scratch_bytes;       /* size of each scratch, >= cc_token_scratch_bytes()    */
+} CcTokenModel;
+
+/* Bytes of zero-initialised device scratch a plan for this model needs (exchange words + tags). */
+uint64_t cc_token_scratch_bytes(const CcTokenModel* model);
+/* Builds the stage program for the model on the current device; *plan is an opaque handle. */
+int cc_token_plan_create(const CcTokenModel* model, void** plan);
+int cc_token_plan_destroy(void* plan);
+/* One decoded token.  token_in / input_pos: device i32 [1].  token_out: device i32 [1] (arg-max of the logits, first
+ * index on ties).  logits_out: bf16 [vocab] or NULL.  probs_out: bf16 [vocab] softmax(logits) or NULL. */
+int cc_decode_token(void* plan, const int32_t* token_in, const int32_t* input_pos, int32_t* token_out,
+                    void* logits_out, void* probs_out, void* stream);
+/* Tests / diagnostics: where a stage's output vector lives inside the scratch.  which: 0 q|k|v, 1 y, 2 wo partials
+ * [world][dim], 3 h, 4 gate, 5 w2 partials [world][dim], 6 layer input x (layer >= 1; layer == n_layers: head input).
+ * Words are u64 = {bf16 x 2 | tag << 32}. */
+int cc_token_buffer(void* plan, int32_t layer, int32_t which, uint64_t* offset_bytes, int32_t* n_words);
+/* Diagnostics: device buffer u64 [n_stages][n_ctas][2] of %globaltimer stamps (stage entered, input staged). */
+int cc_token_set_trace(void* plan, void* device_buffer);
+int cc_token_info(void* plan, int32_t* n_ctas, int32_t* n_stages_program, int32_t* ring_stages, int32_t* smem_bytes);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,7 @@ NON_HYBRID = [n for n in ALL_FIXTURES if not n.startswith("hybrid")]
 HYBRID = [n for n in ALL_FIXTURES if n.startswith("hybrid")]
 
 
-def _run_trace(name):
+def _run_trace(name, **step_kwargs):
     from device_utils import device_cache_from_golden, oracle_from_golden
     g = Golden(name)
     cache = device_cache_from_golden(g)
@@ -35,7 +35,7 @@ def _run_trace(name):
         k = s["k_new"].view(1, g.Hkv, 1, g.D).to(dev)
         v = s["v_new"].view(1, g.Hkv, 1, g.D).to(dev)
         ip.fill_(s["input_pos"])
-        y = cache.decode_step(q, k, v, ip, is_punc=s["is_punc"])
+        y = cache.decode_step(q, k, v, ip, is_punc=s["is_punc"], **step_kwargs)
         y = y[0, :, 0].cpu()
         yo, idx_o, probs_o = oc.decode_step(s["q"], s["k_new"], s["v_new"], s["input_pos"],
                                             fill_idx=s["fill_idx"] if g.policy == "external" else None,
@@ -105,6 +105,10 @@ SHAPES = [
 
 @pytest.mark.parametrize("strategy,Hkv,G,D,L,n_filled,steps", SHAPES)
 def test_decode_matches_oracle_on_seeded_state(strategy, Hkv, G, D, L, n_filled, steps):
+    _seeded_state_run(strategy, Hkv, G, D, L, n_filled, steps)
+
+
+def _seeded_state_run(strategy, Hkv, G, D, L, n_filled, steps, **step_kwargs):
     from device_utils import make_device_cache, oracle_like, synthetic_fill
     strategy, _, opt = strategy.partition(":")
     extra = dict(W=int(opt.strip("wt")), thresholding=opt.endswith("t")) if opt else {}
@@ -123,7 +127,7 @@ def test_decode_matches_oracle_on_seeded_state(strategy, Hkv, G, D, L, n_filled,
         ip.fill_(pos)
         fi = cache._external_fill_idx(ip).cpu() if cache.policy == 0 else None
         y = cache.decode_step(q.view(1, Hkv * G, 1, D).cuda(), k.view(1, Hkv, 1, D).cuda(),
-                              v.view(1, Hkv, 1, D).cuda(), ip)[0, :, 0].cpu()
+                              v.view(1, Hkv, 1, D).cuda(), ip, **step_kwargs)[0, :, 0].cpu()
         yo, idx_o, probs_o = oc.decode_step(q, k, v, pos, fill_idx=fi)
         if cache.policy != 0:
             assert torch.equal(cache._fill_idx.cpu(), idx_o), f"eviction index differs at step {t}"
