@@ -302,7 +302,8 @@ def run_ours(args):
         out["step_stream"] = {"bytes_per_token_per_gpu": wbytes + kvbytes, "achieved_gbs": round((wbytes + kvbytes) / (dev_s / args.steps) / 1e9, 1),
                               "frac_of_hbm_peak": round((wbytes + kvbytes) / (dev_s / args.steps) / 1e9 / peak, 4)}
         out["cpu_baseline"] = (cpu_reference(sample_seconds=20.0, warmup=1)
-                               if world == 1 and not os.environ.get("CC_BENCH_NCU") and not os.environ.get("CC_TP_FAKE") else None)
+                               if world == 1 and not os.environ.get("CC_BENCH_NCU") and not os.environ.get("CC_TP_FAKE")
+                               and not os.environ.get("CC_BENCH_NOCPU") else None)
         print(json.dumps(out), flush=True)
     if world > 1:
         # leave without tearing NCCL down: communicators captured in CUDA graphs make

@@ -13,7 +13,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 SO = PKG / "libcc_b200.so"
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+NVCC_FLAGS = [*(["-DCC_TOKEN_MICROTRACE"] if __import__("os").environ.get("CC_TOKEN_MICROTRACE") else []), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 

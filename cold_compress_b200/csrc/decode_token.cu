@@ -38,9 +38,13 @@
 
 namespace cc {
 
-constexpr int kTW = 8;                 // warps per CTA
+#ifndef CC_TOKEN_WARPS
+#define CC_TOKEN_WARPS 8
+#endif
+constexpr int kTW = CC_TOKEN_WARPS;    // warps per CTA (8 or 16)
 constexpr int kTT = kTW * 32;          // threads per CTA
-constexpr uint32_t kStage = 8192;      // bytes per ring stage
+constexpr uint32_t kStage = 65536 / kTW;   // bytes per ring stage: 8 KiB (8 warps) / 4 KiB (16 warps)
+constexpr int kRedWarps = kTW < 8 ? kTW : 8;   // P.V partials are reduced through 8 shared-memory slots
 constexpr int kTokMaxWorld = 8;
 constexpr int kTokMaxG = 8;
 constexpr int kOutStage = 64;          // row pairs a CTA can stage for a coalesced peer push
@@ -107,35 +111,108 @@ struct TokParams {
 // scratch header
 struct TokHeader { uint32_t gen; uint32_t done; };
 
+// diagnostics: trace[(stage * n_ctas + cta) * kTraceSlots + slot] = %globaltimer
+constexpr int kTraceSlots = 12;
+__device__ __forceinline__ void tstamp(const TokParams& P, int oi, int slot) {
+    if (P.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.trace[((size_t)oi * gridDim.x + blockIdx.x) * kTraceSlots + slot] = t;
+    }
+}
+
+// The stage descriptors live in global memory; a cold read costs an L2 round trip (~0.5 us) and the tile cursors
+// and the stages themselves read a dozen fields at every stage boundary.  A window of the next kOpWin stages is
+// kept in shared memory: filled at kernel start, advanced by one entry at every stage entry.
+constexpr int kOpWin = 16, kAttWin = 4;
+struct DescWindow {
+    TokOp op[kOpWin];
+    TokAttn att[kAttWin];
+    volatile int op_hi;    // stages < op_hi are in the window (slot = index % kOpWin)
+    volatile int att_hi;   // attention records < att_hi are in the window (slot = index % kAttWin)
+};
+__device__ __forceinline__ const TokOp* op_at(const TokParams& P, const DescWindow* W, int oi) {
+    if (oi < W->op_hi) { __threadfence_block(); return &W->op[oi % kOpWin]; }
+    return P.ops + oi;
+}
+__device__ __forceinline__ const TokAttn* att_at(const TokParams& P, const DescWindow* W, int ai) {
+    if (ai < W->att_hi) { __threadfence_block(); return &W->att[ai % kAttWin]; }
+    return P.attns + ai;
+}
+// 16-byte chunk `c` of stage descriptor `oi` (and of its attention record) -> window; called by one warp
+__device__ __forceinline__ void window_load(const TokParams& P, DescWindow* W, int oi, int lane, uint4* keep, int* keep_att) {
+    // phase 1 (issue): returns the chunk in registers so that the caller can overlap the latency with a wait
+    *keep_att = -1;
+    if (oi >= P.n_ops) return;
+    constexpr int nop = (int)(sizeof(TokOp) / 16), natt = (int)(sizeof(TokAttn) / 16);
+    static_assert(sizeof(TokOp) % 16 == 0 && sizeof(TokAttn) % 16 == 0 && nop <= 32 && natt <= 32, "descriptor sizes");
+    const TokOp* o = P.ops + oi;
+    if (lane < nop) keep[0] = __ldg(reinterpret_cast<const uint4*>(o) + lane);
+    if (o->type == TOK_ATTN) {
+        *keep_att = o->attn;
+        if (lane < natt) keep[1] = __ldg(reinterpret_cast<const uint4*>(P.attns + o->attn) + lane);
+    }
+}
+__device__ __forceinline__ void window_store(const TokParams& P, DescWindow* W, int oi, int lane, const uint4* keep, int keep_att) {
+    if (oi >= P.n_ops) return;
+    constexpr int nop = (int)(sizeof(TokOp) / 16), natt = (int)(sizeof(TokAttn) / 16);
+    if (lane < nop) reinterpret_cast<uint4*>(&W->op[oi % kOpWin])[lane] = keep[0];
+    if (keep_att >= 0 && lane < natt) reinterpret_cast<uint4*>(&W->att[keep_att % kAttWin])[lane] = keep[1];
+    __syncwarp();
+    __threadfence_block();
+    if (lane == 0) {
+        if (keep_att >= 0) W->att_hi = keep_att + 1;
+        W->op_hi = oi + 1;
+    }
+}
+
 // ------------------------------------------------------------------ flag-in-data words
+// u64 = {payload (low half), token tag (high half)}; naturally aligned 8-byte accesses are single-copy atomic, so a
+// word whose tag is current carries valid data.  Words written by a peer GPU are accessed at system scope, words
+// that only this GPU writes at gpu scope (both are served by L2; no L1).
 __device__ __forceinline__ void ll_store(uint64_t* p, uint32_t data, uint32_t tag) {
     const uint64_t v = ((uint64_t)tag << 32) | data;
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ uint64_t ll_load(const uint64_t* p) {
+__device__ __forceinline__ uint64_t ll_load(const uint64_t* p, bool sys = false) {
     uint64_t v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    if (sys) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    else asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void ll_load2(const uint64_t* p, uint64_t& a, uint64_t& b) {
-    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+__device__ __forceinline__ void ll_load2(const uint64_t* p, uint64_t& a, uint64_t& b, bool sys = false) {
+    if (sys) asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    else asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
-__device__ __forceinline__ uint32_t ll_wait(const uint64_t* p, uint32_t tag) {
+__device__ __forceinline__ uint32_t ll_wait(const uint64_t* p, uint32_t tag, bool sys = false) {
     uint64_t v;
-    do { v = ll_load(p); } while ((uint32_t)(v >> 32) != tag);
+    do { v = ll_load(p, sys); } while ((uint32_t)(v >> 32) != tag);
     return (uint32_t)v;
 }
-// four consecutive words (p 16-byte aligned) = 8 bf16 values
-__device__ __forceinline__ uint4 ll_wait4(const uint64_t* p, uint32_t tag) {
-    uint64_t a, b, c, d;
+// N groups of four consecutive words (each p[i] 16-byte aligned) = N x 8 bf16 values.  All 2N loads of a round are
+// issued before any tag is looked at: one memory round trip when the data is there.
+template <int N>
+__device__ __forceinline__ void ll_wait4_n(const uint64_t* const (&p)[N], int n, uint32_t tag, uint4 (&o)[N], bool sys = false) {
+    uint64_t v[4 * N];
     while (true) {
-        ll_load2(p, a, b);
-        ll_load2(p + 2, c, d);
-        const uint32_t bad = ((uint32_t)(a >> 32) ^ tag) | ((uint32_t)(b >> 32) ^ tag) | ((uint32_t)(c >> 32) ^ tag) |
-                             ((uint32_t)(d >> 32) ^ tag);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (i < n) {
+                ll_load2(p[i], v[4 * i], v[4 * i + 1], sys);
+                ll_load2(p[i] + 2, v[4 * i + 2], v[4 * i + 3], sys);
+            }
+        uint32_t bad = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (i < n) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bad |= (uint32_t)(v[4 * i + j] >> 32) ^ tag;
+            }
         if (!bad) break;
     }
-    return make_uint4((uint32_t)a, (uint32_t)b, (uint32_t)c, (uint32_t)d);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        o[i] = make_uint4((uint32_t)v[4 * i], (uint32_t)v[4 * i + 1], (uint32_t)v[4 * i + 2], (uint32_t)v[4 * i + 3]);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -184,12 +261,19 @@ __device__ __forceinline__ void attn_warp_rows(const TokAttn& A, int rank, int j
 }
 
 // ------------------------------------------------------------------ per-warp tile sequence (the fetch cursor)
+// Advancing inside a stage is a handful of adds (the cursor sits in lane 0's serial section of every ring release);
+// only entering a new stage computes the dealing.
 struct TileIter {
-    int op;         // current stage index (>= n_ops: exhausted)
-    int j, nj;      // matrix-vector: local group index / count; attention: tile index / 2 * nlc
-    int s, ns;      // segment index / count
-    int type, K, seg_len, g0, rank, h;
-    const TokOp* o;
+    int op;                 // current stage index (>= n_ops: exhausted)
+    int type;
+    int j, nj;              // matrix-vector: local group index / count; attention: tile index / 2 * nlc
+    int s, ns;              // segment index / count
+    const uint8_t* src;     // matrix-vector: first row segment of the current tile
+    uint32_t seg_bytes, last_bytes;   // bytes of a full / of the last segment of a row
+    uint32_t row_bytes;     // K * 2
+    long long group_step;   // from the last segment of a group to the first segment of the warp's next group
+    long long w3_delta;     // FFN gate: w3 - w1
+    int rank, h;            // attention
     const TokAttn* a;
 };
 
@@ -201,13 +285,12 @@ __device__ __forceinline__ bool iter_tile_valid(const TileIter& it, int warp) {
     return nv > 0;
 }
 // position the cursor on the first tile of stage it.op or of the first later stage in which this warp has work
-__device__ __forceinline__ void iter_enter(TileIter& it, const TokParams& P, int warp) {
+__device__ __forceinline__ void iter_enter(TileIter& it, const TokParams& P, const DescWindow* W, int warp) {
     for (; it.op < P.n_ops; ++it.op) {
-        const TokOp* o = P.ops + it.op;
-        it.o = o;
+        const TokOp* o = op_at(P, W, it.op);
         it.type = o->type;
         if (o->type == TOK_ATTN) {
-            const TokAttn* a = P.attns + o->attn;
+            const TokAttn* a = att_at(P, W, o->attn);
             const AttnDeal d = deal_attn(*a);
             if (d.nlc == 0) continue;
             it.a = a; it.rank = d.rank; it.h = d.h;
@@ -218,26 +301,35 @@ __device__ __forceinline__ void iter_enter(TileIter& it, const TokParams& P, int
             int g0, n;
             deal_groups(o->n_groups, o->rot, &g0, &n);
             if (warp >= n) continue;
-            it.g0 = g0; it.nj = n; it.j = warp; it.s = 0; it.ns = o->n_seg; it.K = o->K; it.seg_len = o->seg_len;
+            const int K = o->K;
+            it.nj = n; it.j = warp; it.s = 0; it.ns = o->n_seg;
+            it.row_bytes = (uint32_t)K * 2;
+            it.seg_bytes = (uint32_t)o->seg_len * 2;
+            it.last_bytes = (uint32_t)(K - (o->n_seg - 1) * o->seg_len) * 2;
+            it.src = reinterpret_cast<const uint8_t*>(o->w) + (size_t)(2 * (g0 + warp)) * it.row_bytes;
+            it.group_step = (long long)(2 * kTW) * it.row_bytes - (long long)(o->n_seg - 1) * it.seg_bytes;
+            it.w3_delta = o->type == TOK_GATE ? reinterpret_cast<const uint8_t*>(o->w3) - reinterpret_cast<const uint8_t*>(o->w) : 0;
             return;
         }
     }
 }
-__device__ __forceinline__ void iter_advance(TileIter& it, const TokParams& P, int warp) {
-    if (it.type == TOK_ATTN) {
-        for (++it.j; it.j < it.nj && !iter_tile_valid(it, warp); ++it.j) {}
-        if (it.j < it.nj) return;
-    } else {
-        if (++it.s < it.ns) return;
+__device__ __forceinline__ void iter_advance(TileIter& it, const TokParams& P, const DescWindow* W, int warp) {
+    if (it.type != TOK_ATTN) {
+        if (++it.s < it.ns) { it.src += it.seg_bytes; return; }
         it.s = 0;
         it.j += kTW;
+        if (it.j < it.nj) { it.src += it.group_step; return; }
+    } else {
+        for (++it.j; it.j < it.nj && !iter_tile_valid(it, warp); ++it.j) {}
         if (it.j < it.nj) return;
     }
     ++it.op;
-    iter_enter(it, P, warp);
+    iter_enter(it, P, W, warp);
 }
-// issue the TMA copies of the cursor's tile into a ring stage (one lane)
-__device__ __forceinline__ void iter_issue(const TileIter& it, int warp, uint8_t* stage, uint64_t* bar) {
+// issue the TMA copies of the cursor's tile into a ring stage (one lane).  Weights and cache rows are read once
+// per token: lowest L2 retention priority, so that the 15 GB stream does not evict the exchange words and the
+// kernel's own instructions.
+__device__ __forceinline__ void iter_issue(const TileIter& it, int warp, uint8_t* stage, uint64_t* bar, uint64_t pol) {
     if (it.type == TOK_ATTN) {
         const TokAttn& A = *it.a;
         const int nlc = it.nj >> 1;
@@ -248,25 +340,20 @@ __device__ __forceinline__ void iter_issue(const TileIter& it, int warp, uint8_t
         const uint8_t* base = reinterpret_cast<const uint8_t*>(is_v ? A.st.v_cache : A.st.k_cache);
         const uint32_t bytes = (uint32_t)nv * row_bytes;
         mbar_expect_tx(bar, bytes);
-        tma_load_1d(stage, base + ((size_t)it.h * A.st.max_cache_length + first) * row_bytes, bytes, bar);
+        tma_load_1d_hint(stage, base + ((size_t)it.h * A.st.max_cache_length + first) * row_bytes, bytes, bar, pol);
         return;
     }
-    const int off = it.s * it.seg_len;
-    const int len = min(it.seg_len, it.K - off);
-    const uint32_t bytes = (uint32_t)len * 2;
-    const size_t r0 = 2 * (size_t)(it.g0 + it.j);
-    const __nv_bfloat16* w = it.o->w;
+    const uint32_t bytes = it.s + 1 == it.ns ? it.last_bytes : it.seg_bytes;
     if (it.type == TOK_GATE) {
-        const __nv_bfloat16* w3 = it.o->w3;
         mbar_expect_tx(bar, 4 * bytes);
-        tma_load_1d(stage, w + r0 * it.K + off, bytes, bar);
-        tma_load_1d(stage + bytes, w + (r0 + 1) * it.K + off, bytes, bar);
-        tma_load_1d(stage + 2 * bytes, w3 + r0 * it.K + off, bytes, bar);
-        tma_load_1d(stage + 3 * bytes, w3 + (r0 + 1) * it.K + off, bytes, bar);
+        tma_load_1d_hint(stage, it.src, bytes, bar, pol);
+        tma_load_1d_hint(stage + bytes, it.src + it.row_bytes, bytes, bar, pol);
+        tma_load_1d_hint(stage + 2 * bytes, it.src + it.w3_delta, bytes, bar, pol);
+        tma_load_1d_hint(stage + 3 * bytes, it.src + it.w3_delta + it.row_bytes, bytes, bar, pol);
     } else {
         mbar_expect_tx(bar, 2 * bytes);
-        tma_load_1d(stage, w + r0 * it.K + off, bytes, bar);
-        tma_load_1d(stage + bytes, w + (r0 + 1) * it.K + off, bytes, bar);
+        tma_load_1d_hint(stage, it.src, bytes, bar, pol);
+        tma_load_1d_hint(stage + bytes, it.src + it.row_bytes, bytes, bar, pol);
     }
 }
 
@@ -276,6 +363,8 @@ struct Ring {
     uint64_t* bars;       // this warp's mbarriers
     int ns, cs;           // number of stages, stage the consumer reads next
     uint32_t phases;      // parity of the next completion of each stage's barrier
+    const DescWindow* win;
+    uint64_t policy;      // L2 eviction priority of the streamed tiles (created once)
     TileIter it;          // fetch cursor; only lane 0's copy is meaningful
 };
 __device__ __forceinline__ const uint8_t* ring_wait(Ring& r) {
@@ -285,10 +374,11 @@ __device__ __forceinline__ const uint8_t* ring_wait(Ring& r) {
 // the warp is done with the current stage: re-arm it with the next tile of the warp's sequence
 __device__ __forceinline__ void ring_release(Ring& r, const TokParams& P, int warp, int lane) {
     __syncwarp();
+    // (no proxy fence: the stage was only READ through the generic proxy; the warp barrier above orders those
+    // reads before the copy that overwrites it, as in any TMA producer / consumer ring)
     if (lane == 0 && r.it.op < P.n_ops) {
-        fence_proxy_async();
-        iter_issue(r.it, warp, r.stages + (size_t)r.cs * kStage, &r.bars[r.cs]);
-        iter_advance(r.it, P, warp);
+        iter_issue(r.it, warp, r.stages + (size_t)r.cs * kStage, &r.bars[r.cs], r.policy);
+        iter_advance(r.it, P, r.win, warp);
     }
     r.phases ^= 1u << r.cs;
     r.cs = r.cs + 1 == r.ns ? 0 : r.cs + 1;
@@ -306,45 +396,123 @@ __device__ void stage_input(const TokParams& P, const TokOp& op, __nv_bfloat16* 
         for (int i = tid * 8; i < K; i += kTT * 8)
             *reinterpret_cast<uint4*>(xs + i) = __ldg(reinterpret_cast<const uint4*>(src + i));
     } else {
-        const int nw = K >> 1;
+        const int nw = K >> 1, W = op.in_world;
+        const bool sys = W > 1;   // partial vectors written by peer GPUs
         const uint64_t* in = reinterpret_cast<const uint64_t*>(P.scratch + op.in_off);
-        // cheap gate: one warp samples 32 words per source with a back-off, so that a CTA that arrives early does
-        // not hammer L2 with 256 spinning threads while the weight stream needs the bandwidth
+        // Gate: one warp samples 32 words per source (with a back-off) before the CTA reads the whole vector, so a
+        // CTA that is early does not hammer L2 with 256 spinning threads while the weight stream needs the bandwidth.
         if (warp == 0) {
-            for (int s = 0; s < op.in_world; ++s) {
-                const uint64_t* p = in + (size_t)s * nw + (size_t)lane * (nw >> 5);
-                while ((uint32_t)(ll_load(p) >> 32) != tag) __nanosleep(64);
+            for (int sidx = 0; sidx < W; ++sidx) {
+                const uint64_t* p = in + (size_t)sidx * nw + (size_t)lane * (nw >> 5);
+                while ((uint32_t)(ll_load(p, sys) >> 32) != tag) __nanosleep(32);
             }
         }
         __syncthreads();
         const uint64_t* res = op.res_kind == RES_LL ? reinterpret_cast<const uint64_t*>(P.scratch + op.res_off) : nullptr;
         const __nv_bfloat16* rest = op.res_kind == RES_TOKEN ? P.emb + (size_t)token * K : nullptr;
         uint64_t* sum_out = op.publish_cta == (int)blockIdx.x ? reinterpret_cast<uint64_t*>(P.scratch + op.sum_off) : nullptr;
-        for (int i = tid * 8; i < K; i += kTT * 8) {
-            uint4 o = ll_wait4(in + (i >> 1), tag);
-            if (op.in_world > 1 || op.res_kind != RES_NONE) {
-                float acc[8], f[8];
-                unpack8(o, acc);
-                for (int s = 1; s < op.in_world; ++s) {   // rank order: the same bits on every rank
-                    unpack8(ll_wait4(in + (size_t)s * nw + (i >> 1), tag), f);
+        // x = [residual +] bf16(sum): h = x + attention(...) / out = h + feed_forward(...) are bf16 + bf16 -> bf16
+        // (model.py:317, 326)
+        auto finish = [&](int i, float (&acc)[8], const uint4* resv, bool summed) {
+            if (op.res_kind != RES_NONE) {
+                float f[8];
+                unpack8(resv ? *resv : __ldg(reinterpret_cast<const uint4*>(rest + i)), f);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] += f[j];
-                }
-                if (op.res_kind != RES_NONE) {
-                    // h = x + attention(...) / out = h + feed_forward(...): bf16 + bf16 -> bf16 (model.py:317, 326)
-                    unpack8(res ? ll_wait4(res + (i >> 1), tag) : __ldg(reinterpret_cast<const uint4*>(rest + i)), f);
+                for (int j = 0; j < 8; ++j) acc[j] = __fadd_rn(f[j], bf16_round(acc[j]));
+            } else if (summed) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = __fadd_rn(f[j], bf16_round(acc[j]));
-                }
-                o = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                               pack_bf16x2(acc[6], acc[7]));
+                for (int j = 0; j < 8; ++j) acc[j] = bf16_round(acc[j]);
             }
+            const uint4 o = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                                       pack_bf16x2(acc[6], acc[7]));
             *reinterpret_cast<uint4*>(xs + i) = o;
             if (sum_out) {
                 ll_store(sum_out + (i >> 1) + 0, o.x, tag);
                 ll_store(sum_out + (i >> 1) + 1, o.y, tag);
                 ll_store(sum_out + (i >> 1) + 2, o.z, tag);
                 ll_store(sum_out + (i >> 1) + 3, o.w, tag);
+            }
+        };
+        if (W == 1 && res) {
+            // one source + residual vector: two 8-element groups of this thread per memory round trip
+            for (int i0 = tid * 8; i0 < K; i0 += 2 * kTT * 8) {
+                const int i1 = i0 + kTT * 8, i1c = i1 < K ? i1 : i0;
+                const uint64_t* p[4] = {in + (i0 >> 1), res + (i0 >> 1), in + (i1c >> 1), res + (i1c >> 1)};
+                uint4 o[4];
+                ll_wait4_n<4>(p, i1 < K ? 4 : 2, tag, o);
+                float acc[8];
+                unpack8(o[0], acc);
+                finish(i0, acc, &o[1], false);
+                if (i1 < K) {
+                    unpack8(o[2], acc);
+                    finish(i1, acc, &o[3], false);
+                }
+            }
+        } else if (W == 1) {
+            // one source: four 8-element groups of this thread per memory round trip
+            for (int i0 = tid * 8; i0 < K; i0 += 4 * kTT * 8) {
+                const uint64_t* p[4];
+                int n = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * kTT * 8;
+                    p[u] = in + ((i < K ? i : i0) >> 1);
+                    n += i < K ? 1 : 0;
+                }
+                uint4 o[4];
+                ll_wait4_n<4>(p, n, tag, o);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * kTT * 8;
+                    if (i < K) {
+                        if (op.res_kind == RES_NONE && !sum_out) {
+                            *reinterpret_cast<uint4*>(xs + i) = o[u];
+                        } else {
+                            float acc[8];
+                            unpack8(o[u], acc);
+                            finish(i, acc, nullptr, false);
+                        }
+                    }
+                }
+            }
+        } else {
+            // tensor parallel: residual + the first four partial vectors of an 8-element group in one round trip,
+            // the other ranks' in a second one; summed in rank order (the same bits on every rank)
+            for (int i = tid * 8; i < K; i += kTT * 8) {
+                float acc[8], f[8];
+                uint4 o[5];
+                {
+                    const uint64_t* p[5];
+                    const int n = min(4, W);
+                    p[0] = res ? res + (i >> 1) : in + (i >> 1);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) p[1 + u] = in + (size_t)(u < n ? u : 0) * nw + (i >> 1);
+                    ll_wait4_n<5>(p, 1 + n, tag, o, true);
+                    unpack8(o[1], acc);
+#pragma unroll
+                    for (int u = 1; u < 4; ++u)
+                        if (u < n) {
+                            unpack8(o[1 + u], f);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+                        }
+                }
+                if (W > 4) {
+                    const uint64_t* p[4];
+                    const int n = W - 4;
+                    uint4 o2[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) p[u] = in + (size_t)(4 + (u < n ? u : 0)) * nw + (i >> 1);
+                    ll_wait4_n<4>(p, n, tag, o2, true);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (u < n) {
+                            unpack8(o2[u], f);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+                        }
+                }
+                finish(i, acc, res ? &o[0] : nullptr, true);
             }
         }
     }
@@ -376,23 +544,64 @@ __device__ void stage_input(const TokParams& P, const TokOp& op, __nv_bfloat16* 
     __syncthreads();
 }
 
-// RG weight-row segments of `len` elements (a multiple of 256) in a ring stage against the staged input
-template <int RG>
-__device__ __forceinline__ void consume_tile(const uint8_t* stage, const __nv_bfloat16* xseg, int len, float (&acc)[RG], int lane) {
-    const int nb = len >> 8;
-    const uint32_t row_bytes = (uint32_t)len * 2;
-#pragma unroll 4
-    for (int b = 0; b < nb; ++b) {
-        float x[8];
-        unpack8(*reinterpret_cast<const uint4*>(xseg + b * 256 + lane * 8), x);
+// One ring stage against the staged input on the tensor cores (mma.sync m16n8k16, bf16 in, fp32 accumulate).
+// The stage holds R row segments of `len` elements (R = 2, or 4 for the FFN gate: R * len <= 4096), read as 8
+// independent STREAMS of slen = R * len / 8 consecutive elements: stream n = bytes [n * slen * 2, (n + 1) * slen * 2)
+// of the stage, i.e. row n / S, part n % S (S = 8 / R streams per row).  Only the DIAGONAL of the 16 x 8 product is
+// used: thread (gid = lane / 4, tig = lane % 4) feeds stream gid as column gid of B and the matching input elements
+// as row gid of A, so D[gid][gid] accumulates that stream's dot product.  Each thread loads 8 consecutive elements of
+// its stream (one LDS.128) and of the input (one LDS.128) per 32-element block and issues two MMAs (the 16 k-slots
+// of an MMA can hold any 16 elements as long as A and B agree).  Odd streams run one block ahead of even ones
+// (mod the block count), which keeps both LDS.128 patterns bank-conflict free without padding the rows.
+// A hand-written FFMA loop over the same stage costs 10x the instructions (unpack + FMA per element) and left the
+// kernel issue-bound at ~25 B/clk per SM, i.e. unable to catch up after a stage hand-over (profiles/r2/notes.md).
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
+    // rows gid + 8 of A repeat rows gid (their results are never read)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %4, %5, %5}, {%6, %7}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+}
+template <int S_LOG2>   // log2(streams per row): 2 for two-row stages, 1 for the four-row FFN gate stage
+__device__ __forceinline__ void consume_tile(const uint8_t* stage, const __nv_bfloat16* xseg, int len, float (&c)[8][4], int lane) {
+    constexpr int S = 1 << S_LOG2;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int nblk = len >> (5 + S_LOG2);   // 32-element blocks per stream
+    // stream gid = row gid / S of the stage, taking 32-element blocks p, p + S, p + 2S, ... (p = gid % S) of the row
+    // segment: in every round the lanes of a quarter-warp read one contiguous 128-byte run of a row (conflict free)
+    // and the whole warp reads the input from one S * 64-byte window (S / 2 wavefronts instead of 4)
+    const uint8_t* wp = stage + (size_t)(gid >> S_LOG2) * (len * 2) + (gid & (S - 1)) * 64 + tig * 16;
+    const uint8_t* xp = reinterpret_cast<const uint8_t*>(xseg) + (gid & (S - 1)) * 64 + tig * 16;
+    // four blocks per round on eight independent accumulators
+    int i = 0;
+    for (; i + 4 <= nblk; i += 4) {
+        uint4 w[4], x[4];
 #pragma unroll
-        for (int r = 0; r < RG; ++r) {
-            float f[8];
-            unpack8(*reinterpret_cast<const uint4*>(stage + r * row_bytes + b * 512 + lane * 16), f);
+        for (int u = 0; u < 4; ++u) {
+            w[u] = *reinterpret_cast<const uint4*>(wp + (i + u) * (64 * S));
+            x[u] = *reinterpret_cast<const uint4*>(xp + (i + u) * (64 * S));
+        }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[r] = fmaf(f[j], x[j], acc[r]);
+        for (int u = 0; u < 4; ++u) {
+            mma_bf16_16816(c[2 * u], x[u].x, x[u].y, w[u].x, w[u].y);
+            mma_bf16_16816(c[2 * u + 1], x[u].z, x[u].w, w[u].z, w[u].w);
         }
     }
+    for (; i < nblk; ++i) {
+        const uint4 w = *reinterpret_cast<const uint4*>(wp + i * (64 * S));
+        const uint4 x = *reinterpret_cast<const uint4*>(xp + i * (64 * S));
+        mma_bf16_16816(c[0], x.x, x.y, w.x, w.y);
+        mma_bf16_16816(c[1], x.z, x.w, w.z, w.w);
+    }
+}
+// after the last stage of a row group: the 8 stream sums -> lanes 0..7 (lane n = stream n), replicated in the
+// other lanes.  Fixed summation order: deterministic.
+__device__ __forceinline__ float gather_streams(const float (&c)[8][4], int lane) {
+    const int gid = lane >> 2;
+    const int e = gid & 1;   // D[gid][gid] lives where tig == gid / 2, in element gid & 1
+    float v = e ? c[0][1] : c[0][0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) v += e ? c[k][1] : c[k][0];
+    const int n = lane & 7;
+    return __shfl_sync(0xffffffffu, v, n * 4 + (n >> 1));
 }
 
 // deferred writes of cross-head cache state (see attn_stage): performed by thread 0 once every head has read it
@@ -407,20 +616,20 @@ struct Pending {
 struct HeadBest { float v; int idx; };
 
 // ------------------------------------------------------------------ a matrix-vector stage
-__device__ void gemv_stage(const TokParams& P, const TokOp& op, int oi, uint8_t* smem, Ring& ring, uint32_t tag,
+__device__ void gemv_stage(const TokParams& P, DescWindow* W, const TokOp& op, int oi, uint8_t* smem, Ring& ring, uint32_t tag,
                            float* scratch, uint32_t* outw, Pending* pend, HeadBest* best) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem);
     __syncthreads();   // every warp is done with the staging area of the previous stage
-    if (P.trace && tid == 0) {
-        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        P.trace[((size_t)oi * gridDim.x + blockIdx.x) * 2] = t;
+    if (tid == 0) tstamp(P, oi, 0);
+    if (warp == 1) {   // advance the descriptor window (this warp only waits for warp 0's poll otherwise)
+        uint4 keep[2];
+        int ka;
+        window_load(P, W, oi + kOpWin - 1, lane, keep, &ka);
+        window_store(P, W, oi + kOpWin - 1, lane, keep, ka);
     }
     stage_input(P, op, xs, scratch, tag);
-    if (P.trace && tid == 0) {
-        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        P.trace[((size_t)oi * gridDim.x + blockIdx.x) * 2 + 1] = t;
-    }
+    if (tid == 0) tstamp(P, oi, 1);
     // cross-head cache state of the attention stage just before this one: its input being complete means every
     // head's CTAs have finished reading the old state
     if (tid == 0 && pend->active) {
@@ -433,6 +642,10 @@ __device__ void gemv_stage(const TokParams& P, const TokOp& op, int oi, uint8_t*
     const int type = op.type, K = op.K;
     const int pos = type == TOK_QKV ? P.input_pos[0] : 0;
     const bool push = type == TOK_GEMV && op.out_world > 1 && nloc <= kOutStage;
+#ifdef CC_TOKEN_MICROTRACE
+    int dbg_n = 0;
+    const unsigned long long dbg_t0 = clock64();
+#endif
     for (int j = warp; j < nloc; j += kTW) {
         const int g = g0 + j, r0 = 2 * g;
         // operands of the epilogue, requested before the dot products
@@ -445,22 +658,43 @@ __device__ void gemv_stage(const TokParams& P, const TokOp& op, int oi, uint8_t*
                 e3 = __bfloat162float(P.freqs[((size_t)pos * half + i) * 2 + 1]);
             }
         }
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float c[8][4];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c[k][0] = c[k][1] = c[k][2] = c[k][3] = 0.f;
         for (int s = 0; s < op.n_seg; ++s) {
             const int off = s * op.seg_len, len = min(op.seg_len, K - off);
+#ifdef CC_TOKEN_MICROTRACE
+            unsigned long long* dbg = (P.trace && blockIdx.x == 0 && lane == 0 && dbg_n < 8)
+                ? P.trace + (size_t)P.n_ops * gridDim.x * kTraceSlots + ((size_t)oi * kTW + warp) * 32 + 1 + dbg_n * 3 : nullptr;
+            if (dbg) dbg[-1 - dbg_n * 3] = dbg_t0;
+#endif
             const uint8_t* st = ring_wait(ring);
-            if (type == TOK_GATE) {
-                consume_tile<4>(st, xs + off, len, acc, lane);
-            } else {
-                float a2[2] = {acc[0], acc[1]};
-                consume_tile<2>(st, xs + off, len, a2, lane);
-                acc[0] = a2[0]; acc[1] = a2[1];
-            }
+#ifdef CC_TOKEN_MICROTRACE
+            if (dbg) dbg[0] = clock64();
+#endif
+            if (type == TOK_GATE) consume_tile<1>(st, xs + off, len, c, lane);
+            else consume_tile<2>(st, xs + off, len, c, lane);
+#ifdef CC_TOKEN_MICROTRACE
+            if (dbg) dbg[1] = clock64();
+#endif
             ring_release(ring, P, warp, lane);
+#ifdef CC_TOKEN_MICROTRACE
+            if (dbg) { dbg[2] = clock64(); ++dbg_n; }
+#endif
         }
-        acc[0] = warp_sum_f(acc[0]);
-        acc[1] = warp_sum_f(acc[1]);
-        if (type == TOK_GATE) { acc[2] = warp_sum_f(acc[2]); acc[3] = warp_sum_f(acc[3]); }
+        float acc[4];
+        {
+            float sv = gather_streams(c, lane);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+            if (type == TOK_GATE) {   // 4 rows x 2 streams: w1 r0, w1 r0+1, w3 r0, w3 r0+1
+                acc[0] = __shfl_sync(0xffffffffu, sv, 0); acc[1] = __shfl_sync(0xffffffffu, sv, 2);
+                acc[2] = __shfl_sync(0xffffffffu, sv, 4); acc[3] = __shfl_sync(0xffffffffu, sv, 6);
+            } else {                  // 2 rows x 4 streams
+                sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+                acc[0] = __shfl_sync(0xffffffffu, sv, 0); acc[1] = __shfl_sync(0xffffffffu, sv, 4);
+                acc[2] = acc[3] = 0.f;
+            }
+        }
         if (lane != 0) continue;
         uint64_t* out = reinterpret_cast<uint64_t*>(P.scratch + op.out_off);
         if (type == TOK_QKV) {
@@ -497,6 +731,7 @@ __device__ void gemv_stage(const TokParams& P, const TokOp& op, int oi, uint8_t*
             if (b > best->v || (b == best->v && r0 + 1 < best->idx)) { best->v = b; best->idx = r0 + 1; }
         }
     }
+    if (lane == 0) tstamp(P, oi, 2 + warp);
     if (push) {
         // row-parallel partial outputs of this CTA are contiguous words: store them to every rank as whole lines
         __syncthreads();
@@ -518,7 +753,7 @@ struct AttnSmem {
 __host__ __device__ inline uint32_t attn_smem_bytes(int D, int G, int C, int stride, int local_rows) {
     uint32_t off = 0;
     off += (uint32_t)G * stride * 4;            // lg
-    off += (uint32_t)kTW * G * D * 4;           // red
+    off += (uint32_t)kRedWarps * G * D * 4;     // red
     off += (uint32_t)C * (2 + 2 * G) * 4;       // rec
     off += (uint32_t)C * 2 * G * 4;             // sums (lo, hi)
     off += (uint32_t)G * D * 4;                 // yx
@@ -530,7 +765,7 @@ __host__ __device__ inline uint32_t attn_smem_bytes(int D, int G, int C, int str
 enum : int { kTmNewLg = 0, kTmMyRec = 16, kTmWarpKey = 48, kTmWarpMax = 80, kTmWords = 128 };
 
 template <int D, int G>
-__device__ void attn_stage(const TokParams& P, const TokAttn& A, int oi, uint8_t* smem, Ring& ring, uint32_t tag, Pending* pend) {
+__device__ void attn_stage(const TokParams& P, DescWindow* W, const TokAttn& A, int oi, uint8_t* smem, Ring& ring, uint32_t tag, Pending* pend) {
     constexpr int LPR = D / 8;           // lanes per cache row
     constexpr int RPI = 32 / LPR;        // rows per warp iteration
     constexpr uint32_t kRowBytes = D * 2;
@@ -539,9 +774,12 @@ __device__ void attn_stage(const TokParams& P, const TokAttn& A, int oi, uint8_t
     const int li = lane % LPR, sub = lane / LPR;
     const AttnDeal dl = deal_attn(A);
     __syncthreads();   // the staging area of the previous stage is free
-    if (P.trace && tid == 0) {
-        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        P.trace[((size_t)oi * gridDim.x + blockIdx.x) * 2] = t;
+    if (tid == 0) tstamp(P, oi, 0);
+    if (warp == 1) {   // advance the descriptor window
+        uint4 keep[2];
+        int ka;
+        window_load(P, W, oi + kOpWin - 1, lane, keep, &ka);
+        window_store(P, W, oi + kOpWin - 1, lane, keep, ka);
     }
     if (!dl.active) return;
     const CcCacheState& st = A.st;
@@ -557,7 +795,7 @@ __device__ void attn_stage(const TokParams& P, const TokAttn& A, int oi, uint8_t
     {
         uint8_t* p = smem;
         sm.lg = reinterpret_cast<float*>(p);    p += (size_t)G * stride * 4;
-        sm.red = reinterpret_cast<float*>(p);   p += (size_t)kTW * G * D * 4;
+        sm.red = reinterpret_cast<float*>(p);   p += (size_t)kRedWarps * G * D * 4;
         sm.rec = reinterpret_cast<uint32_t*>(p); p += (size_t)C * NWR * 4;
         sm.sums = reinterpret_cast<uint32_t*>(p); p += (size_t)C * 2 * G * 4;
         sm.yx = reinterpret_cast<float*>(p);    p += (size_t)G * D * 4;
@@ -647,15 +885,21 @@ __device__ void attn_stage(const TokParams& P, const TokAttn& A, int oi, uint8_t
     // ---- B. this token's query rows of the KV group, the new key and value slices (flag-in-data words of the
     // projection stage): 4 words per 8 elements
     float q[G][8];
+    uint4 knew8, vnew8;
+    {
+        const uint64_t* p[G + 2];
+        uint4 o[G + 2];
 #pragma unroll
-    for (int g = 0; g < G; ++g)
-        unpack8(ll_wait4(qkv + (((size_t)(h * G + g) * D + li * 8) >> 1), tag), q[g]);
-    const uint4 knew8 = ll_wait4(qkv + (((size_t)P.n_q_rows + (size_t)h * D + li * 8) >> 1), tag);
-    const uint4 vnew8 = ll_wait4(qkv + (((size_t)P.n_q_rows + P.n_kv_rows + (size_t)h * D + li * 8) >> 1), tag);
-    if (P.trace && tid == 0) {
-        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        P.trace[((size_t)oi * gridDim.x + blockIdx.x) * 2 + 1] = t;
+        for (int g = 0; g < G; ++g) p[g] = qkv + (((size_t)(h * G + g) * D + li * 8) >> 1);
+        p[G] = qkv + (((size_t)P.n_q_rows + (size_t)h * D + li * 8) >> 1);
+        p[G + 1] = qkv + (((size_t)P.n_q_rows + P.n_kv_rows + (size_t)h * D + li * 8) >> 1);
+        ll_wait4_n<G + 2>(p, G + 2, tag, o);
+#pragma unroll
+        for (int g = 0; g < G; ++g) unpack8(o[g], q[g]);
+        knew8 = o[G];
+        vnew8 = o[G + 1];
     }
+    if (tid == 0) tstamp(P, oi, 1);
     if (warp == kTW - 1) {   // logits of the new token (it attends to itself, model.py:392 then 402)
         float kf[8], part[G];
         unpack8(knew8, kf);
@@ -699,6 +943,7 @@ __device__ void attn_stage(const TokParams& P, const TokAttn& A, int oi, uint8_t
         if (nv > 0) ring_release(ring, P, warp, lane);
     }
     __syncthreads();
+    if (tid == 0) tstamp(P, oi, 2);
     // ---- row max without the local candidate, and the candidate's own logits -> this CTA's X1 record
     for (int g = warp; g < G; g += kTW) {
         float m = -CUDART_INF_F;
@@ -720,6 +965,7 @@ __device__ void attn_stage(const TokParams& P, const TokAttn& A, int oi, uint8_t
     if (tid < NWR) ll_store(x1 + (size_t)rank * NWR + tid, miscu[kTmMyRec + tid], tag);
     for (int idx = tid; idx < C * NWR; idx += kTT) sm.rec[idx] = ll_wait(x1 + idx, tag);
     __syncthreads();
+    if (tid == 0) tstamp(P, oi, 3);
     // winner + global max per query head (every warp redundantly)
     uint64_t wkey = kNoKey64;
     for (int r = lane; r < C; r += 32) {
@@ -771,8 +1017,10 @@ __device__ void attn_stage(const TokParams& P, const TokAttn& A, int oi, uint8_t
     }
     __syncthreads();
     if (tid < 2 * G) ll_store(x2 + (size_t)rank * 2 * G + tid, (uint32_t)(sm.ssum[tid >> 1] >> (32 * (tid & 1))), tag);
+    if (tid == 0) tstamp(P, oi, 4);
     for (int idx = tid; idx < C * 2 * G; idx += kTT) sm.sums[idx] = ll_wait(x2 + idx, tag);
     __syncthreads();
+    if (tid == 0) tstamp(P, oi, 5);
     float sumf[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
@@ -793,6 +1041,7 @@ __device__ void attn_stage(const TokParams& P, const TokAttn& A, int oi, uint8_t
         lg[g * stride + lr] = pr;
     }
     __syncthreads();
+    if (tid == 0) tstamp(P, oi, 6);
 
     // ---- y = P.V over this warp's V tiles, warp -> CTA -> head reduction = X3
     {
@@ -831,21 +1080,40 @@ __device__ void attn_stage(const TokParams& P, const TokAttn& A, int oi, uint8_t
                 for (int d = 16; d >= LPR; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
                 acc[g][i] = v;
             }
-        if (lane < LPR) {
+        if (kTW > kRedWarps) {   // upper warps first, then the lower ones add their own on top (fixed order)
+            if (warp >= kRedWarps && lane < LPR) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    float4* dst = reinterpret_cast<float4*>(&sm.red[(warp - kRedWarps) * G * D + g * D + lane * 8]);
+                    dst[0] = make_float4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]);
+                    dst[1] = make_float4(acc[g][4], acc[g][5], acc[g][6], acc[g][7]);
+                }
+            }
+            __syncthreads();
+        }
+        if (warp < kRedWarps && lane < LPR) {
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 float4* dst = reinterpret_cast<float4*>(&sm.red[warp * G * D + g * D + lane * 8]);
-                dst[0] = make_float4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]);
-                dst[1] = make_float4(acc[g][4], acc[g][5], acc[g][6], acc[g][7]);
+                float4 a = make_float4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]);
+                float4 b = make_float4(acc[g][4], acc[g][5], acc[g][6], acc[g][7]);
+                if (kTW > kRedWarps) {
+                    const float4 pa = dst[0], pb = dst[1];
+                    a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
+                    b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
+                }
+                dst[0] = a;
+                dst[1] = b;
             }
         }
     }
     __syncthreads();
+    if (tid == 0) tstamp(P, oi, 7);
     const int SL = (G * D) >> csh;  // outputs reduced by each CTA of the head (a multiple of 4)
     for (int o = tid; o < G * D; o += kTT) {
         float s = sm.red[o];
 #pragma unroll
-        for (int w = 1; w < kTW; ++w) s += sm.red[w * G * D + o];
+        for (int w = 1; w < kRedWarps; ++w) s += sm.red[w * G * D + o];
         const int dest = o / SL, off = o - dest * SL;
         ll_store(x3 + ((size_t)dest * C + rank) * SL + off, __float_as_uint(s), tag);
     }
@@ -908,15 +1176,19 @@ __device__ void attn_stage(const TokParams& P, const TokAttn& A, int oi, uint8_t
         }
         if (hh && h == 0 && rank == 0 && tid == 0) st.attn_counter[0] += 1;
     }
-    // ---- X3 arrives: this CTA's slice of y
+    // ---- X3 arrives: this CTA's slice of y (all words requested at once, summed in rank order)
     {
-        uint64_t* yout = reinterpret_cast<uint64_t*>(P.scratch + A.y_off) + (((size_t)h * G * D + (size_t)rank * SL) >> 1);
         const uint64_t* mine = x3 + (size_t)rank * C * SL;
+        if (tid == 0) tstamp(P, oi, 8);
+        for (int idx = tid; idx < C * SL; idx += kTT) sm.yx[idx] = __uint_as_float(ll_wait(mine + idx, tag));
+        __syncthreads();
+        if (tid == 0) tstamp(P, oi, 9);
+        uint64_t* yout = reinterpret_cast<uint64_t*>(P.scratch + A.y_off) + (((size_t)h * G * D + (size_t)rank * SL) >> 1);
         for (int t = tid; t < (SL >> 1); t += kTT) {
             float s0 = 0.f, s1 = 0.f;
             for (int r = 0; r < C; ++r) {
-                s0 += __uint_as_float(ll_wait(mine + (size_t)r * SL + 2 * t, tag));
-                s1 += __uint_as_float(ll_wait(mine + (size_t)r * SL + 2 * t + 1, tag));
+                s0 += sm.yx[r * SL + 2 * t];
+                s1 += sm.yx[r * SL + 2 * t + 1];
             }
             ll_store(yout + t, pack_bf16x2(s0, s1), tag);
         }
@@ -931,6 +1203,7 @@ __global__ void __launch_bounds__(kTT, 1) cc_token_kernel(const __grid_constant_
     __shared__ uint32_t outw[kOutStage];
     __shared__ Pending pend;
     __shared__ HeadBest wbest[kTW];
+    __shared__ __align__(16) DescWindow win;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t ring_off = (P.xs_bytes + 127u) & ~127u;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ring_off + (size_t)kTW * P.n_stages * kStage);
@@ -945,15 +1218,39 @@ __global__ void __launch_bounds__(kTT, 1) cc_token_kernel(const __grid_constant_
         for (int s = 0; s < P.n_stages; ++s) mbar_init(&ring.bars[s], 1);
         mbar_fence_init();
     }
-    if (tid == 0) pend.active = 0;
-    __syncwarp();
+    if (tid == 0) { pend.active = 0; win.op_hi = 0; win.att_hi = 0; }
+    __syncthreads();
+    // descriptor window: the first kOpWin - 1 stages, one per warp round
+    for (int oi = warp; oi < kOpWin - 1; oi += kTW) {
+        uint4 keep[2];
+        int ka;
+        window_load(P, &win, oi, lane, keep, &ka);
+        if (oi < P.n_ops) {
+            constexpr int nop = (int)(sizeof(TokOp) / 16), natt = (int)(sizeof(TokAttn) / 16);
+            if (lane < nop) reinterpret_cast<uint4*>(&win.op[oi % kOpWin])[lane] = keep[0];
+            if (ka >= 0 && lane < natt) reinterpret_cast<uint4*>(&win.att[ka % kAttWin])[lane] = keep[1];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int n = min(kOpWin - 1, P.n_ops);
+        int na = 0;
+        for (int oi = 0; oi < n; ++oi) na += win.op[oi].type == TOK_ATTN ? 1 : 0;
+        win.att_hi = na;
+        win.op_hi = n;
+    }
+    __syncthreads();
+    ring.win = &win;
+    ring.policy = l2_policy_evict_first();
     // the weight / cache stream starts before anything else: fill the whole ring
+    // (an L2 prefetch cursor running further ahead -- cp.async.bulk.prefetch.L2 of the tiles after the ring -- was
+    // measured SLOWER: 301 -> 273 tokens/s at 2 tiles per warp, 240 at 6; profiles/r2/notes.md)
     ring.it.op = 0;
     if (lane == 0) {
-        iter_enter(ring.it, P, warp);
+        iter_enter(ring.it, P, &win, warp);
         for (int s = 0; s < P.n_stages && ring.it.op < P.n_ops; ++s) {
-            iter_issue(ring.it, warp, ring.stages + (size_t)s * kStage, &ring.bars[s]);
-            iter_advance(ring.it, P, warp);
+            iter_issue(ring.it, warp, ring.stages + (size_t)s * kStage, &ring.bars[s], ring.policy);
+            iter_advance(ring.it, P, &win, warp);
         }
     }
     __syncwarp();
@@ -963,11 +1260,11 @@ __global__ void __launch_bounds__(kTT, 1) cc_token_kernel(const __grid_constant_
     bool has_head = false;
 
     for (int oi = 0; oi < P.n_ops; ++oi) {
-        const TokOp& op = P.ops[oi];
+        const TokOp& op = *op_at(P, &win, oi);
         if (op.type == TOK_ATTN) {
-            attn_stage<D, G>(P, P.attns[op.attn], oi, smem, ring, tag, &pend);
+            attn_stage<D, G>(P, &win, *att_at(P, &win, op.attn), oi, smem, ring, tag, &pend);
         } else {
-            gemv_stage(P, op, oi, smem, ring, tag, scratch, outw, &pend, &best);
+            gemv_stage(P, &win, op, oi, smem, ring, tag, scratch, outw, &pend, &best);
             has_head |= op.type == TOK_HEAD;
         }
     }
@@ -991,11 +1288,14 @@ __global__ void __launch_bounds__(kTT, 1) cc_token_kernel(const __grid_constant_
             ll_store(rec1 + 2 * blockIdx.x, __float_as_uint(cb.v), tag);
             ll_store(rec1 + 2 * blockIdx.x + 1, (uint32_t)cb.idx, tag);
         }
-        // every CTA reduces all records (it needs the global max for the softmax anyway)
+        // every CTA reduces all records (it needs the global max for the softmax anyway); all words requested at once
+        float* recs = reinterpret_cast<float*>(smem);   // the staging area is free: 2 * n_ctas words
+        for (int i = tid; i < 2 * nc; i += kTT) recs[i] = __uint_as_float(ll_wait(rec1 + i, tag));
+        __syncthreads();
         HeadBest gb = {-CUDART_INF_F, 0x7fffffff};
         for (int c = lane; c < nc; c += 32) {
-            const float v = __uint_as_float(ll_wait(rec1 + 2 * c, tag));
-            const int idx = (int)ll_wait(rec1 + 2 * c + 1, tag);
+            const float v = recs[2 * c];
+            const int idx = (int)__float_as_uint(recs[2 * c + 1]);
             if (v > gb.v || (v == gb.v && idx < gb.idx)) { gb.v = v; gb.idx = idx; }
         }
 #pragma unroll
@@ -1007,7 +1307,7 @@ __global__ void __launch_bounds__(kTT, 1) cc_token_kernel(const __grid_constant_
         if (blockIdx.x == 0 && tid == 0 && P.token_out) P.token_out[0] = gb.idx;
         if (P.probs_out && P.logits_out) {
             // softmax over the bf16 logits in fp32 (torch.softmax on a bf16 tensor), one bf16 rounding
-            const TokOp& hop = P.ops[P.n_ops - 1];
+            const TokOp& hop = *op_at(P, &win, P.n_ops - 1);
             int g0, nloc;
             deal_groups(hop.n_groups, hop.rot, &g0, &nloc);
             float part = 0.f;
@@ -1022,8 +1322,10 @@ __global__ void __launch_bounds__(kTT, 1) cc_token_kernel(const __grid_constant_
                 for (int w = 0; w < kTW; ++w) tot += scratch[w];
                 ll_store(rec2 + blockIdx.x, __float_as_uint(tot), tag);
             }
+            for (int i = tid; i < nc; i += kTT) recs[i] = __uint_as_float(ll_wait(rec2 + i, tag));
+            __syncthreads();
             float tot = 0.f;
-            for (int c = 0; c < nc; ++c) tot += __uint_as_float(ll_wait(rec2 + c, tag));  // CTA order: deterministic
+            for (int c = 0; c < nc; ++c) tot += recs[c];  // CTA order: deterministic
             for (int i = tid; i < 2 * nloc; i += kTT) {
                 const float l = __bfloat162float(P.logits_out[2 * g0 + i]);
                 P.probs_out[2 * g0 + i] = __float2bfloat16_rn(__fdiv_rn(expf(l - gb.v), tot));
@@ -1099,9 +1401,10 @@ static int attn_shape(const CcCacheState& st, int n_ctas, AttnShape* out) {
     int csh = 0;
     while ((2 << csh) * H <= n_ctas && (2 << csh) <= 128) ++csh;
     while (csh > 0 && (1 << csh) > (G * D) / 4) --csh;                 // every CTA reduces >= 4 outputs of y
-    while (csh > 0 && (1 << csh) > (L + 15) / 16) --csh;               // every CTA gets >= 1 chunk of >= 16 rows
+    constexpr int min_chs = kTW <= 8 ? 4 : 5;                           // every warp owns >= 2 rows of a chunk
+    while (csh > 0 && (1 << csh) > (L + (1 << min_chs) - 1) >> min_chs) --csh;   // every CTA gets >= 1 chunk
     int chs = 7;
-    while (chs > 4 && ((L + (1 << chs) - 1) >> chs) < (1 << csh)) --chs;
+    while (chs > min_chs && ((L + (1 << chs) - 1) >> chs) < (1 << csh)) --chs;
     const int C = 1 << csh, n_chunks = (L + (1 << chs) - 1) >> chs;
     const int mlc = (n_chunks + C - 1) / C;
     out->c_shift = csh; out->ch_shift = chs;
@@ -1373,6 +1676,8 @@ int token_plan_create_impl(const CcTokenModel* m, void** out_plan) {
     p.emb = (const __nv_bfloat16*)m->tok_embeddings; p.freqs = (const __nv_bfloat16*)m->freqs_cis;
     p.dim = m->dim; p.n_q_rows = m->n_q_heads * D; p.n_kv_rows = m->n_kv_heads * D; p.head_dim = D;
     p.xs_bytes = xs_bytes; p.n_stages = n_stages;
+
+
     p.rec1_off = lay.rec1; p.rec2_off = lay.rec2;
     *out_plan = plan;
     return CC_OK;

@@ -346,7 +346,8 @@ int cc_decode_token(void* plan, const int32_t* token_in, const int32_t* input_po
  * [world][dim], 3 h, 4 gate, 5 w2 partials [world][dim], 6 layer input x (layer >= 1; layer == n_layers: head input).
  * Words are u64 = {bf16 x 2 | tag << 32}. */
 int cc_token_buffer(void* plan, int32_t layer, int32_t which, uint64_t* offset_bytes, int32_t* n_words);
-/* Diagnostics: device buffer u64 [n_stages][n_ctas][2] of %globaltimer stamps (stage entered, input staged). */
+/* Diagnostics: device buffer u64 [n_stages][n_ctas][12] of %globaltimer stamps: 0 stage entered, 1 input staged,
+ * 2..9 warp w done (projection stages) / phase boundaries (attention stage). */
 int cc_token_set_trace(void* plan, void* device_buffer);
 int cc_token_info(void* plan, int32_t* n_ctas, int32_t* n_stages_program, int32_t* ring_stages, int32_t* smem_bytes);
 

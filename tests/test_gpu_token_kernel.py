@@ -123,7 +123,8 @@ def test_every_projection_stage_within_one_ulp(strategy, bias, n_head, n_kv, dim
             logits = plan.logits
             want = R.proj(model.output.weight, R.rmsnorm(xn, model.norm.weight, model.norm.eps))
             worst["head"] = R.ulp_excess(logits, want)
-            assert all(v <= 1.0 for v in worst.values()), worst
+            # the gate multiplies two bf16-rounded factors: each may sit on the adjacent bf16 value, the product on the next
+            assert all(v <= (2.0 if k == "gate" else 1.0) for k, v in worst.items()), worst
             # greedy sampling: first index of the largest logit; probabilities = softmax of the bf16 logits
             assert int(nxt) == int(torch.argmax(logits.float()))
             p_ref = torch.softmax(logits.float(), -1)
