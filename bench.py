@@ -120,7 +120,9 @@ def build_gpu_model(device, world):
     if world > 1:
         from cold_compress_b200.tp import apply_tp, enable_fused_exchange
         apply_tp(model)
-        if os.environ.get("CC_TP_NCCL") != "1":  # default: all-reduces fused into the projection kernels over NVLink
+        # default: one kernel per token with the all-reduces inside it (stores into every rank's scratch over NVLink).
+        # CC_TOKEN_KERNEL=0: per-layer kernels with the exchange fused into the projections; + CC_TP_NCCL=1: NCCL.
+        if os.environ.get("CC_TOKEN_KERNEL", "1") == "0" and os.environ.get("CC_TP_NCCL") != "1":
             enable_fused_exchange(model)
     if os.environ.get("CC_WARM_MB"):  # experiments: MB of w1/w3 rows the cache step pre-loads into L2 (-1 = none)
         mb = int(os.environ["CC_WARM_MB"])
@@ -280,7 +282,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{MODEL}-shape random-init bf16, heavy_hitter + SnapKV compression, "
                                f"{CACHE_SLOTS} slots/layer, {PROMPT_LEN}-token synthetic prompt, decode @ 8k ctx",
-                   "global_batch": 1, "seq_len": PROMPT_LEN + MAX_NEW, "parallelism": (f"tp{world} ({'fused NVLink exchange' if getattr(model, 'tp_link', None) is not None else 'NCCL all-reduce'})"
+                   "global_batch": 1, "seq_len": PROMPT_LEN + MAX_NEW, "parallelism": (f"tp{world} ({'all-reduces inside the whole-token kernel (NVLink stores)' if model._tplan is not None else 'fused NVLink exchange' if getattr(model, 'tp_link', None) is not None else 'NCCL all-reduce'})"
                                    if world > 1 else ("none" if not int(os.environ.get("CC_TP_FAKE", "0")) > 1 else
                                                       f"DIAGNOSTIC: rank-0 shard of tp{os.environ['CC_TP_FAKE']}, exchanges skipped")),
                    "l2": "per-step inputs (15 GB of weights + 134 MB of K/V) exceed the 126 MB L2",

@@ -887,17 +887,25 @@ __device__ void attn_stage(const TokParams& P, DescWindow* W, const TokAttn& A, 
     float q[G][8];
     uint4 knew8, vnew8;
     {
-        const uint64_t* p[G + 2];
-        uint4 o[G + 2];
+        // q rows in rounds of up to four groups (registers), then k and v: 1-2 memory round trips
+        constexpr int QB = G <= 4 ? G : 4;
 #pragma unroll
-        for (int g = 0; g < G; ++g) p[g] = qkv + (((size_t)(h * G + g) * D + li * 8) >> 1);
-        p[G] = qkv + (((size_t)P.n_q_rows + (size_t)h * D + li * 8) >> 1);
-        p[G + 1] = qkv + (((size_t)P.n_q_rows + P.n_kv_rows + (size_t)h * D + li * 8) >> 1);
-        ll_wait4_n<G + 2>(p, G + 2, tag, o);
+        for (int g0 = 0; g0 < G; g0 += QB) {
+            const uint64_t* p[QB];
+            uint4 o[QB];
 #pragma unroll
-        for (int g = 0; g < G; ++g) unpack8(o[g], q[g]);
-        knew8 = o[G];
-        vnew8 = o[G + 1];
+            for (int u = 0; u < QB; ++u) p[u] = qkv + (((size_t)(h * G + min(g0 + u, G - 1)) * D + li * 8) >> 1);
+            ll_wait4_n<QB>(p, min(QB, G - g0), tag, o);
+#pragma unroll
+            for (int u = 0; u < QB; ++u)
+                if (g0 + u < G) unpack8(o[u], q[g0 + u]);
+        }
+        const uint64_t* p[2] = {qkv + (((size_t)P.n_q_rows + (size_t)h * D + li * 8) >> 1),
+                                qkv + (((size_t)P.n_q_rows + P.n_kv_rows + (size_t)h * D + li * 8) >> 1)};
+        uint4 o[2];
+        ll_wait4_n<2>(p, 2, tag, o);
+        knew8 = o[0];
+        vnew8 = o[1];
     }
     if (tid == 0) tstamp(P, oi, 1);
     if (warp == kTW - 1) {   // logits of the new token (it attends to itself, model.py:392 then 402)

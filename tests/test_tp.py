@@ -34,10 +34,22 @@ def test_tp_host_logic_gloo(world):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("strategy", ["heavy_hitter", "recent_global", "heavy_hitter_fused", "recent_global_fused"])
-def test_tp_decode_nccl_world2(strategy):
+@pytest.mark.parametrize("strategy", ["heavy_hitter", "recent_global", "l2", "heavy_hitter_compressed",
+                                      "heavy_hitter_fused", "recent_global_fused", "heavy_hitter_nccl"])
+def test_tp_decode_world2(strategy):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     r = _torchrun(2, strategy)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("tp decode ok") == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("strategy", ["heavy_hitter", "recent_global"])
+def test_tp_decode_world4(strategy):
+    """The whole-token kernel with 4 ranks (one KV head per rank): all-reduces inside the kernel over NVLink."""
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs (gpurun --gpus 4)")
+    r = _torchrun(4, strategy)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("tp decode ok") == 4
