@@ -1,20 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- decode tokens/sec of the compressed-KV decode path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1..5] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): Llama-3-8B-shape, random-init bf16 weights, synthetic token
-ids, cache_strategy=heavy_hitter (SnapKV prompt compression), 1024 slots per layer, 7680-token
-prompt + 512 decode positions = 8192 = the model's block size ("8k ctx").  One *step* = one decoded
-token through all 32 layers.  `value` = decode tokens/s with every input resident in HBM (the step
-is a CUDA graph whose only inputs are the previous token and the position, both on the device);
-`e2e` = the same through the public `generate`-style loop with the token id coming from pinned host
-memory and the sampled token read back to the host every step.
+Workloads = the five BASELINE.json configs (random-init bf16 weights, synthetic token ids):
+  1  Llama-3-8B-shape, recent_global, 64 slots, 128-token prompt                       (the reference's CPU plumbing case)
+  2  Llama-3-8B-shape, heavy_hitter + SnapKV compression, 1024 slots, 7680-token prompt = "8k ctx"   (default at N = 1)
+  3  Llama-3-8B-shape, l2, 512 slots, 4096-token prompt
+  4  Qwen2-7B-shape, hybrid (FastGen per-head strategies), 17408 slots allocated / ~2048 live, 16384-token prompt
+  5  Llama-3-8B-shape, heavy_hitter with pyramid cache lengths (sum 33128 slots), 7680-token prompt  (default at N > 1,
+     tp.py head sharding)
+One *step* = one decoded token through every layer.  `value` = decode tokens/s with every input resident in HBM (the
+step is ONE persistent kernel, or a CUDA graph of per-layer kernels for config 4, whose only inputs are the previous
+token and the position, both on the device); `e2e` = the same through the public decode loop with the token id coming
+from pinned host memory and the sampled token read back to the host every step.
 
-`--impl reference` times the reference's CPU path for the same workload on the host cores: the
-model shell through the same torch CPU ops the reference calls (nn.Linear GEMVs, RMSNorm, RoPE)
-and the cache/attention step through oracle/ (the C restatement of cache.py + attention_utils.py).
+`--impl reference` runs the UNMODIFIED reference (installed into baseline/_ref by tools/install_reference.sh, see
+DESIGN.md) on the host cores: its own Transformer / KVCache classes and its own decode_one_token, caches in a
+synthetic full post-prefill state (the reference's O(S^2) CPU prefill of an 8k prompt takes ~20 minutes).  Without
+baseline/_ref it falls back to the port (torch CPU GEMVs + oracle/ for cache and attention) and says so.
 """
 from __future__ import annotations
 
@@ -34,16 +39,42 @@ import torch
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-MODEL = "Meta-Llama-3-8B-Instruct"
-PROMPT_LEN, MAX_NEW, CACHE_SLOTS = 7680, 512, 1024
-METRIC = "decode tokens/sec @ 8k ctx, 1024-slot heavy-hitter"
+LLAMA, QWEN = "Meta-Llama-3-8B-Instruct", "Qwen2-7B-Instruct"
+HYBRID_STRATEGIES = [   # ~2048 live slots per head of 17408 allocated
+    {"strategy": "window", "recent_window": 0.1176},
+    {"strategy": "window_heavy_hitter", "recent_window": 0.0588, "heavy_hitter_frac": 0.0588},
+    {"strategy": "full"},
+]
+CONFIGS = {
+    1: dict(model=LLAMA, strategy="recent_global", compressor="recent_global", slots=64.0, pattern="tile", prompt=128, max_new=16,
+            what="recent_global, 64 slots/layer, 128-token synthetic prompt"),
+    2: dict(model=LLAMA, strategy="heavy_hitter", compressor="heavy_hitter", slots=1024.0, pattern="tile", prompt=7680, max_new=512,
+            what="heavy_hitter + SnapKV compression, 1024 slots/layer, 7680-token synthetic prompt, decode @ 8k ctx"),
+    3: dict(model=LLAMA, strategy="l2", compressor="l2", slots=512.0, pattern="tile", prompt=4096, max_new=256,
+            what="l2, 512 slots/layer, 4096-token synthetic prompt"),
+    4: dict(model=QWEN, strategy="hybrid", compressor="full", slots=1.0, pattern="tile", prompt=16384, max_new=1024,
+            what="hybrid (FastGen per-head strategies, ~2048 live of 17408 slots per head), 16384-token synthetic prompt"),
+    5: dict(model=LLAMA, strategy="heavy_hitter", compressor="heavy_hitter", slots=1024.0, pattern="pyramid", prompt=7680, max_new=512,
+            what="heavy_hitter + SnapKV compression, pyramid cache lengths (2036 ... 256, sum 33128 slots), 7680-token "
+                 "synthetic prompt, decode @ 8k ctx"),
+}
+METRIC = "decode tokens/sec @ 8k ctx, 1024-slot heavy-hitter"   # BASELINE.json's metric (configs 2 and 5)
+PROMPT_LEN, MAX_NEW = CONFIGS[2]["prompt"], CONFIGS[2]["max_new"]   # (profiles/ scripts)
 
 
-def cache_kwargs():
-    return dict(max_cache_length=[float(CACHE_SLOTS)], cache_bits=None, cache_length_pattern="tile",
-                cache_strategy=["heavy_hitter"], cache_strategy_pattern="tile", feed_long_prompts=False,
-                prompt_compression_strategy=["heavy_hitter"], global_tokens=4, recent_window=10,
-                history_window_size=1, attn_thresholding=False, min_recovery_frac=0.9)
+def metric_name(cfg_id):
+    return METRIC if cfg_id in (2, 5) else f"decode tokens/sec (BASELINE config {cfg_id})"
+
+
+def cache_kwargs(cfg=None):
+    cfg = cfg or CONFIGS[2]
+    kw = dict(max_cache_length=[cfg["slots"]], cache_bits=None, cache_length_pattern=cfg["pattern"],
+              cache_strategy=[cfg["strategy"]], cache_strategy_pattern="tile", feed_long_prompts=False,
+              prompt_compression_strategy=[cfg["compressor"]], global_tokens=4, recent_window=10,
+              history_window_size=1, attn_thresholding=False, min_recovery_frac=0.9)
+    if cfg["strategy"] == "hybrid":
+        kw["hybrid_strategies"] = [dict(s) for s in HYBRID_STRATEGIES]
+    return kw
 
 
 def env_int(name, default):
@@ -93,10 +124,10 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------- our arm (GPU)
 
-def build_gpu_model(device, world):
+def build_gpu_model(device, world, model_name=LLAMA):
     from cold_compress_b200.model import ModelArgs, Transformer
-    cfg = ModelArgs.from_name(MODEL)
-    cfg.block_size = 16384  # only sizes the RoPE table (random-init model); decode positions start at 7680
+    cfg = ModelArgs.from_name(model_name)
+    cfg.block_size = 32768  # only sizes the RoPE table (random-init model); decode positions run past the prompt
     torch.manual_seed(0)
     with torch.device(device):
         model = Transformer(cfg).to(torch.bfloat16)
@@ -124,9 +155,6 @@ def build_gpu_model(device, world):
         # CC_TOKEN_KERNEL=0: per-layer kernels with the exchange fused into the projections; + CC_TP_NCCL=1: NCCL.
         if os.environ.get("CC_TOKEN_KERNEL", "1") == "0" and os.environ.get("CC_TP_NCCL") != "1":
             enable_fused_exchange(model)
-    if os.environ.get("CC_WARM_MB"):  # experiments: MB of w1/w3 rows the cache step pre-loads into L2 (-1 = none)
-        mb = int(os.environ["CC_WARM_MB"])
-        model.warm_l2_ffn_bytes = -1 if mb < 0 else mb << 20
     return model.eval()
 
 
@@ -138,29 +166,39 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def k1_roofline(model, steps, device):
-    """Average duration of the fused decode kernel alone: the 32 per-layer launches of one token as
-    one CUDA graph (inputs = 134 MB of K/V across layers > L2, plus a 256 MB L2 flush between
-    replays, outside the timed events)."""
+def live_kv_bytes(model):
+    """Algorithmic bytes of the cache stage per token on this rank: live K and V rows, bf16."""
+    total = 0
+    for b in model.layers:
+        c = b.attention.kv_cache
+        live = int(c.cache_cts.sum()) if c.cache_cts.numel() > 1 else min(int(c.cache_cts), c.max_cache_length) * c.n_heads
+        total += 2 * live * c.head_dim * 2
+    return total
+
+
+def k1_roofline(model, steps, device, pos0):
+    """Average duration of the per-layer decode kernel (cc_decode_step) alone: the per-layer launches of one token as
+    one CUDA graph (K/V of all layers > L2, plus a 256 MB L2 flush between replays, outside the timed events)."""
     caches = [b.attention.kv_cache for b in model.layers]
     c0 = caches[0]
-    Hkv, D, L = c0.n_heads, c0.head_dim, c0.max_cache_length
-    G = model.config.n_head // model.config.n_local_heads
+    Hkv, D = c0.n_heads, c0.head_dim
+    G = model.layers[0].attention.n_head // model.layers[0].attention.n_local_heads
     gen = torch.Generator(device=device).manual_seed(7)
     q = (torch.randn(1, Hkv * G, 1, D, device=device, generator=gen) * 1.5).to(torch.bfloat16)
     k = torch.randn(1, Hkv, 1, D, device=device, generator=gen).to(torch.bfloat16)
     v = torch.randn(1, Hkv, 1, D, device=device, generator=gen).to(torch.bfloat16)
-    pos = torch.tensor([PROMPT_LEN + MAX_NEW - 64], dtype=torch.int32, device=device)
+    pos = torch.tensor([pos0], dtype=torch.int32, device=device)
+    ids = torch.zeros(1, 1, dtype=torch.int32, device=device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     stream = torch.cuda.Stream()
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.stream(stream):
         for c in caches:  # eager once: plans + output buffers
-            c.decode_step(q, k, v, pos)
+            c.decode_step(q, k, v, pos, input_ids=ids)
         stream.synchronize()
         with torch.cuda.graph(graph, stream=stream):
             for c in caches:
-                c.decode_step(q, k, v, pos, overlap_predecessor=True)  # 32 distinct layers
+                c.decode_step(q, k, v, pos, input_ids=ids, overlap_predecessor=True)
         times = []
         for i in range(steps + 3):
             flush.fill_(i & 0xff)
@@ -173,18 +211,18 @@ def k1_roofline(model, steps, device):
             if i >= 3:
                 times.append(e0.elapsed_time(e1) * 1e-3 / len(caches))
     per_launch = statistics.mean(times)
-    alg_bytes = 2 * Hkv * L * D * 2  # live K and V rows of the layer, bf16
+    alg_bytes = live_kv_bytes(model) / len(caches)
     peak, peak_src = peaks()
     achieved = alg_bytes / per_launch / 1e9
     traffic = None
     prof = ROOT / "profiles" / "k1_traffic.json"
-    if prof.exists():
+    if prof.exists() and c0.max_cache_length == 1024 and Hkv == 8:
         traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
     return {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": "cc_decode_kernel<128,4,naive>",
-            "us_per_launch": round(per_launch * 1e6, 3), "algorithmic_bytes_per_launch": alg_bytes,
+            "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": "cc_decode_kernel (one launch per layer)",
+            "us_per_launch": round(per_launch * 1e6, 3), "algorithmic_bytes_per_launch": int(alg_bytes),
             "peak_source": peak_src, "launches_timed": len(times) * len(caches),
-            "method": "32 per-layer launches per CUDA-graph replay, CUDA events per replay, 256 MB L2 flush between replays"}
+            "method": "per-layer launches of one token per CUDA-graph replay, CUDA events per replay, 256 MB L2 flush between replays"}
 
 
 def run_ours(args):
@@ -193,6 +231,8 @@ def run_ours(args):
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     local = env_int("LOCAL_RANK", 0)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
+    cfg_id = args.config or (2 if world == 1 else 5)
+    cfg = CONFIGS[cfg_id]
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
     real_stdout = None
@@ -212,20 +252,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    model = build_gpu_model(device, world)
-    ck = cache_kwargs()
-    gu.setup_caches(model, SyntheticTokenizer(), device, PROMPT_LEN + MAX_NEW, ck)
+    model = build_gpu_model(device, world, cfg["model"])
+    ck = cache_kwargs(cfg)
+    P, MAXNEW = cfg["prompt"], cfg["max_new"]
+    gu.setup_caches(model, SyntheticTokenizer(vocab_size=model.config.vocab_size), device, P + MAXNEW, ck)
     torch.manual_seed(1234)
-    prompt = torch.randint(0, model.config.vocab_size, (PROMPT_LEN,), dtype=torch.int32, device=device)
+    prompt = torch.randint(0, model.config.vocab_size, (P,), dtype=torch.int32, device=device)
     with torch.no_grad():
         t0 = time.perf_counter()
-        tok, _ = gu.prefill(model, prompt.view(1, -1), torch.arange(PROMPT_LEN, device=device))
+        tok, _ = gu.prefill(model, prompt.view(1, -1), torch.arange(P, device=device))
         torch.cuda.synchronize()
         prefill_s = time.perf_counter() - t0
         decoder = gu.GraphedDecoder()
-        input_pos = torch.tensor([PROMPT_LEN], dtype=torch.int32, device=device)
+        input_pos = torch.tensor([P], dtype=torch.int32, device=device)
         tok = tok.view(1, 1).clone()
-        assert PROMPT_LEN + args.warmup + 2 * args.steps + 128 < model.config.block_size, "too many steps for the RoPE table"
+        assert P + args.warmup + 2 * args.steps + 128 < model.config.block_size, "too many steps for the RoPE table"
 
         def step_device(tok):
             nxt, _ = decoder(model, tok, input_pos)
@@ -274,18 +315,50 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dev_s, e2e_s = times.tolist()
-        roof = k1_roofline(model, min(args.steps, 32), device) if rank == 0 and not os.environ.get("CC_BENCH_NCU") else None
+        token_kernel = model._tplan is not None
+        # one token streams every non-embedding weight of this rank plus the live K/V once
+        wbytes = sum(p.numel() * p.element_size() for n, p in model.named_parameters() if "tok_embeddings" not in n)
+        kvbytes = live_kv_bytes(model)
+        peak, peak_src = peaks()
+        roof = None
+        if rank == 0 and not os.environ.get("CC_BENCH_NCU"):
+            if token_kernel:
+                # the dominant (only) kernel of a step is cc_token_kernel: one launch per token, timed by the CUDA events
+                # around the K timed steps above; algorithmic bytes per launch = this rank's weights + live K/V rows
+                per_launch = dev_s / args.steps
+                achieved = (wbytes + kvbytes) / per_launch / 1e9
+                traffic = None
+                prof = ROOT / "profiles" / "r2" / "token_traffic.json"
+                if prof.exists() and cfg_id == 2 and world == 1:
+                    traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+                roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                        "frac": round(achieved / peak, 4), "traffic": traffic,
+                        "kernel": "cc_token_kernel (one persistent launch per decoded token: all layers, head, sampling)",
+                        "us_per_launch": round(per_launch * 1e6, 1), "algorithmic_bytes_per_launch": int(wbytes + kvbytes),
+                        "algorithmic_bytes": {"weights": int(wbytes), "live_kv": int(kvbytes)},
+                        "peak_source": peak_src, "launches_timed": args.steps,
+                        "method": "CUDA events around the K timed steps (one launch each); inputs of a step (weights + K/V) exceed L2"}
+                if args.k1:
+                    roof["per_layer_kernel"] = k1_roofline(model, min(args.steps, 32), device, int(input_pos.item()))
+            else:
+                roof = k1_roofline(model, min(args.steps, 32), device, int(input_pos.item()))
     ours_per_step = model.kernels_per_token() if model.fused_decode else model.config.n_layer
+    par = "none"
+    if world > 1:
+        par = (f"tp{world} (tp.py head / column sharding; " +
+               ("all-reduces inside the whole-token kernel, NVLink stores)" if token_kernel else
+                "fused NVLink exchange between per-layer kernels)" if getattr(model, "tp_link", None) is not None else "NCCL all-reduce)"))
+    elif int(os.environ.get("CC_TP_FAKE", "0")) > 1:
+        par = f"DIAGNOSTIC: rank-0 shard of tp{os.environ['CC_TP_FAKE']}, exchanges skipped"
     out = {
-        "metric": METRIC, "value": round(args.steps / dev_s, 2), "unit": "tokens/s", "n_gpus": world,
+        "metric": metric_name(cfg_id), "value": round(args.steps / dev_s, 2), "unit": "tokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(dev_s / args.steps * 1e3, 4),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{MODEL}-shape random-init bf16, heavy_hitter + SnapKV compression, "
-                               f"{CACHE_SLOTS} slots/layer, {PROMPT_LEN}-token synthetic prompt, decode @ 8k ctx",
-                   "global_batch": 1, "seq_len": PROMPT_LEN + MAX_NEW, "parallelism": (f"tp{world} ({'all-reduces inside the whole-token kernel (NVLink stores)' if model._tplan is not None else 'fused NVLink exchange' if getattr(model, 'tp_link', None) is not None else 'NCCL all-reduce'})"
-                                   if world > 1 else ("none" if not int(os.environ.get("CC_TP_FAKE", "0")) > 1 else
-                                                      f"DIAGNOSTIC: rank-0 shard of tp{os.environ['CC_TP_FAKE']}, exchanges skipped")),
-                   "l2": "per-step inputs (15 GB of weights + 134 MB of K/V) exceed the 126 MB L2",
+        "config": {"workload": f"BASELINE config {cfg_id}: {cfg['model']}-shape random-init bf16, {cfg['what']}",
+                   "global_batch": 1, "seq_len": P + MAXNEW, "parallelism": par,
+                   "decode_path": "one persistent kernel per token (cc_decode_token)" if token_kernel else
+                                  "per-layer kernels in one CUDA graph (" + str(getattr(model, "token_kernel_reason", "CC_TOKEN_KERNEL=0")) + ")",
+                   "l2": "per-step inputs (this rank's weights + live K/V) exceed the 126 MB L2",
                    "prefill_seconds": round(prefill_s, 2)},
         "e2e": {"value": round(args.steps / e2e_s, 2), "unit": "tokens/s", "h2d_bytes_per_step": 8,
                 "d2h_bytes_per_step": 4},
@@ -297,15 +370,10 @@ def run_ours(args):
         os.dup2(real_stdout, 1)
     if rank == 0:
         out["roofline"] = roof
-        # context for tokens/s: one token streams every non-embedding weight of this rank plus the live K/V once
-        wbytes = sum(p.numel() * p.element_size() for n, p in model.named_parameters() if "tok_embeddings" not in n)
-        kvbytes = sum(2 * c.n_heads * c.max_cache_length * c.head_dim * 2 for c in (b.attention.kv_cache for b in model.layers))
-        peak, _src = peaks()
         out["step_stream"] = {"bytes_per_token_per_gpu": wbytes + kvbytes, "achieved_gbs": round((wbytes + kvbytes) / (dev_s / args.steps) / 1e9, 1),
                               "frac_of_hbm_peak": round((wbytes + kvbytes) / (dev_s / args.steps) / 1e9 / peak, 4)}
-        out["cpu_baseline"] = (cpu_reference(sample_seconds=20.0, warmup=1)
-                               if world == 1 and not os.environ.get("CC_BENCH_NCU") and not os.environ.get("CC_TP_FAKE")
-                               and not os.environ.get("CC_BENCH_NOCPU") else None)
+        skip_cpu = world != 1 or os.environ.get("CC_BENCH_NCU") or os.environ.get("CC_TP_FAKE") or os.environ.get("CC_BENCH_NOCPU")
+        out["cpu_baseline"] = None if skip_cpu else cpu_baseline(cfg_id, sample_seconds=20.0, warmup=1)
         print(json.dumps(out), flush=True)
     if world > 1:
         # leave without tearing NCCL down: communicators captured in CUDA graphs make
@@ -318,36 +386,161 @@ def run_ours(args):
 
 # --------------------------------------------------------------------------- reference arm (host CPU)
 
-class CpuLayer:
-    """One transformer block on the host: torch CPU ops for the projections (what the reference
-    calls), oracle/ for the cache + attention step."""
+def usable_cores() -> int:
+    """Cores this process may use: min(affinity mask, cgroup CPU quota).  torchrun's OMP_NUM_THREADS=1 default is
+    NOT honoured here: the reference arm is one process that owns the host."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = Path("/sys/fs/cgroup/cpu.max").read_text().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
 
-    def __init__(self, cfg, block, seed):
+
+def _tiled(block, shape, gen):
+    """A bf16 tensor of `shape` made of shifted copies of one random block: memcpy-speed init, distinct memory."""
+    n = math.prod(shape)
+    shift = int(torch.randint(0, block.numel(), (1,), generator=gen))
+    return block.roll(shift).repeat(-(-n // block.numel()))[:n].view(*shape).contiguous()
+
+
+def load_reference():
+    """The unmodified reference's modules from baseline/_ref, or None."""
+    ref = ROOT / "baseline" / "_ref"
+    if not (ref / "generation_utils.py").exists():
+        return None
+    if str(ref) not in sys.path:
+        sys.path.insert(0, str(ref))
+    import importlib
+    mods = {n: importlib.import_module(n) for n in ("model", "cache", "generation_utils")}
+    for m in mods.values():
+        assert Path(m.__file__).resolve().parent == ref.resolve(), f"{m.__name__} resolved outside baseline/_ref"
+    return mods
+
+
+_REF_STATE = {}
+
+
+def reference_decoder(cfg_id):
+    """(step function, description) running the unmodified reference's decode_one_token on the host."""
+    if cfg_id in _REF_STATE:
+        return _REF_STATE[cfg_id]
+    mods = load_reference()
+    if mods is None:
+        return None
+    cfg = CONFIGS[cfg_id]
+    rmodel, rgu = mods["model"], mods["generation_utils"]
+    gen = torch.Generator().manual_seed(0)
+    block = (torch.randn(8 << 20, generator=gen) * 0.02).to(torch.bfloat16)
+    with torch.device("meta"):
+        model = rmodel.Transformer.from_name(cfg["model"])
+    model = model.to(dtype=torch.bfloat16).to_empty(device="cpu")
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            p.data = torch.ones(p.shape, dtype=torch.bfloat16) if "norm" in name else _tiled(block, tuple(p.shape), gen)
+    model.config.block_size = 32768
+    model.eval()
+    P, MAXNEW = cfg["prompt"], cfg["max_new"]
+    ck = cache_kwargs(cfg)
+    tokenizer = None
+    if cfg["strategy"] == "hybrid":
+        class _Tok:   # the two id lists hybrid caches ask the tokenizer for (tokenizer.py:55-63)
+            def special_ids(self):
+                return [[0], [1]]
+
+            def punctuation_ids(self):
+                return list(range(2, 34))
+        tokenizer = _Tok()
+    rgu.setup_caches(model, tokenizer, torch.device("cpu"), P + MAXNEW, ck)
+    # synthetic full post-prefill state (what the compressed prompt leaves behind): ascending kept positions incl.
+    # the global tokens and the recent tail, random K/V and scores
+    for layer in model.layers:
+        c = layer.attention.kv_cache
+        H, L, D = c.k_cache.shape[1], c.k_cache.shape[2], c.k_cache.shape[3]
+        live = min(L, P) if cfg["strategy"] != "hybrid" else 2048
+        c.k_cache[:, :, :live].copy_(_tiled(block, (1, H, live, D), gen))
+        c.v_cache[:, :, :live].copy_(_tiled(block, (1, H, live, D), gen))
+        keep = torch.sort(torch.randperm(P - 20, generator=gen)[: live - 20] + 4).values
+        pos = torch.cat([torch.arange(4), keep[: live - 20], torch.arange(P - 16, P)]).int()
+        c.pos[:, :, :live] = pos
+        c.mask[..., :live] = True
+        c.cache_cts.fill_(live)
+        if hasattr(c, "attn_history_num"):
+            c.attn_history_num[:, :, :live].copy_(torch.rand(c.attn_history_num[:, :, :live].shape, generator=gen).to(c.attn_history_num.dtype))
+            c.attn_history_denom[:, :, :live] = 1
+            c.attn_counter.fill_(1)
+        if hasattr(c, "key_norm"):
+            c.key_norm.copy_(torch.linalg.vector_norm(c.k_cache.float(), dim=-1).to(c.key_norm.dtype))
+        if cfg["strategy"] == "hybrid":
+            c.cache_strategies.fill_(1)   # window_heavy_hitter on every head
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+    state = {"tok": torch.tensor([[17]], dtype=torch.int32), "pos": torch.tensor([P], dtype=torch.int32)}
+
+    def step():
+        with torch.no_grad(), sdpa_kernel([SDPBackend.MATH]):   # as decode_n_tokens does (generation_utils.py:193-196)
+            nxt, _ = rgu.decode_one_token(model, state["tok"], state["pos"])
+        state["tok"] = nxt.view(1, 1)
+        state["pos"] += 1
+
+    desc = (f"the unmodified reference (baseline/_ref: its Transformer, KVCache classes and decode_one_token, torch CPU ops), "
+            f"{cfg['model']}-shape, {len(model.layers)} layers, caches in a synthetic full post-prefill state")
+    _REF_STATE[cfg_id] = (step, desc)
+    return _REF_STATE[cfg_id]
+
+
+def cpu_baseline(cfg_id, sample_seconds=20.0, warmup=1, steps=None):
+    """tokens/s of the reference's CPU path on the host cores (all usable cores), on a bounded sample."""
+    cores = usable_cores()
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    torch.set_num_threads(cores)
+    ref = None
+    try:
+        ref = reference_decoder(cfg_id)
+    except Exception as e:   # the installed reference could not be driven: say so and fall back to the port
+        sys.stderr.write(f"[bench] reference arm unavailable ({type(e).__name__}: {e}); falling back to the port\n")
+    if ref is not None:
+        step, desc = ref
+        kind = "reference"
+    else:
+        if cfg_id not in (2, 5):
+            return None
+        step, desc, kind = port_decoder(), ("port: GEMVs via torch CPU ops as the reference calls them, cache + attention via "
+                                            "oracle/cc_oracle.c (OpenMP)"), "port"
+    for _ in range(warmup):
+        step()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        step()
+        n += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and n >= steps) or (steps is None and el >= sample_seconds) or el > 240:
+            break
+    return {"value": round(n / el, 3), "unit": "tokens/s", "cores": cores, "kind": kind,
+            "sample": f"{n} full-model decode tokens in {el:.1f} s on {cores} threads; {desc}"}
+
+
+# ---- the port (only used when baseline/_ref is missing): torch CPU GEMVs + oracle/ cache step
+
+class CpuLayer:
+    def __init__(self, cfg, block, seed, slots, prompt):
         from oracle.oracle import OracleCache
-        D = cfg.head_dim
+        D = cfg["head_dim"]
         self.cfg = cfg
         g = torch.Generator().manual_seed(seed)
-
-        def w(*shape):  # tiled copies of one random block: memcpy-speed init, distinct memory per weight
-            n = math.prod(shape)
-            reps = -(-n // block.numel())
-            shift = int(torch.randint(0, block.numel(), (1,), generator=g))
-            return block.roll(shift).repeat(reps)[:n].view(*shape).contiguous()
-
-        kv = cfg.n_local_heads * D
-        self.wqkv, self.wo = w(cfg.dim + 2 * kv, cfg.dim), w(cfg.dim, cfg.dim)
-        self.w1, self.w3, self.w2 = w(cfg.intermediate_size, cfg.dim), w(cfg.intermediate_size, cfg.dim), \
-            w(cfg.dim, cfg.intermediate_size)
-        self.n1 = torch.ones(cfg.dim, dtype=torch.bfloat16)
-        self.n2 = torch.ones(cfg.dim, dtype=torch.bfloat16)
-        G = cfg.n_head // cfg.n_local_heads
-        oc = OracleCache("heavy_hitter", cfg.n_local_heads, G, D, CACHE_SLOTS, 4, 10, 1)
-        # synthetic post-prefill state: full cache, ascending kept positions incl. globals and the recent tail
-        H, L = cfg.n_local_heads, CACHE_SLOTS
-        oc.k_cache.copy_(w(H, L, D))
-        oc.v_cache.copy_(w(H, L, D))
-        keep = torch.sort(torch.randperm(PROMPT_LEN - 20, generator=g)[: L - 20] + 4).values
-        pos = torch.cat([torch.arange(4), keep[: L - 20], torch.arange(PROMPT_LEN - 16, PROMPT_LEN)]).int()
+        kv = cfg["n_kv"] * D
+        dim, inter = cfg["dim"], cfg["inter"]
+        self.wqkv, self.wo = _tiled(block, (dim + 2 * kv, dim), g), _tiled(block, (dim, dim), g)
+        self.w1, self.w3, self.w2 = _tiled(block, (inter, dim), g), _tiled(block, (inter, dim), g), _tiled(block, (dim, inter), g)
+        self.n1 = torch.ones(dim, dtype=torch.bfloat16)
+        self.n2 = torch.ones(dim, dtype=torch.bfloat16)
+        H, L = cfg["n_kv"], slots
+        oc = OracleCache("heavy_hitter", H, cfg["n_head"] // H, D, L, 4, 10, 1)
+        oc.k_cache.copy_(_tiled(block, (H, L, D), g))
+        oc.v_cache.copy_(_tiled(block, (H, L, D), g))
+        keep = torch.sort(torch.randperm(prompt - 20, generator=g)[: L - 20] + 4).values
+        pos = torch.cat([torch.arange(4), keep[: L - 20], torch.arange(prompt - 16, prompt)]).int()
         oc.pos.copy_(pos.expand(H, L))
         oc.mask.fill_(True)
         oc.cache_cts.fill_(L)
@@ -356,107 +549,79 @@ class CpuLayer:
         self.cache = oc
 
     @staticmethod
-    def rmsnorm(x, wt, eps):
+    def rmsnorm(x, wt, eps=1e-5):
         xf = x.float()
         return (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).type_as(x) * wt
 
+    @staticmethod
+    def rope(x, fc):
+        xs = x.float().reshape(*x.shape[:-1], -1, 2)
+        fc = fc.view(1, xs.size(1), 1, xs.size(3), 2)
+        re = xs[..., 0] * fc[..., 0] - xs[..., 1] * fc[..., 1]
+        im = xs[..., 1] * fc[..., 0] + xs[..., 0] * fc[..., 1]
+        return torch.stack([re, im], -1).flatten(3).type_as(x)
+
     def forward(self, x, freqs, pos):
-        from cold_compress_b200.model import apply_rotary_emb
         cfg = self.cfg
         F = torch.nn.functional
-        D, Hq, Hkv = cfg.head_dim, cfg.n_head, cfg.n_local_heads
-        h = self.rmsnorm(x, self.n1, cfg.norm_eps)
+        D, Hq, Hkv = cfg["head_dim"], cfg["n_head"], cfg["n_kv"]
+        h = self.rmsnorm(x, self.n1)
         q, k, v = F.linear(h, self.wqkv).split([Hq * D, Hkv * D, Hkv * D], dim=-1)
-        q = apply_rotary_emb(q.view(1, 1, Hq, D), freqs)
-        k = apply_rotary_emb(k.view(1, 1, Hkv, D), freqs)
+        q = self.rope(q.view(1, 1, Hq, D), freqs)
+        k = self.rope(k.view(1, 1, Hkv, D), freqs)
         y, _, _ = self.cache.decode_step(q.reshape(Hq, D), k.reshape(Hkv, D), v.reshape(Hkv, D).contiguous(), pos)
         x = x + F.linear(y.view(1, 1, Hq * D), self.wo)
-        h = self.rmsnorm(x, self.n2, cfg.norm_eps)
+        h = self.rmsnorm(x, self.n2)
         return x + F.linear(F.silu(F.linear(h, self.w1)) * F.linear(h, self.w3), self.w2)
 
 
-_CPU_MODEL = None
+_PORT = None
 
 
-def cpu_model():
-    global _CPU_MODEL
-    if _CPU_MODEL is None:
-        from cold_compress_b200.model import ModelArgs, precompute_freqs_cis
-        cfg = ModelArgs.from_name(MODEL)
-        cfg.block_size = 16384
+def port_decoder():
+    global _PORT
+    if _PORT is None:
+        cfg = dict(dim=4096, inter=14336, n_head=32, n_kv=8, head_dim=128, n_layer=32, vocab=128256)
         torch.manual_seed(0)
         block = (torch.randn(8 << 20) * 0.02).to(torch.bfloat16)
-        layers = [CpuLayer(cfg, block, 100 + i) for i in range(cfg.n_layer)]
-        emb = (torch.randn(4096, cfg.dim) * 0.02).to(torch.bfloat16)  # only rows actually looked up matter
-        out_w = block.repeat(-(-cfg.vocab_size * cfg.dim // block.numel()))[: cfg.vocab_size * cfg.dim].view(
-            cfg.vocab_size, cfg.dim)
-        freqs = precompute_freqs_cis(cfg.block_size, cfg.head_dim, cfg.rope_base, torch.bfloat16)
-        _CPU_MODEL = (cfg, layers, emb, out_w, freqs)
-    return _CPU_MODEL
+        layers = [CpuLayer(cfg, block, 100 + i, 1024, 7680) for i in range(cfg["n_layer"])]
+        emb = (torch.randn(4096, cfg["dim"]) * 0.02).to(torch.bfloat16)
+        out_w = _tiled(block, (cfg["vocab"], cfg["dim"]), torch.Generator().manual_seed(5))
+        half = cfg["head_dim"] // 2
+        inv = 1.0 / (500000 ** (torch.arange(0, cfg["head_dim"], 2)[:half].float() / cfg["head_dim"]))
+        state = {"tok": 17, "pos": 7680}
 
-
-def cpu_decode_token(tok, pos):
-    cfg, layers, emb, out_w, freqs = cpu_model()
-    x = emb[tok % emb.shape[0]].view(1, 1, -1)
-    fr = freqs[pos: pos + 1]
-    for layer in layers:
-        x = layer.forward(x, fr, pos)
-    logits = torch.nn.functional.linear(CpuLayer.rmsnorm(x, layers[0].n1, cfg.norm_eps), out_w)
-    return int(torch.argmax(torch.softmax(logits[0, -1].float(), dim=-1)))
-
-
-def usable_cores() -> int:
-    """Cores this process may actually use: min(affinity mask, cgroup CPU quota, OMP_NUM_THREADS)."""
-    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    try:
-        quota, period = Path("/sys/fs/cgroup/cpu.max").read_text().split()[:2]
-        if quota != "max":
-            n = min(n, max(1, int(int(quota) / int(period))))
-    except (OSError, ValueError):
-        pass
-    if os.environ.get("OMP_NUM_THREADS", "").isdigit():
-        n = min(n, int(os.environ["OMP_NUM_THREADS"]))
-    return max(1, n)
-
-
-def cpu_reference(sample_seconds=20.0, warmup=1, steps=None):
-    """tokens/s of the reference's CPU path (port): whole-model decode on the host cores."""
-    from oracle import oracle
-    # usable cores = the affinity mask (a container may see 128 logical CPUs but own 32; oversubscribing
-    # torch's intra-op pool beyond that collapses its GEMV throughput by 60x)
-    cores = usable_cores()
-    torch.set_num_threads(cores)
-    cpu_model()
-    tok, pos = 17, PROMPT_LEN
-    for _ in range(warmup):
-        tok = cpu_decode_token(tok, pos)
-        pos += 1
-    n, t0 = 0, time.perf_counter()
-    while True:
-        tok = cpu_decode_token(tok, pos)
-        pos += 1
-        n += 1
-        el = time.perf_counter() - t0
-        if (steps is not None and n >= steps) or (steps is None and el >= sample_seconds) or el > 240:
-            break
-    return {"value": round(n / el, 3), "unit": "tokens/s", "cores": cores, "kind": "port",
-            "sample": f"{n} full-model decode tokens ({MODEL}-shape, 32 layers, 1024-slot heavy_hitter caches in a "
-                      f"synthetic full post-prefill state) in {el:.1f} s; GEMVs via torch CPU ops as the reference "
-                      f"calls them, cache+attention via oracle/cc_oracle.c with {oracle.threads()} OpenMP threads"}
+        def step():
+            pos = state["pos"]
+            ang = pos * inv
+            fr = torch.stack([torch.cos(ang), torch.sin(ang)], -1).to(torch.bfloat16).view(1, half, 2)
+            x = emb[state["tok"] % emb.shape[0]].view(1, 1, -1)
+            for layer in layers:
+                x = layer.forward(x, fr, pos)
+            logits = torch.nn.functional.linear(CpuLayer.rmsnorm(x, layers[0].n1), out_w)
+            state["tok"] = int(torch.argmax(torch.softmax(logits[0, -1].float(), dim=-1)))
+            state["pos"] += 1
+        _PORT = step
+    return _PORT
 
 
 def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
-    base = cpu_reference(warmup=max(1, min(args.warmup, 3)), steps=args.steps)
+    cfg_id = args.config or (2 if args.gpus == 1 else 5)
+    cfg = CONFIGS[cfg_id]
+    base = cpu_baseline(cfg_id, warmup=max(1, min(args.warmup, 3)), steps=args.steps)
+    if base is None:
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref is missing and the port only covers configs 2 and 5"}), flush=True)
+        return
     n = int(base["sample"].split()[0])
-    out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "tokens/s", "n_gpus": args.gpus,
+    out = {"impl": "reference", "metric": metric_name(cfg_id), "value": base["value"], "unit": "tokens/s", "n_gpus": args.gpus,
            "steps": n, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": round(1e3 / base["value"], 3),
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-           "config": {"workload": f"{MODEL}-shape random-init bf16, heavy_hitter, {CACHE_SLOTS} slots/layer, decode @ 8k ctx "
-                                  "(reference CPU path, host cores)", "global_batch": 1,
-                      "seq_len": PROMPT_LEN + MAX_NEW, "parallelism": "none"},
+           "config": {"workload": f"BASELINE config {cfg_id}: {cfg['model']}-shape random-init bf16, {cfg['what']} "
+                                  "(reference CPU path on the host cores, unsharded)",
+                      "global_batch": 1, "seq_len": cfg["prompt"] + cfg["max_new"], "parallelism": "none"},
            "cpu_baseline": base,
            "e2e": {"value": base["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -469,6 +634,9 @@ def main():
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=0, choices=[0, 1, 2, 3, 4, 5],
+                    help="BASELINE.json config (default: 2 on one GPU, 5 = pyramid lengths under head sharding on several)")
+    ap.add_argument("--k1", action="store_true", help="also time the per-layer decode kernel (cc_decode_step) alone")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

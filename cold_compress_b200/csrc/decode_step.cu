@@ -871,20 +871,24 @@ static int g_smem_optin = 0;
 static unsigned long long* g_trace = nullptr;  // diagnostics only (cc_debug_set_trace)
 void set_trace_buffer(unsigned long long* buf) { g_trace = buf; }
 
+static int g_limits_dev = -1;
 static int device_limits() {
-    if (g_num_sms) return CC_OK;
     int dev = 0;
+    cudaGetDevice(&dev);
+    if (g_num_sms && g_limits_dev == dev) return CC_OK;
+    g_num_sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return set_error(CC_ERR_NO_DEVICE, "no CUDA device");
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return set_error(CC_ERR_NO_DEVICE, "cudaGetDeviceProperties failed");
     if (prop.major != 10) return set_error(CC_ERR_NO_DEVICE, "this library is built for sm_100a (Blackwell B200) only");
     g_num_sms = prop.multiProcessorCount;
     g_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    g_limits_dev = dev;
     return CC_OK;
 }
 
 // Plans are cached per (shape, policy class): the occupancy query is not free.
-struct PlanKey { int D, G, naive, H, L, policy; };
+struct PlanKey { int D, G, naive, H, L, policy, dev; };
 struct PlanEntry { PlanKey k; LaunchPlan p; };
 static PlanEntry g_plans[128];
 static int g_nplans = 0;
@@ -892,9 +896,11 @@ static int g_nplans = 0;
 static int make_plan(const CcCacheState* st, bool needs_epoch, LaunchPlan* out) {
     const int D = st->head_dim, G = st->q_per_kv, H = st->n_kv_heads, L = st->max_cache_length;
     const bool naive = st->attn_mode == CC_ATTN_NAIVE_BF16;
+    int dev = 0;
+    cudaGetDevice(&dev);   // plans (occupancy, shared-memory limits) belong to a device
     for (int i = 0; i < g_nplans; ++i) {
         const PlanKey& k = g_plans[i].k;
-        if (k.D == D && k.G == G && k.naive == (int)naive && k.H == H && k.L == L && k.policy == st->policy) {
+        if (k.D == D && k.G == G && k.naive == (int)naive && k.H == H && k.L == L && k.policy == st->policy && k.dev == dev) {
             *out = g_plans[i].p;
             return CC_OK;
         }
@@ -938,10 +944,11 @@ static int make_plan(const CcCacheState* st, bool needs_epoch, LaunchPlan* out) 
             if (getenv("CC_B200_DEBUG_PLAN"))
                 fprintf(stderr, "[cc plan] D=%d G=%d policy=%d L=%d: C=%d stages=%d smem=%u max_active_clusters=%d\n", D, G,
                         st->policy, L, C, ns, lay.total, max_clusters);
-            if (max_clusters < H && C > 1) continue;
-            (void)needs_epoch;
+            // (the epoch barrier spins on the other heads' clusters: without co-residency it would never complete,
+            // whatever the cluster size)
+            if (max_clusters < H && (C > 1 || needs_epoch)) continue;
             LaunchPlan p = {fn, C, chs, mlc, ns, stride, lay.total};
-            if (g_nplans < 128) g_plans[g_nplans++] = {{D, G, (int)naive, H, L, st->policy}, p};
+            if (g_nplans < 128) g_plans[g_nplans++] = {{D, G, (int)naive, H, L, st->policy, dev}, p};
             *out = p;
             return CC_OK;
         }

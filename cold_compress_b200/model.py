@@ -313,6 +313,8 @@ class Transformer(nn.Module):
                 attn_top_k: Optional[float] = 1.0) -> Tensor:
         assert self.freqs_cis is not None, "Caches must be initialized first"
         if not is_prefill and self._fused_ready(idx):
+            # the fused kernels attend over every live slot: top-k decode attention is refused, not ignored
+            assert attn_top_k in (None, 1, 1.0), "top-k decode attention is not supported with cache masks"
             return self._decode_fused(idx, input_pos)
         freqs_cis = self.freqs_cis[input_pos]
         x = self.tok_embeddings(idx)

@@ -8,6 +8,7 @@ small fixed sets.  `get_tokenizer` returns it when no tokenizer file exists next
 """
 from __future__ import annotations
 
+import zlib
 from pathlib import Path
 
 import torch
@@ -45,7 +46,12 @@ class SyntheticTokenizer(TokenizerInterface):
         self.vocab_size = vocab_size
 
     def encode(self, text):
-        return [1 + (hash(w) % (self.vocab_size - 2)) for w in str(text).split()]
+        # a stable hash: the same ids in every process (Python's hash() is salted per process, which would give the
+        # ranks of a tensor-parallel run different prompts)
+        return [2 + (zlib.crc32(w.encode()) % (self.vocab_size - 2)) for w in str(text).split()]
+
+    def encode_prompt(self, prompt):
+        return [self.bos_id()] + self.encode(prompt)
 
     def decode(self, tokens):
         return " ".join(str(int(t)) for t in tokens)
@@ -67,12 +73,25 @@ class SyntheticTokenizer(TokenizerInterface):
 
 
 def get_tokenizer(tokenizer_model_path, model_name=None, is_chat=False):
+    """Synthetic ids when there is no tokenizer file next to the checkpoint.  Real tokenizers (SentencePiece /
+    tiktoken / HF) are not part of the hot path and are not re-implemented here: the reference's own tokenizer.py has
+    the same interface and is NOT shadowed by dropin/ -- its scripts keep using it."""
     path = Path(str(tokenizer_model_path))
     if path.is_file() or (path.is_dir() and (path / "tokenizer.json").exists()):
-        raise NotImplementedError("real tokenizers are outside this build: use the reference's tokenizer.py "
-                                  "(same interface) next to this package")
+        raise NotImplementedError("a tokenizer file was found: use the reference's tokenizer.py (same interface); "
+                                  "cold_compress_b200.tokenizer only provides synthetic ids")
     return SyntheticTokenizer()
 
 
-def encode(tokenizer, string, device="cuda", is_chat=True):
-    return torch.tensor(tokenizer.encode(string), dtype=torch.int, device=device)
+def encode_tokens(tokenizer, string, bos=True, device="cuda"):
+    tokens = tokenizer.encode(string)
+    if bos:
+        tokens = [tokenizer.bos_id()] + tokens
+    return torch.tensor(tokens, dtype=torch.int, device=device)
+
+
+def encode(tokenizer, prompt, device="cuda", bos=True, is_chat=True):
+    """Same signature and meaning as the reference (tokenizer.py:335-349)."""
+    if is_chat:
+        return torch.tensor(tokenizer.encode_prompt(prompt), dtype=torch.int, device=device)
+    return encode_tokens(tokenizer, prompt, device=device, bos=bos)

@@ -117,7 +117,8 @@ class FusedExchange:
         import torch.distributed._symmetric_memory as symm
         group = group or dist.group.WORLD
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        assert 2 <= self.world <= 8
+        # the in-kernel collection reads the ranks in pairs (csrc/gemv.cu tp_collect): even worlds only
+        assert self.world in (2, 4, 8), f"the fused exchange supports 2, 4 or 8 ranks, not {self.world}"
         self.dim = model.output.in_features
         self.n_ops = 2 * len(model.layers)
         dev = model.output.weight.device

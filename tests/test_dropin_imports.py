@@ -13,7 +13,6 @@ NEEDED = {
                          "print_stats", "generate", "get_model_size", "load_model", "merge_cache_config",
                          "setup_caches", "decode_n_tokens", "prefill", "decode_one_token", "reset_caches",
                          "get_cache_stats", "normalize_cache_length", "apply_pattern"],
-    "tokenizer": ["get_tokenizer", "encode", "TokenizerInterface"],
     "tp": ["maybe_init_dist", "apply_tp"],
     "model": ["Transformer", "Attention", "FeedForward", "TransformerBlock", "ModelArgs", "find_multiple",
               "transformer_configs", "precompute_freqs_cis", "apply_rotary_emb", "RMSNorm"],
@@ -45,10 +44,28 @@ def test_dropin_modules_export_what_generate_py_imports():
             assert "cold_compress_b200" in (module.__doc__ or ""), f"{mod} resolved to a foreign module"
             for n in names:
                 assert hasattr(module, n), f"{mod}.{n} missing"
+        # the tokenizer is NOT shadowed: the reference's scripts keep their own tokenizer.py
+        assert not (ROOT / "cold_compress_b200" / "dropin" / "tokenizer.py").exists()
     finally:
         sys.path.pop(0)
         for mod in NEEDED:
             sys.modules.pop(mod, None)
+
+
+def test_synthetic_tokenizer_matches_reference_interface():
+    import inspect
+    import subprocess
+    from cold_compress_b200 import tokenizer as tk
+    t = tk.SyntheticTokenizer(vocab_size=1000)
+    ids = tk.encode(t, "a quick brown fox", device="cpu", bos=False, is_chat=False)
+    assert ids.dtype.is_floating_point is False and ids.numel() == 4 and int(ids.max()) < 1000
+    assert tk.encode(t, "a quick brown fox", device="cpu", is_chat=True)[0] == t.bos_id()
+    assert list(inspect.signature(tk.encode).parameters) == ["tokenizer", "prompt", "device", "bos", "is_chat"]
+    # stable across processes (tensor-parallel ranks must see the same prompt)
+    out = subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, %r); from cold_compress_b200 import tokenizer as tk; "
+                          "print(tk.SyntheticTokenizer(vocab_size=1000).encode('a quick brown fox'))" % str(ROOT)],
+                         capture_output=True, text=True, env={"PYTHONHASHSEED": "123", "PATH": "/usr/bin:/bin"})
+    assert out.stdout.strip() == str(t.encode("a quick brown fox")), out.stderr[-500:]
 
 
 def test_cli_arguments_match_reference_defaults():
