@@ -41,13 +41,28 @@ namespace cc {
 #ifndef CC_TOKEN_WARPS
 #define CC_TOKEN_WARPS 8
 #endif
-constexpr int kTW = CC_TOKEN_WARPS;    // warps per CTA (8 or 16)
-constexpr int kTT = kTW * 32;          // threads per CTA
+#ifndef CC_TOKEN_PRODUCER
+#define CC_TOKEN_PRODUCER 1
+#endif
+constexpr int kTW = CC_TOKEN_WARPS;    // consumer warps per CTA (8 or 16)
+constexpr int kTT = kTW * 32;          // consumer threads per CTA
+constexpr bool kProducer = CC_TOKEN_PRODUCER != 0;   // one extra warp owns every ring's fetch cursor
+// The producer warp comes with a whole warpgroup (setmaxnreg works on aligned groups of 4 warps): registers are
+// dealt per scheduler, so a 9th warp alone would cap every thread at 168 registers; instead the kernel starts at
+// 168 (384 threads), the producer warpgroup shrinks to kProducerRegs and the two consumer warpgroups grow to
+// kConsumerRegs (128 * 40 + 256 * 232 = 64512 <= 65536).
+constexpr int kLaunchThreads = kTT + (kProducer ? 128 : 0);
+constexpr int kProducerRegs = 40, kConsumerRegs = 232;
+static_assert(!kProducer || kTW == 8, "the producer warpgroup layout assumes 8 consumer warps");
+// CTA-wide barrier of the consumer warps (the producer warp never joins it)
+__device__ __forceinline__ void cta_sync() {
+    if (kProducer) asm volatile("bar.sync 1, %0;" :: "n"(kTT) : "memory");
+    else __syncthreads();
+}
 constexpr uint32_t kStage = 65536 / kTW;   // bytes per ring stage: 8 KiB (8 warps) / 4 KiB (16 warps)
 constexpr int kRedWarps = kTW < 8 ? kTW : 8;   // P.V partials are reduced through 8 shared-memory slots
 constexpr int kTokMaxWorld = 8;
 constexpr int kTokMaxG = 8;
-constexpr int kOutStage = 64;          // row pairs a CTA can stage for a coalesced peer push
 constexpr uint64_t kNoKey64 = ~0ull;
 
 enum : int { TOK_QKV = 0, TOK_ATTN = 1, TOK_GEMV = 2, TOK_GATE = 3, TOK_HEAD = 4 };
@@ -62,7 +77,7 @@ struct TokOp {
     int32_t seg_len;      // elements of a row per ring stage (multiple of 256)
     int32_t n_seg;        // ceil(K / seg_len)
     int32_t rot;          // rotation of the CTA dealing (spreads the +1 row groups over CTAs from stage to stage)
-    int32_t layer;
+    int32_t grp_base;     // n_groups / n_ctas (dealt on the host: no integer division in the kernel)
     int32_t in_kind;      // IN_TOKEN: embedding row of the input token; IN_LL: in_world partial vectors at in_off
     int32_t in_world;
     int32_t res_kind;     // residual added to the (summed) input: none / embedding row / flag-in-data vector at res_off
@@ -70,7 +85,7 @@ struct TokOp {
     int32_t out_world;    // TOK_GEMV: ranks the partial output is stored to (1 = this rank only)
     int32_t attn;         // TOK_ATTN: index into the attention table
     float eps;
-    int32_t pad;
+    int32_t grp_rem;      // n_groups % n_ctas
     uint64_t in_off, res_off, sum_off, out_off;   // byte offsets inside the scratch (identical on every rank)
     const __nv_bfloat16 *norm_w, *w, *w3, *bias;
 };
@@ -225,14 +240,27 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 }
 
 // ------------------------------------------------------------------ dealing of work to CTAs and warps
-// matrix-vector stage: CTA c owns row groups [g0, g0 + n); warp w of the CTA owns local groups w, w + 8, ...
-__device__ __forceinline__ void deal_groups(int n_groups, int rot, int* g0, int* n) {
+// matrix-vector stage: CTA c owns row groups [g0, g0 + n).  Inside the CTA the unit of work is a TILE = (group,
+// segment) pair = one ring stage: tile t = j * n_seg + s of the CTA goes to warp t % kTW, so the warps of a CTA differ
+// by at most one tile (dealing whole groups left warps with 1 or 2 groups of 7 tiles each in the w2 stage: the stage
+// then ended with a few warps crawling through a latency-bound tail while the others sat on full rings).
+__device__ __forceinline__ void deal_groups(const TokOp& op, int* g0, int* n) {
     const int nc = (int)gridDim.x;
-    int c = (int)blockIdx.x + rot;
+    int c = (int)blockIdx.x + op.rot;
     if (c >= nc) c -= nc;
-    const int base = n_groups / nc, rem = n_groups - base * nc;
-    *g0 = c * base + min(c, rem);
-    *n = base + (c < rem ? 1 : 0);
+    *g0 = c * op.grp_base + min(c, op.grp_rem);
+    *n = op.grp_base + (c < op.grp_rem ? 1 : 0);
+}
+// first tile of warp `w`: (j, s) with j * n_seg + s == w
+__device__ __forceinline__ void first_tile(int w, int n_seg, int* j, int* s) {
+    int jj = 0, ss = w;
+    while (ss >= n_seg) { ss -= n_seg; ++jj; }
+    *j = jj; *s = ss;
+}
+__device__ __forceinline__ void next_tile(int n_seg, int* j, int* s) {
+    int jj = *j, ss = *s + kTW;
+    while (ss >= n_seg) { ss -= n_seg; ++jj; }
+    *j = jj; *s = ss;
 }
 // attention stage: CTA unit u < H * C works on KV head u / C as rank u % C of that head; chunk j of rank r is
 // global chunk r + j * C; warp w owns rows [w * RW, (w + 1) * RW) of every chunk
@@ -266,12 +294,11 @@ __device__ __forceinline__ void attn_warp_rows(const TokAttn& A, int rank, int j
 struct TileIter {
     int op;                 // current stage index (>= n_ops: exhausted)
     int type;
-    int j, nj;              // matrix-vector: local group index / count; attention: tile index / 2 * nlc
+    int j, nj;              // matrix-vector: group index / groups of this CTA; attention: tile index / 2 * nlc
     int s, ns;              // segment index / count
-    const uint8_t* src;     // matrix-vector: first row segment of the current tile
+    const uint8_t* base;    // matrix-vector: first row of the CTA's first group
     uint32_t seg_bytes, last_bytes;   // bytes of a full / of the last segment of a row
     uint32_t row_bytes;     // K * 2
-    long long group_step;   // from the last segment of a group to the first segment of the warp's next group
     long long w3_delta;     // FFN gate: w3 - w1
     int rank, h;            // attention
     const TokAttn* a;
@@ -299,15 +326,15 @@ __device__ __forceinline__ void iter_enter(TileIter& it, const TokParams& P, con
             if (it.j < it.nj) return;
         } else {
             int g0, n;
-            deal_groups(o->n_groups, o->rot, &g0, &n);
-            if (warp >= n) continue;
+            deal_groups(*o, &g0, &n);
+            first_tile(warp, o->n_seg, &it.j, &it.s);
+            if (it.j >= n) continue;
             const int K = o->K;
-            it.nj = n; it.j = warp; it.s = 0; it.ns = o->n_seg;
+            it.nj = n; it.ns = o->n_seg;
             it.row_bytes = (uint32_t)K * 2;
             it.seg_bytes = (uint32_t)o->seg_len * 2;
             it.last_bytes = (uint32_t)(K - (o->n_seg - 1) * o->seg_len) * 2;
-            it.src = reinterpret_cast<const uint8_t*>(o->w) + (size_t)(2 * (g0 + warp)) * it.row_bytes;
-            it.group_step = (long long)(2 * kTW) * it.row_bytes - (long long)(o->n_seg - 1) * it.seg_bytes;
+            it.base = reinterpret_cast<const uint8_t*>(o->w) + (size_t)(2 * g0) * it.row_bytes;
             it.w3_delta = o->type == TOK_GATE ? reinterpret_cast<const uint8_t*>(o->w3) - reinterpret_cast<const uint8_t*>(o->w) : 0;
             return;
         }
@@ -315,16 +342,17 @@ __device__ __forceinline__ void iter_enter(TileIter& it, const TokParams& P, con
 }
 __device__ __forceinline__ void iter_advance(TileIter& it, const TokParams& P, const DescWindow* W, int warp) {
     if (it.type != TOK_ATTN) {
-        if (++it.s < it.ns) { it.src += it.seg_bytes; return; }
-        it.s = 0;
-        it.j += kTW;
-        if (it.j < it.nj) { it.src += it.group_step; return; }
+        next_tile(it.ns, &it.j, &it.s);
+        if (it.j < it.nj) return;
     } else {
         for (++it.j; it.j < it.nj && !iter_tile_valid(it, warp); ++it.j) {}
         if (it.j < it.nj) return;
     }
     ++it.op;
     iter_enter(it, P, W, warp);
+}
+__device__ __forceinline__ const uint8_t* iter_src(const TileIter& it) {
+    return it.base + (size_t)(2 * it.j) * it.row_bytes + (size_t)it.s * it.seg_bytes;
 }
 // issue the TMA copies of the cursor's tile into a ring stage (one lane).  Weights and cache rows are read once
 // per token: lowest L2 retention priority, so that the 15 GB stream does not evict the exchange words and the
@@ -344,44 +372,91 @@ __device__ __forceinline__ void iter_issue(const TileIter& it, int warp, uint8_t
         return;
     }
     const uint32_t bytes = it.s + 1 == it.ns ? it.last_bytes : it.seg_bytes;
+    const uint8_t* src = iter_src(it);
     if (it.type == TOK_GATE) {
         mbar_expect_tx(bar, 4 * bytes);
-        tma_load_1d_hint(stage, it.src, bytes, bar, pol);
-        tma_load_1d_hint(stage + bytes, it.src + it.row_bytes, bytes, bar, pol);
-        tma_load_1d_hint(stage + 2 * bytes, it.src + it.w3_delta, bytes, bar, pol);
-        tma_load_1d_hint(stage + 3 * bytes, it.src + it.w3_delta + it.row_bytes, bytes, bar, pol);
+        tma_load_1d_hint(stage, src, bytes, bar, pol);
+        tma_load_1d_hint(stage + bytes, src + it.row_bytes, bytes, bar, pol);
+        tma_load_1d_hint(stage + 2 * bytes, src + it.w3_delta, bytes, bar, pol);
+        tma_load_1d_hint(stage + 3 * bytes, src + it.w3_delta + it.row_bytes, bytes, bar, pol);
     } else {
         mbar_expect_tx(bar, 2 * bytes);
-        tma_load_1d_hint(stage, it.src, bytes, bar, pol);
-        tma_load_1d_hint(stage + bytes, it.src + it.row_bytes, bytes, bar, pol);
+        tma_load_1d_hint(stage, src, bytes, bar, pol);
+        tma_load_1d_hint(stage + bytes, src + it.row_bytes, bytes, bar, pol);
     }
 }
 
 // ------------------------------------------------------------------ the per-warp ring
+// Stage s of warp w: a "full" mbarrier (armed with expect_tx by whoever issues the copies, completed by the TMA
+// engine) and, with the producer warp, an "empty" mbarrier (one arrival by the consumer warp's lane 0).
 struct Ring {
     uint8_t* stages;      // this warp's stages
-    uint64_t* bars;       // this warp's mbarriers
+    uint64_t* bars;       // this warp's full barriers
+    uint64_t* empty;      // this warp's empty barriers (producer mode)
     int ns, cs;           // number of stages, stage the consumer reads next
-    uint32_t phases;      // parity of the next completion of each stage's barrier
+    uint32_t phases;      // parity of the next completion of each stage's full barrier
     const DescWindow* win;
     uint64_t policy;      // L2 eviction priority of the streamed tiles (created once)
-    TileIter it;          // fetch cursor; only lane 0's copy is meaningful
+    TileIter it;          // fetch cursor (self-refill mode: lane 0's copy; producer mode: unused)
 };
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ const uint8_t* ring_wait(Ring& r) {
     mbar_wait(&r.bars[r.cs], (r.phases >> r.cs) & 1u);
     return r.stages + (size_t)r.cs * kStage;
 }
-// the warp is done with the current stage: re-arm it with the next tile of the warp's sequence
+// the warp is done with the current stage.  Producer mode: hand it back (one mbarrier arrival; the producer warp
+// re-arms it with the next tile of this warp's sequence).  Self-refill mode: lane 0 re-arms it itself.
 __device__ __forceinline__ void ring_release(Ring& r, const TokParams& P, int warp, int lane) {
     __syncwarp();
     // (no proxy fence: the stage was only READ through the generic proxy; the warp barrier above orders those
-    // reads before the copy that overwrites it, as in any TMA producer / consumer ring)
-    if (lane == 0 && r.it.op < P.n_ops) {
+    // reads before the arrival / the copy that overwrites it, as in any TMA producer / consumer ring)
+    if (kProducer) {
+        if (lane == 0) mbar_arrive(&r.empty[r.cs]);
+    } else if (lane == 0 && r.it.op < P.n_ops) {
         iter_issue(r.it, warp, r.stages + (size_t)r.cs * kStage, &r.bars[r.cs], r.policy);
         iter_advance(r.it, P, r.win, warp);
     }
     r.phases ^= 1u << r.cs;
     r.cs = r.cs + 1 == r.ns ? 0 : r.cs + 1;
+}
+// The producer warp: lane w owns the fetch cursor of consumer warp w's ring.  All lanes poll their ring's next
+// empty barrier with ONE non-blocking test per round (the lanes stay converged), the lanes whose stage is free issue
+// its copies and advance their cursor.  The ~500-cycle serial section of a refill (expect_tx, 2-4 bulk copies, cursor
+// arithmetic) is off the consumers' path, and eight refills cost one pass.
+__device__ void producer_loop(const TokParams& P, const DescWindow* W, uint8_t* ring_base, uint64_t* full, uint64_t* empty, int lane) {
+    if (lane >= kTW) return;
+    const int ns = P.n_stages;
+    uint8_t* stages = ring_base + (size_t)lane * ns * kStage;
+    uint64_t* fb = full + lane * ns;
+    uint64_t* eb = empty + lane * ns;
+    const uint64_t policy = l2_policy_evict_first();
+    TileIter it;
+    it.op = 0;
+    iter_enter(it, P, W, lane);
+    int ps = 0;
+    uint32_t par = 0xffffffffu;   // a fresh barrier passes a wait on the phase "before the first": every stage starts free
+    // (a second cursor prefetching the tiles beyond the ring into L2 while the ring is full -- cp.async.bulk.prefetch.L2,
+    // 2 / 4 / 8 / 16 tiles per warp -- was measured 0.4 / 0.7 / 1.8 / 3.9 % SLOWER than none: profiles/r2/notes.md)
+    while (it.op < P.n_ops) {
+        if (mbar_test(&eb[ps], (par >> ps) & 1u)) {
+            iter_issue(it, lane, stages + (size_t)ps * kStage, &fb[ps], policy);
+            iter_advance(it, P, W, lane);
+            par ^= 1u << ps;
+            ps = ps + 1 == ns ? 0 : ps + 1;
+        }
+    }
 }
 
 // ------------------------------------------------------------------ input staging of a matrix-vector stage
@@ -407,7 +482,7 @@ __device__ void stage_input(const TokParams& P, const TokOp& op, __nv_bfloat16* 
                 while ((uint32_t)(ll_load(p, sys) >> 32) != tag) __nanosleep(32);
             }
         }
-        __syncthreads();
+        cta_sync();
         const uint64_t* res = op.res_kind == RES_LL ? reinterpret_cast<const uint64_t*>(P.scratch + op.res_off) : nullptr;
         const __nv_bfloat16* rest = op.res_kind == RES_TOKEN ? P.emb + (size_t)token * K : nullptr;
         uint64_t* sum_out = op.publish_cta == (int)blockIdx.x ? reinterpret_cast<uint64_t*>(P.scratch + op.sum_off) : nullptr;
@@ -516,7 +591,7 @@ __device__ void stage_input(const TokParams& P, const TokOp& op, __nv_bfloat16* 
             }
         }
     }
-    __syncthreads();
+    cta_sync();
     if (op.norm_w == nullptr) return;
     float ss = 0.f;
     for (int i = tid * 8; i < K; i += kTT * 8) {
@@ -527,81 +602,89 @@ __device__ void stage_input(const TokParams& P, const TokOp& op, __nv_bfloat16* 
     }
     ss = warp_sum_f(ss);
     if (lane == 0) scratch[warp] = ss;
-    __syncthreads();
+    cta_sync();
     float tot = 0.f;
     for (int w = 0; w < kTW; ++w) tot += scratch[w];
     const float rstd = rsqrtf(tot / (float)K + op.eps);
-    for (int i = tid * 8; i < K; i += kTT * 8) {
+    auto normalise = [&](int i, const uint4& wq) {
         float f[8], wv[8];
         unpack8(*reinterpret_cast<const uint4*>(xs + i), f);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(op.norm_w + i)), wv);
+        unpack8(wq, wv);
         *reinterpret_cast<uint4*>(xs + i) =
             make_uint4(pack_bf16x2(__fmul_rn(bf16_round(__fmul_rn(f[0], rstd)), wv[0]), __fmul_rn(bf16_round(__fmul_rn(f[1], rstd)), wv[1])),
                        pack_bf16x2(__fmul_rn(bf16_round(__fmul_rn(f[2], rstd)), wv[2]), __fmul_rn(bf16_round(__fmul_rn(f[3], rstd)), wv[3])),
                        pack_bf16x2(__fmul_rn(bf16_round(__fmul_rn(f[4], rstd)), wv[4]), __fmul_rn(bf16_round(__fmul_rn(f[5], rstd)), wv[5])),
                        pack_bf16x2(__fmul_rn(bf16_round(__fmul_rn(f[6], rstd)), wv[6]), __fmul_rn(bf16_round(__fmul_rn(f[7], rstd)), wv[7])));
-    }
-    __syncthreads();
+    };
+    // (requesting the norm weights before the hand-over wait was measured: no change, 64 bytes of spills)
+    for (int i = tid * 8; i < K; i += kTT * 8) normalise(i, __ldg(reinterpret_cast<const uint4*>(op.norm_w + i)));
+    cta_sync();
 }
 
 // One ring stage against the staged input on the tensor cores (mma.sync m16n8k16, bf16 in, fp32 accumulate).
-// The stage holds R row segments of `len` elements (R = 2, or 4 for the FFN gate: R * len <= 4096), read as 8
-// independent STREAMS of slen = R * len / 8 consecutive elements: stream n = bytes [n * slen * 2, (n + 1) * slen * 2)
-// of the stage, i.e. row n / S, part n % S (S = 8 / R streams per row).  Only the DIAGONAL of the 16 x 8 product is
-// used: thread (gid = lane / 4, tig = lane % 4) feeds stream gid as column gid of B and the matching input elements
-// as row gid of A, so D[gid][gid] accumulates that stream's dot product.  Each thread loads 8 consecutive elements of
-// its stream (one LDS.128) and of the input (one LDS.128) per 32-element block and issues two MMAs (the 16 k-slots
-// of an MMA can hold any 16 elements as long as A and B agree).  Odd streams run one block ahead of even ones
-// (mod the block count), which keeps both LDS.128 patterns bank-conflict free without padding the rows.
-// A hand-written FFMA loop over the same stage costs 10x the instructions (unpack + FMA per element) and left the
-// kernel issue-bound at ~25 B/clk per SM, i.e. unable to catch up after a stage hand-over (profiles/r2/notes.md).
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
-    // rows gid + 8 of A repeat rows gid (their results are never read)
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %4, %5, %5}, {%6, %7}, {%0, %1, %2, %3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+// The stage holds R row segments of `len` elements (R = 2, or 4 for the FFN gate: R * len <= 4096).  Every row is
+// read as S = 16 / R STREAMS (8 or 4); stream p of a row takes the 32-element blocks p, p + S, p + 2S, ... of the
+// segment.  The 16 rows of the MMA's A operand are 16 (row, stream) pairs -- rows 0-7 of A: the first R / 2 stage rows
+// x S streams, rows 8-15: the other R / 2 stage rows x the same streams -- and column n of B is the input's stream
+// n % S, so D[m][m % 8] accumulates the dot product of A row m's (row, stream) pair: the diagonal of the upper and of
+// the lower 8 x 8 half.  Thread (gid = lane / 4, tig = lane % 4) loads 8 consecutive elements (one LDS.128) of its
+// stream from the upper row, from the lower row and from the input per block and issues two MMAs (the 16 k-slots
+// of an MMA can hold any 16 elements as long as A and B agree): 256 weight elements per MMA.  In every round the
+// lanes of a quarter-warp read one contiguous 128-byte run of a row and the warp reads S * 64 contiguous bytes of
+// the input: conflict free without padding, 12 (R = 2) or 10 (R = 4) shared-memory wavefronts per KiB of weights.
+// (Round 2, first version: 8 A rows duplicated into 16 = half the weights per MMA and 16 wavefronts per KiB; a
+// hand-written FFMA loop costs 10x the instructions.  Both left the warps barely faster than the HBM stream.)
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-template <int S_LOG2>   // log2(streams per row): 2 for two-row stages, 1 for the four-row FFN gate stage
+template <int S_LOG2>   // log2(streams per row): 3 for two-row stages, 2 for the four-row FFN gate stage
 __device__ __forceinline__ void consume_tile(const uint8_t* stage, const __nv_bfloat16* xseg, int len, float (&c)[8][4], int lane) {
     constexpr int S = 1 << S_LOG2;
     const int gid = lane >> 2, tig = lane & 3;
     const int nblk = len >> (5 + S_LOG2);   // 32-element blocks per stream
-    // stream gid = row gid / S of the stage, taking 32-element blocks p, p + S, p + 2S, ... (p = gid % S) of the row
-    // segment: in every round the lanes of a quarter-warp read one contiguous 128-byte run of a row (conflict free)
-    // and the whole warp reads the input from one S * 64-byte window (S / 2 wavefronts instead of 4)
     const uint8_t* wp = stage + (size_t)(gid >> S_LOG2) * (len * 2) + (gid & (S - 1)) * 64 + tig * 16;
+    const uint32_t lower = (uint32_t)(8 >> S_LOG2) * (uint32_t)(len * 2);   // A row gid + 8: the stage row R / 2 further on
     const uint8_t* xp = reinterpret_cast<const uint8_t*>(xseg) + (gid & (S - 1)) * 64 + tig * 16;
     // four blocks per round on eight independent accumulators
     int i = 0;
     for (; i + 4 <= nblk; i += 4) {
-        uint4 w[4], x[4];
+        uint4 wu[4], wl[4], x[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            w[u] = *reinterpret_cast<const uint4*>(wp + (i + u) * (64 * S));
+            wu[u] = *reinterpret_cast<const uint4*>(wp + (i + u) * (64 * S));
+            wl[u] = *reinterpret_cast<const uint4*>(wp + lower + (i + u) * (64 * S));
             x[u] = *reinterpret_cast<const uint4*>(xp + (i + u) * (64 * S));
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            mma_bf16_16816(c[2 * u], x[u].x, x[u].y, w[u].x, w[u].y);
-            mma_bf16_16816(c[2 * u + 1], x[u].z, x[u].w, w[u].z, w[u].w);
+            mma_bf16_16816(c[2 * u], wu[u].x, wl[u].x, wu[u].y, wl[u].y, x[u].x, x[u].y);
+            mma_bf16_16816(c[2 * u + 1], wu[u].z, wl[u].z, wu[u].w, wl[u].w, x[u].z, x[u].w);
         }
     }
     for (; i < nblk; ++i) {
-        const uint4 w = *reinterpret_cast<const uint4*>(wp + i * (64 * S));
+        const uint4 wu = *reinterpret_cast<const uint4*>(wp + i * (64 * S));
+        const uint4 wl = *reinterpret_cast<const uint4*>(wp + lower + i * (64 * S));
         const uint4 x = *reinterpret_cast<const uint4*>(xp + i * (64 * S));
-        mma_bf16_16816(c[0], x.x, x.y, w.x, w.y);
-        mma_bf16_16816(c[1], x.z, x.w, w.z, w.w);
+        mma_bf16_16816(c[0], wu.x, wl.x, wu.y, wl.y, x.x, x.y);
+        mma_bf16_16816(c[1], wu.z, wl.z, wu.w, wl.w, x.z, x.w);
     }
 }
-// after the last stage of a row group: the 8 stream sums -> lanes 0..7 (lane n = stream n), replicated in the
-// other lanes.  Fixed summation order: deterministic.
-__device__ __forceinline__ float gather_streams(const float (&c)[8][4], int lane) {
-    const int gid = lane >> 2;
-    const int e = gid & 1;   // D[gid][gid] lives where tig == gid / 2, in element gid & 1
-    float v = e ? c[0][1] : c[0][0];
+// after the last stage of a row group: D[gid][gid] (upper rows) and D[gid + 8][gid] (lower rows) live in the thread
+// with tig == gid / 2, elements gid & 1 and 2 + (gid & 1); every other thread contributes zero to the butterflies
+// that follow.  Fixed summation order: deterministic.
+__device__ __forceinline__ void gather_streams(const float (&c)[8][4], int lane, float* upper, float* lower) {
+    const int gid = lane >> 2, tig = lane & 3;
+    const int e = gid & 1;
+    float u = e ? c[0][1] : c[0][0], l = e ? c[0][3] : c[0][2];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) v += e ? c[k][1] : c[k][0];
-    const int n = lane & 7;
-    return __shfl_sync(0xffffffffu, v, n * 4 + (n >> 1));
+    for (int k = 1; k < 8; ++k) {
+        u += e ? c[k][1] : c[k][0];
+        l += e ? c[k][3] : c[k][2];
+    }
+    const bool own = tig == (gid >> 1);
+    *upper = own ? u : 0.f;
+    *lower = own ? l : 0.f;
 }
 
 // deferred writes of cross-head cache state (see attn_stage): performed by thread 0 once every head has read it
@@ -617,10 +700,10 @@ struct HeadBest { float v; int idx; };
 
 // ------------------------------------------------------------------ a matrix-vector stage
 __device__ void gemv_stage(const TokParams& P, DescWindow* W, const TokOp& op, int oi, uint8_t* smem, Ring& ring, uint32_t tag,
-                           float* scratch, uint32_t* outw, Pending* pend, HeadBest* best) {
+                           float* scratch, Pending* pend, HeadBest* best) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem);
-    __syncthreads();   // every warp is done with the staging area of the previous stage
+    cta_sync();   // every warp is done with the staging area of the previous stage
     if (tid == 0) tstamp(P, oi, 0);
     if (warp == 1) {   // advance the descriptor window (this warp only waits for warp 0's poll otherwise)
         uint4 keep[2];
@@ -638,31 +721,22 @@ __device__ void gemv_stage(const TokParams& P, DescWindow* W, const TokOp& op, i
         pend->active = 0;
     }
     int g0, nloc;
-    deal_groups(op.n_groups, op.rot, &g0, &nloc);
-    const int type = op.type, K = op.K;
-    const int pos = type == TOK_QKV ? P.input_pos[0] : 0;
-    const bool push = type == TOK_GEMV && op.out_world > 1 && nloc <= kOutStage;
+    deal_groups(op, &g0, &nloc);
+    const int type = op.type, K = op.K, n_seg = op.n_seg;
+    // partial sums of every tile of this CTA, [group][segment] x {row sums}: behind the staged input
+    float4* part = reinterpret_cast<float4*>(smem + (((size_t)K * 2 + 15) & ~(size_t)15));
 #ifdef CC_TOKEN_MICROTRACE
     int dbg_n = 0;
     const unsigned long long dbg_t0 = clock64();
 #endif
-    for (int j = warp; j < nloc; j += kTW) {
-        const int g = g0 + j, r0 = 2 * g;
-        // operands of the epilogue, requested before the dot products
-        float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
-        if (lane == 0 && type == TOK_QKV) {
-            if (op.bias) { e0 = __bfloat162float(op.bias[r0]); e1 = __bfloat162float(op.bias[r0 + 1]); }
-            if (r0 < P.n_q_rows + P.n_kv_rows) {
-                const int half = P.head_dim >> 1, i = (r0 % P.head_dim) >> 1;
-                e2 = __bfloat162float(P.freqs[((size_t)pos * half + i) * 2]);
-                e3 = __bfloat162float(P.freqs[((size_t)pos * half + i) * 2 + 1]);
-            }
-        }
-        float c[8][4];
+    {
+        int j, sg;
+        first_tile(warp, n_seg, &j, &sg);
+        while (j < nloc) {
+            const int off = sg * op.seg_len, len = min(op.seg_len, K - off);
+            float c[8][4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) c[k][0] = c[k][1] = c[k][2] = c[k][3] = 0.f;
-        for (int s = 0; s < op.n_seg; ++s) {
-            const int off = s * op.seg_len, len = min(op.seg_len, K - off);
+            for (int k = 0; k < 8; ++k) c[k][0] = c[k][1] = c[k][2] = c[k][3] = 0.f;
 #ifdef CC_TOKEN_MICROTRACE
             unsigned long long* dbg = (P.trace && blockIdx.x == 0 && lane == 0 && dbg_n < 8)
                 ? P.trace + (size_t)P.n_ops * gridDim.x * kTraceSlots + ((size_t)oi * kTW + warp) * 32 + 1 + dbg_n * 3 : nullptr;
@@ -672,8 +746,8 @@ __device__ void gemv_stage(const TokParams& P, DescWindow* W, const TokOp& op, i
 #ifdef CC_TOKEN_MICROTRACE
             if (dbg) dbg[0] = clock64();
 #endif
-            if (type == TOK_GATE) consume_tile<1>(st, xs + off, len, c, lane);
-            else consume_tile<2>(st, xs + off, len, c, lane);
+            if (type == TOK_GATE) consume_tile<2>(st, xs + off, len, c, lane);
+            else consume_tile<3>(st, xs + off, len, c, lane);
 #ifdef CC_TOKEN_MICROTRACE
             if (dbg) dbg[1] = clock64();
 #endif
@@ -681,64 +755,69 @@ __device__ void gemv_stage(const TokParams& P, DescWindow* W, const TokOp& op, i
 #ifdef CC_TOKEN_MICROTRACE
             if (dbg) { dbg[2] = clock64(); ++dbg_n; }
 #endif
-        }
-        float acc[4];
-        {
-            float sv = gather_streams(c, lane);
-            sv += __shfl_xor_sync(0xffffffffu, sv, 1);
-            if (type == TOK_GATE) {   // 4 rows x 2 streams: w1 r0, w1 r0+1, w3 r0, w3 r0+1
-                acc[0] = __shfl_sync(0xffffffffu, sv, 0); acc[1] = __shfl_sync(0xffffffffu, sv, 2);
-                acc[2] = __shfl_sync(0xffffffffu, sv, 4); acc[3] = __shfl_sync(0xffffffffu, sv, 6);
-            } else {                  // 2 rows x 4 streams
-                sv += __shfl_xor_sync(0xffffffffu, sv, 2);
-                acc[0] = __shfl_sync(0xffffffffu, sv, 0); acc[1] = __shfl_sync(0xffffffffu, sv, 4);
-                acc[2] = acc[3] = 0.f;
+            float up, lo;
+            gather_streams(c, lane, &up, &lo);
+#pragma unroll
+            for (int d = 1; d <= 8; d <<= 1) {
+                up += __shfl_xor_sync(0xffffffffu, up, d);
+                lo += __shfl_xor_sync(0xffffffffu, lo, d);
             }
+            // gate: upper = w1 rows r0 (lanes 0-15) and r0 + 1 (lanes 16-31), lower = the same rows of w3;
+            // otherwise: upper = row r0, lower = row r0 + 1, each split over the two half-warps
+            const float up_hi = __shfl_sync(0xffffffffu, up, 16), lo_hi = __shfl_sync(0xffffffffu, lo, 16);
+            if (lane == 0)
+                part[j * n_seg + sg] = type == TOK_GATE ? make_float4(up, up_hi, lo, lo_hi) : make_float4(up + up_hi, lo + lo_hi, 0.f, 0.f);
+            next_tile(n_seg, &j, &sg);
         }
-        if (lane != 0) continue;
-        uint64_t* out = reinterpret_cast<uint64_t*>(P.scratch + op.out_off);
+    }
+    if (lane == 0) tstamp(P, oi, 2 + warp);
+    cta_sync();
+    // ---- epilogue: one thread per row group; segment sums in segment order (deterministic, independent of the
+    // warp that computed a tile)
+    const int pos = type == TOK_QKV ? P.input_pos[0] : 0;
+    uint64_t* out = reinterpret_cast<uint64_t*>(P.scratch + op.out_off);
+    for (int j = tid; j < nloc; j += kTT) {
+        const int g = g0 + j, r0 = 2 * g;
+        float4 a4 = part[j * n_seg];
+        for (int sg = 1; sg < n_seg; ++sg) {
+            const float4 b4 = part[j * n_seg + sg];
+            a4.x += b4.x; a4.y += b4.y; a4.z += b4.z; a4.w += b4.w;
+        }
         if (type == TOK_QKV) {
             // nn.Linear (+bias) output is a bf16 tensor; q and k rows rotate in fp32 (model.py:507-519), v rows do not
-            float a = bf16_round(acc[0] + e0), b = bf16_round(acc[1] + e1);
+            float e0 = 0.f, e1 = 0.f;
+            if (op.bias) { e0 = __bfloat162float(op.bias[r0]); e1 = __bfloat162float(op.bias[r0 + 1]); }
+            float a = bf16_round(a4.x + e0), b = bf16_round(a4.y + e1);
             if (r0 < P.n_q_rows + P.n_kv_rows) {
+                const int half = P.head_dim >> 1, i = (r0 & (P.head_dim - 1)) >> 1;
+                const float e2 = __bfloat162float(P.freqs[((size_t)pos * half + i) * 2]);
+                const float e3 = __bfloat162float(P.freqs[((size_t)pos * half + i) * 2 + 1]);
                 const float ra = __fsub_rn(__fmul_rn(a, e2), __fmul_rn(b, e3));
                 const float rb = __fadd_rn(__fmul_rn(b, e2), __fmul_rn(a, e3));
                 a = ra; b = rb;
             }
             ll_store(out + g, pack_bf16x2(a, b), tag);
         } else if (type == TOK_GEMV) {
-            const uint32_t d = pack_bf16x2(bf16_round(acc[0]), bf16_round(acc[1]));
-            if (push) {
-                outw[j] = d;
-            } else {
-                const size_t word = (size_t)P.rank * (op.N >> 1) + g;
-                for (int p = 0; p < op.out_world; ++p)
-                    ll_store(reinterpret_cast<uint64_t*>(P.peers[p] + op.out_off) + word, d, tag);
-            }
+            // row-parallel partial outputs go to every rank (consecutive threads = consecutive words: whole lines)
+            const uint32_t d = pack_bf16x2(bf16_round(a4.x), bf16_round(a4.y));
+            const size_t word = (size_t)P.rank * (op.N >> 1) + g;
+            for (int pr = 0; pr < op.out_world; ++pr)
+                ll_store(reinterpret_cast<uint64_t*>(P.peers[pr] + op.out_off) + word, d, tag);
         } else if (type == TOK_GATE) {
             float o[2];
+            const float w1v[2] = {a4.x, a4.y}, w3v[2] = {a4.z, a4.w};
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const float gt = bf16_round(acc[q]);                      // w1(x), bf16 tensor
+                const float gt = bf16_round(w1v[q]);                      // w1(x), bf16 tensor
                 const float sg = bf16_round(gt / (1.0f + expf(-gt)));     // F.silu in fp32, bf16 out
-                o[q] = __fmul_rn(sg, bf16_round(acc[2 + q]));             // * w3(x)
+                o[q] = __fmul_rn(sg, bf16_round(w3v[q]));                 // * w3(x)
             }
             ll_store(out + g, pack_bf16x2(o[0], o[1]), tag);
         } else {  // TOK_HEAD: logits (model.py:291), running arg-max with torch.argmax's first-index rule
-            const float a = bf16_round(acc[0]), b = bf16_round(acc[1]);
+            const float a = bf16_round(a4.x), b = bf16_round(a4.y);
             if (P.logits_out) *reinterpret_cast<uint32_t*>(P.logits_out + r0) = pack_bf16x2(a, b);
             if (a > best->v || (a == best->v && r0 < best->idx)) { best->v = a; best->idx = r0; }
             if (b > best->v || (b == best->v && r0 + 1 < best->idx)) { best->v = b; best->idx = r0 + 1; }
-        }
-    }
-    if (lane == 0) tstamp(P, oi, 2 + warp);
-    if (push) {
-        // row-parallel partial outputs of this CTA are contiguous words: store them to every rank as whole lines
-        __syncthreads();
-        const size_t word0 = (size_t)P.rank * (op.N >> 1) + g0;
-        for (int t = tid; t < nloc * op.out_world; t += kTT) {
-            const int p = t / nloc, i = t - p * nloc;
-            ll_store(reinterpret_cast<uint64_t*>(P.peers[p] + op.out_off) + word0 + i, outw[i], tag);
         }
     }
 }
@@ -773,7 +852,7 @@ __device__ void attn_stage(const TokParams& P, DescWindow* W, const TokAttn& A, 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int li = lane % LPR, sub = lane / LPR;
     const AttnDeal dl = deal_attn(A);
-    __syncthreads();   // the staging area of the previous stage is free
+    cta_sync();   // the staging area of the previous stage is free
     if (tid == 0) tstamp(P, oi, 0);
     if (warp == 1) {   // advance the descriptor window
         uint4 keep[2];
@@ -830,7 +909,7 @@ __device__ void attn_stage(const TokParams& P, DescWindow* W, const TokAttn& A, 
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
         if (lane == 0) misc[kTmWarpMax + warp] = m;
-        __syncthreads();
+        cta_sync();
         l2_max = misc[kTmWarpMax];
         for (int w = 1; w < kTW; ++w) l2_max = fmaxf(l2_max, misc[kTmWarpMax + w]);
     }
@@ -873,7 +952,7 @@ __device__ void attn_stage(const TokParams& P, DescWindow* W, const TokAttn& A, 
     }
     ckey = warp_min_u64(ckey);
     if (lane == 0) reinterpret_cast<unsigned long long*>(miscu + kTmWarpKey)[warp] = ckey;
-    __syncthreads();
+    cta_sync();
     ckey = lane < kTW ? reinterpret_cast<unsigned long long*>(miscu + kTmWarpKey)[lane] : kNoKey64;
     ckey = warp_min_u64(ckey);
     int cand_local = -1;
@@ -950,7 +1029,7 @@ __device__ void attn_stage(const TokParams& P, DescWindow* W, const TokAttn& A, 
         }
         if (nv > 0) ring_release(ring, P, warp, lane);
     }
-    __syncthreads();
+    cta_sync();
     if (tid == 0) tstamp(P, oi, 2);
     // ---- row max without the local candidate, and the candidate's own logits -> this CTA's X1 record
     for (int g = warp; g < G; g += kTW) {
@@ -968,11 +1047,11 @@ __device__ void attn_stage(const TokParams& P, DescWindow* W, const TokAttn& A, 
         miscu[kTmMyRec + 0] = (uint32_t)(ckey & 0xffffffffu);
         miscu[kTmMyRec + 1] = (uint32_t)(ckey >> 32);
     }
-    __syncthreads();
+    cta_sync();
     // ---- X1: every CTA of the head learns every candidate and every partial max
     if (tid < NWR) ll_store(x1 + (size_t)rank * NWR + tid, miscu[kTmMyRec + tid], tag);
     for (int idx = tid; idx < C * NWR; idx += kTT) sm.rec[idx] = ll_wait(x1 + idx, tag);
-    __syncthreads();
+    cta_sync();
     if (tid == 0) tstamp(P, oi, 3);
     // winner + global max per query head (every warp redundantly)
     uint64_t wkey = kNoKey64;
@@ -1023,11 +1102,11 @@ __device__ void attn_stage(const TokParams& P, DescWindow* W, const TokAttn& A, 
             if (lane == 0 && part) atomicAdd(&sm.ssum[g], (unsigned long long)part);  // integers: order independent
         }
     }
-    __syncthreads();
+    cta_sync();
     if (tid < 2 * G) ll_store(x2 + (size_t)rank * 2 * G + tid, (uint32_t)(sm.ssum[tid >> 1] >> (32 * (tid & 1))), tag);
     if (tid == 0) tstamp(P, oi, 4);
     for (int idx = tid; idx < C * 2 * G; idx += kTT) sm.sums[idx] = ll_wait(x2 + idx, tag);
-    __syncthreads();
+    cta_sync();
     if (tid == 0) tstamp(P, oi, 5);
     float sumf[G];
 #pragma unroll
@@ -1048,7 +1127,7 @@ __device__ void attn_stage(const TokParams& P, DescWindow* W, const TokAttn& A, 
         if (naive) pr = bf16_round(pr);
         lg[g * stride + lr] = pr;
     }
-    __syncthreads();
+    cta_sync();
     if (tid == 0) tstamp(P, oi, 6);
 
     // ---- y = P.V over this warp's V tiles, warp -> CTA -> head reduction = X3
@@ -1097,7 +1176,7 @@ __device__ void attn_stage(const TokParams& P, DescWindow* W, const TokAttn& A, 
                     dst[1] = make_float4(acc[g][4], acc[g][5], acc[g][6], acc[g][7]);
                 }
             }
-            __syncthreads();
+            cta_sync();
         }
         if (warp < kRedWarps && lane < LPR) {
 #pragma unroll
@@ -1115,7 +1194,7 @@ __device__ void attn_stage(const TokParams& P, DescWindow* W, const TokAttn& A, 
             }
         }
     }
-    __syncthreads();
+    cta_sync();
     if (tid == 0) tstamp(P, oi, 7);
     const int SL = (G * D) >> csh;  // outputs reduced by each CTA of the head (a multiple of 4)
     for (int o = tid; o < G * D; o += kTT) {
@@ -1189,7 +1268,7 @@ __device__ void attn_stage(const TokParams& P, DescWindow* W, const TokAttn& A, 
         const uint64_t* mine = x3 + (size_t)rank * C * SL;
         if (tid == 0) tstamp(P, oi, 8);
         for (int idx = tid; idx < C * SL; idx += kTT) sm.yx[idx] = __uint_as_float(ll_wait(mine + idx, tag));
-        __syncthreads();
+        cta_sync();
         if (tid == 0) tstamp(P, oi, 9);
         uint64_t* yout = reinterpret_cast<uint64_t*>(P.scratch + A.y_off) + (((size_t)h * G * D + (size_t)rank * SL) >> 1);
         for (int t = tid; t < (SL >> 1); t += kTT) {
@@ -1205,38 +1284,45 @@ __device__ void attn_stage(const TokParams& P, DescWindow* W, const TokAttn& A, 
 
 // ------------------------------------------------------------------ the kernel
 template <int D, int G>
-__global__ void __launch_bounds__(kTT, 1) cc_token_kernel(const __grid_constant__ TokParams P) {
+__global__ void __launch_bounds__(kLaunchThreads, 1) cc_token_kernel(const __grid_constant__ TokParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ float scratch[kTW];
-    __shared__ uint32_t outw[kOutStage];
     __shared__ Pending pend;
     __shared__ HeadBest wbest[kTW];
     __shared__ __align__(16) DescWindow win;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t ring_off = (P.xs_bytes + 127u) & ~127u;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ring_off + (size_t)kTW * P.n_stages * kStage);
+    uint8_t* ring_base = smem + ring_off;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring_base + (size_t)kTW * P.n_stages * kStage);
+    uint64_t* ebars = bars + kTW * P.n_stages;
 
     Ring ring;
     ring.ns = P.n_stages;
     ring.cs = 0;
     ring.phases = 0;
-    ring.stages = smem + ring_off + (size_t)warp * P.n_stages * kStage;
-    ring.bars = bars + warp * P.n_stages;
-    if (lane == 0) {
-        for (int s = 0; s < P.n_stages; ++s) mbar_init(&ring.bars[s], 1);
+    ring.stages = ring_base + (size_t)(warp < kTW ? warp : 0) * P.n_stages * kStage;
+    ring.bars = bars + (warp < kTW ? warp : 0) * P.n_stages;
+    ring.empty = ebars + (warp < kTW ? warp : 0) * P.n_stages;
+    if (lane == 0 && warp < kTW) {
+        for (int s = 0; s < P.n_stages; ++s) {
+            mbar_init(&ring.bars[s], 1);
+            if (kProducer) mbar_init(&ring.empty[s], 1);
+        }
         mbar_fence_init();
     }
     if (tid == 0) { pend.active = 0; win.op_hi = 0; win.att_hi = 0; }
     __syncthreads();
     // descriptor window: the first kOpWin - 1 stages, one per warp round
-    for (int oi = warp; oi < kOpWin - 1; oi += kTW) {
-        uint4 keep[2];
-        int ka;
-        window_load(P, &win, oi, lane, keep, &ka);
-        if (oi < P.n_ops) {
-            constexpr int nop = (int)(sizeof(TokOp) / 16), natt = (int)(sizeof(TokAttn) / 16);
-            if (lane < nop) reinterpret_cast<uint4*>(&win.op[oi % kOpWin])[lane] = keep[0];
-            if (ka >= 0 && lane < natt) reinterpret_cast<uint4*>(&win.att[ka % kAttWin])[lane] = keep[1];
+    if (warp < kTW) {
+        for (int oi = warp; oi < kOpWin - 1; oi += kTW) {
+            uint4 keep[2];
+            int ka;
+            window_load(P, &win, oi, lane, keep, &ka);
+            if (oi < P.n_ops) {
+                constexpr int nop = (int)(sizeof(TokOp) / 16), natt = (int)(sizeof(TokAttn) / 16);
+                if (lane < nop) reinterpret_cast<uint4*>(&win.op[oi % kOpWin])[lane] = keep[0];
+                if (ka >= 0 && lane < natt) reinterpret_cast<uint4*>(&win.att[ka % kAttWin])[lane] = keep[1];
+            }
         }
     }
     __syncthreads();
@@ -1249,19 +1335,28 @@ __global__ void __launch_bounds__(kTT, 1) cc_token_kernel(const __grid_constant_
     }
     __syncthreads();
     ring.win = &win;
-    ring.policy = l2_policy_evict_first();
     // the weight / cache stream starts before anything else: fill the whole ring
     // (an L2 prefetch cursor running further ahead -- cp.async.bulk.prefetch.L2 of the tiles after the ring -- was
     // measured SLOWER: 301 -> 273 tokens/s at 2 tiles per warp, 240 at 6; profiles/r2/notes.md)
-    ring.it.op = 0;
-    if (lane == 0) {
-        iter_enter(ring.it, P, &win, warp);
-        for (int s = 0; s < P.n_stages && ring.it.op < P.n_ops; ++s) {
-            iter_issue(ring.it, warp, ring.stages + (size_t)s * kStage, &ring.bars[s], ring.policy);
-            iter_advance(ring.it, P, &win, warp);
+    if (kProducer) {
+        if (warp >= kTW) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(kProducerRegs));
+            if (warp == kTW) producer_loop(P, &win, ring_base, bars, ebars, lane);
+            return;   // every later CTA-wide barrier is the consumers' named barrier
         }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(kConsumerRegs));
+    } else {
+        ring.policy = l2_policy_evict_first();
+        ring.it.op = 0;
+        if (lane == 0) {
+            iter_enter(ring.it, P, &win, warp);
+            for (int s = 0; s < P.n_stages && ring.it.op < P.n_ops; ++s) {
+                iter_issue(ring.it, warp, ring.stages + (size_t)s * kStage, &ring.bars[s], ring.policy);
+                iter_advance(ring.it, P, &win, warp);
+            }
+        }
+        __syncwarp();
     }
-    __syncwarp();
     TokHeader* hdr = reinterpret_cast<TokHeader*>(P.scratch);
     const uint32_t tag = *reinterpret_cast<volatile uint32_t*>(&hdr->gen) + 1u;
     HeadBest best = {-CUDART_INF_F, 0x7fffffff};
@@ -1272,11 +1367,11 @@ __global__ void __launch_bounds__(kTT, 1) cc_token_kernel(const __grid_constant_
         if (op.type == TOK_ATTN) {
             attn_stage<D, G>(P, &win, *att_at(P, &win, op.attn), oi, smem, ring, tag, &pend);
         } else {
-            gemv_stage(P, &win, op, oi, smem, ring, tag, scratch, outw, &pend, &best);
+            gemv_stage(P, &win, op, oi, smem, ring, tag, scratch, &pend, &best);
             has_head |= op.type == TOK_HEAD;
         }
     }
-    __syncthreads();
+    cta_sync();
     if (tid == 0 && pend.active) {   // a program that ends with an attention stage (tests)
         if (pend.pos_ptr) *pend.pos_ptr = pend.pos_val;
         if (pend.kn_ptr) *pend.kn_ptr = (uint16_t)pend.kn_val;
@@ -1285,8 +1380,14 @@ __global__ void __launch_bounds__(kTT, 1) cc_token_kernel(const __grid_constant_
 
     // ---- greedy sampling (generation_utils.py:136-142): arg-max over all CTAs' rows, optional softmax
     if (has_head) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {   // every thread tracked the rows it finished
+            const float ov = __shfl_xor_sync(0xffffffffu, best.v, d);
+            const int oidx = __shfl_xor_sync(0xffffffffu, best.idx, d);
+            if (ov > best.v || (ov == best.v && oidx < best.idx)) { best.v = ov; best.idx = oidx; }
+        }
         if (lane == 0) wbest[warp] = best;
-        __syncthreads();
+        cta_sync();
         HeadBest cb = wbest[0];
         for (int w = 1; w < kTW; ++w)
             if (wbest[w].v > cb.v || (wbest[w].v == cb.v && wbest[w].idx < cb.idx)) cb = wbest[w];
@@ -1299,7 +1400,7 @@ __global__ void __launch_bounds__(kTT, 1) cc_token_kernel(const __grid_constant_
         // every CTA reduces all records (it needs the global max for the softmax anyway); all words requested at once
         float* recs = reinterpret_cast<float*>(smem);   // the staging area is free: 2 * n_ctas words
         for (int i = tid; i < 2 * nc; i += kTT) recs[i] = __uint_as_float(ll_wait(rec1 + i, tag));
-        __syncthreads();
+        cta_sync();
         HeadBest gb = {-CUDART_INF_F, 0x7fffffff};
         for (int c = lane; c < nc; c += 32) {
             const float v = recs[2 * c];
@@ -1317,13 +1418,13 @@ __global__ void __launch_bounds__(kTT, 1) cc_token_kernel(const __grid_constant_
             // softmax over the bf16 logits in fp32 (torch.softmax on a bf16 tensor), one bf16 rounding
             const TokOp& hop = *op_at(P, &win, P.n_ops - 1);
             int g0, nloc;
-            deal_groups(hop.n_groups, hop.rot, &g0, &nloc);
+            deal_groups(hop, &g0, &nloc);
             float part = 0.f;
             for (int i = tid; i < 2 * nloc; i += kTT)
                 part += expf(__bfloat162float(P.logits_out[2 * g0 + i]) - gb.v);
             part = warp_sum_f(part);
             if (lane == 0) scratch[warp] = part;
-            __syncthreads();
+            cta_sync();
             uint64_t* rec2 = reinterpret_cast<uint64_t*>(P.scratch + P.rec2_off);
             if (tid == 0) {
                 float tot = 0.f;
@@ -1331,7 +1432,7 @@ __global__ void __launch_bounds__(kTT, 1) cc_token_kernel(const __grid_constant_
                 ll_store(rec2 + blockIdx.x, __float_as_uint(tot), tag);
             }
             for (int i = tid; i < nc; i += kTT) recs[i] = __uint_as_float(ll_wait(rec2 + i, tag));
-            __syncthreads();
+            cta_sync();
             float tot = 0.f;
             for (int c = 0; c < nc; ++c) tot += recs[c];  // CTA order: deterministic
             for (int i = tid; i < 2 * nloc; i += kTT) {
@@ -1341,7 +1442,7 @@ __global__ void __launch_bounds__(kTT, 1) cc_token_kernel(const __grid_constant_
         }
     }
     // ---- the last CTA to finish advances the token tag
-    __syncthreads();
+    cta_sync();
     if (tid == 0) {
         __threadfence();
         const uint32_t prev = atomicAdd(&hdr->done, 1u);
@@ -1554,11 +1655,15 @@ int token_plan_create_impl(const CcTokenModel* m, void** out_plan) {
     auto base_op = [&](int type, int K, int N, int rg, int layer) {
         TokOp o;
         memset(&o, 0, sizeof(o));
-        o.type = type; o.K = K; o.N = N; o.n_groups = N / 2; o.layer = layer;
+        (void)layer;
+        o.type = type; o.K = K; o.N = N; o.n_groups = N / 2;
         seg_plan(K, rg, &o.seg_len, &o.n_seg);
         o.rot = next_rot(o.n_groups);
+        o.grp_base = o.n_groups / n_ctas; o.grp_rem = o.n_groups % n_ctas;
         o.publish_cta = -1; o.in_world = 1; o.out_world = 1; o.attn = -1;
-        if ((uint32_t)K * 2 > xs_bytes) xs_bytes = (uint32_t)K * 2;
+        // staged input + one float4 of partial sums per tile of a CTA
+        const uint32_t need = (((uint32_t)K * 2 + 15u) & ~15u) + (uint32_t)(o.grp_base + 1) * o.n_seg * 16u;
+        if (need > xs_bytes) xs_bytes = need;
         return o;
     };
     const int qkv_rows = (m->n_q_heads + 2 * m->n_kv_heads) * D;
@@ -1583,7 +1688,7 @@ int token_plan_create_impl(const CcTokenModel* m, void** out_plan) {
         {
             TokOp o;
             memset(&o, 0, sizeof(o));
-            o.type = TOK_ATTN; o.layer = l; o.attn = (int)attns.size(); o.publish_cta = -1;
+            o.type = TOK_ATTN; o.attn = (int)attns.size(); o.publish_cta = -1;
             TokAttn a;
             memset(&a, 0, sizeof(a));
             a.st = y.cache;
@@ -1638,7 +1743,7 @@ int token_plan_create_impl(const CcTokenModel* m, void** out_plan) {
         o.w = (const __nv_bfloat16*)m->output;
         ops.push_back(o);
     }
-    xs_bytes = (xs_bytes + 1023u) & ~1023u;
+    xs_bytes = (xs_bytes + 127u) & ~127u;
     TokKernelFn fn = pick_tok_kernel(D, G);
     cudaFuncAttributes fattr;
     if (cudaFuncGetAttributes(&fattr, fn) != cudaSuccess) {
@@ -1647,19 +1752,19 @@ int token_plan_create_impl(const CcTokenModel* m, void** out_plan) {
     }
     const int max_dyn = optin - (int)fattr.sharedSizeBytes;   // static shared memory counts against the same limit
     // shared memory: staging area | ring (8 warps x n_stages x 8 KiB) | mbarriers
-    const int avail = max_dyn - (int)xs_bytes - 1024 /* barriers + slack */;
+    const int avail = max_dyn - (int)xs_bytes - (8 * kTW * 16 + 64) /* full + empty barriers of up to 8 stages */;
     int n_stages = avail / (int)(kTW * kStage);
     if (n_stages > 8) n_stages = 8;
     if (const char* e = getenv("CC_B200_TOKEN_STAGES")) n_stages = atoi(e) < n_stages && atoi(e) > 0 ? atoi(e) : n_stages;
     if (n_stages < 2) return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_token: staging area leaves fewer than 2 ring stages per warp");
-    const uint32_t smem = ((xs_bytes + 127u) & ~127u) + (uint32_t)n_stages * kTW * kStage + (uint32_t)n_stages * kTW * 8 + 64;
+    const uint32_t smem = ((xs_bytes + 127u) & ~127u) + (uint32_t)n_stages * kTW * kStage + (uint32_t)n_stages * kTW * 16 + 64;
 
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) != cudaSuccess) {
         cudaGetLastError();
         return set_error(CC_ERR_CUDA, "cc_token: cannot raise the dynamic shared memory limit");
     }
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTT, smem) != cudaSuccess || per_sm < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kLaunchThreads, smem) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
         return set_error(CC_ERR_UNSUPPORTED_SHAPE, "cc_token: the kernel does not fit an SM with this shared-memory plan");
     }
@@ -1709,7 +1814,7 @@ int decode_token_impl(void* vp, const int32_t* token_in, const int32_t* input_po
     p.logits_out = (__nv_bfloat16*)logits_out; p.probs_out = (__nv_bfloat16*)probs_out;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(plan->n_ctas);
-    cfg.blockDim = dim3(kTT);
+    cfg.blockDim = dim3(kLaunchThreads);
     cfg.dynamicSmemBytes = plan->smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr;

@@ -15,6 +15,7 @@ from pathlib import Path
 import torch
 
 ROOT = Path(__file__).resolve().parent.parent
+TOK_VOCAB = 64
 sys.path.insert(0, str(ROOT))
 
 
@@ -37,7 +38,13 @@ def main():
                 p.fill_(1.0)
             else:
                 p.normal_(0.0, 0.02)
-    torch.save({k: v.to(torch.bfloat16) for k, v in model.state_dict().items()}, d / "model.pth")
+    sd = {k: v.to(torch.bfloat16) for k, v in model.state_dict().items()}
+    # the tokenizer below knows TOK_VOCAB pieces: rows of the output head beyond it are zero, so greedy decoding
+    # (arg-max over logits whose first TOK_VOCAB entries are random and the rest exactly 0) only emits ids that the
+    # reference's tokenizer.decode (generate.py:136) accepts
+    sd["output.weight"][TOK_VOCAB:] = 0
+    sd["output.weight"][:TOK_VOCAB] *= 8
+    torch.save(sd, d / "model.pth")
     import sentencepiece as spm
     corpus = d / "corpus.txt"
     words = ["the", "cache", "keeps", "heavy", "hitters", "and", "recent", "tokens", "while", "old", "keys", "are", "evicted",
@@ -45,7 +52,7 @@ def main():
     gen = torch.Generator().manual_seed(a.seed)
     lines = [" ".join(words[int(i)] for i in torch.randint(0, len(words), (12,), generator=gen)) for _ in range(400)]
     corpus.write_text("\n".join(lines) + "\n")
-    spm.SentencePieceTrainer.train(input=str(corpus), model_prefix=str(d / "tokenizer"), vocab_size=64, model_type="bpe",
+    spm.SentencePieceTrainer.train(input=str(corpus), model_prefix=str(d / "tokenizer"), vocab_size=TOK_VOCAB, model_type="bpe",
                                    bos_id=1, eos_id=2, unk_id=0, pad_id=-1, minloglevel=2)
     corpus.unlink()
     (d / "tokenizer.vocab").unlink(missing_ok=True)
