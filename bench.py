@@ -84,17 +84,20 @@ def env_int(name, default):
 # --------------------------------------------------------------------------- clocks sampling
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms.  The sampler is started before the warm-up steps (the
+    tool needs a few hundred ms to come up; the timed region of a tensor-parallel run is ~0.1-0.5 s) and `mark()`
+    brackets the timed region: the summary uses the samples taken inside it, or, if the region was shorter than the
+    tool's period, every sample taken under load since the warm-up began."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.rows, self.proc, self.idx, self.marks = [], None, gpu_index, []
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -104,7 +107,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
+
+    def mark(self):
+        self.marks.append(time.perf_counter())
 
     def __exit__(self, *exc):
         if self.proc:
@@ -114,12 +120,18 @@ class ClockSampler:
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
+        rows, window = self.rows, "warm-up + timed steps"
+        if len(self.marks) >= 2:
+            inside = [r for r in self.rows if self.marks[0] <= r[0] <= self.marks[-1]]
+            if inside:
+                rows, window = inside, "timed steps"
+        rows = [r[1:] for r in rows]
+        sm = [int(r[0]) for r in rows if r[0].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in rows)]
         return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons,
-                "samples": len(self.rows)}
+                "sm_max_mhz": int(rows[0][1]) if rows[0][1].isdigit() else None, "reasons": reasons,
+                "samples": len(rows), "window": window}
 
 
 # --------------------------------------------------------------------------- our arm (GPU)
@@ -273,11 +285,15 @@ def run_ours(args):
             input_pos.add_(1)
             return nxt.view(1, 1)
 
+        clocks = ClockSampler(local)
+        clocks.__enter__()
         for _ in range(max(3, args.warmup)):
             tok = step_device(tok)
+        torch.cuda.synchronize()
         # ---- value: K steps, device-resident inputs, CUDA events, max over ranks
-        with ClockSampler(local) as clocks:
+        try:
             barrier()
+            clocks.mark()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             if os.environ.get("CC_BENCH_NCU"):  # ncu --profile-from-start off: capture only timed steps
                 torch.cuda.profiler.start()
@@ -310,7 +326,10 @@ def run_ours(args):
                 cur += 1
             barrier()
             e2e_s = time.perf_counter() - t0
+            clocks.mark()
             input_pos.fill_(cur)
+        finally:
+            clocks.__exit__(None, None, None)
         times = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -631,8 +650,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
-    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=0, choices=[0, 1, 2, 3, 4, 5],
                     help="BASELINE.json config (default: 2 on one GPU, 5 = pyramid lengths under head sharding on several)")

@@ -50,9 +50,12 @@ constexpr bool kProducer = CC_TOKEN_PRODUCER != 0;   // one extra warp owns ever
 // The producer warp comes with a whole warpgroup (setmaxnreg works on aligned groups of 4 warps): registers are
 // dealt per scheduler, so a 9th warp alone would cap every thread at 168 registers; instead the kernel starts at
 // 168 (384 threads), the producer warpgroup shrinks to kProducerRegs and the two consumer warpgroups grow to
-// kConsumerRegs (128 * 40 + 256 * 232 = 64512 <= 65536).
+// kConsumerRegs (128 * 40 + 256 * 232 = 64512 = 384 * 168).
 constexpr int kLaunchThreads = kTT + (kProducer ? 128 : 0);
 constexpr int kProducerRegs = 40, kConsumerRegs = 232;
+// setmaxnreg moves registers inside the CTA's own launch allocation (384 x 168): what the producer warpgroup gives
+// up must cover what the consumers take, or the consumers' setmaxnreg.inc waits forever (48 / 232 hangs the kernel)
+static_assert(128 * (168 - kProducerRegs) >= 256 * (kConsumerRegs - 168), "setmaxnreg split exceeds the CTA's register allocation");
 static_assert(!kProducer || kTW == 8, "the producer warpgroup layout assumes 8 consumer warps");
 // CTA-wide barrier of the consumer warps (the producer warp never joins it)
 __device__ __forceinline__ void cta_sync() {
@@ -119,7 +122,7 @@ struct TokParams {
     int32_t dim, n_q_rows, n_kv_rows, head_dim;
     uint32_t xs_bytes;            // staging area at the start of shared memory (input vector / attention scratch)
     int32_t n_stages;             // ring stages per warp
-    uint64_t rec1_off, rec2_off;  // arg-max / softmax-sum records, one per CTA
+    uint64_t rec1_off, rec2_off, rec3_off;  // logit arg-max / softmax-sum / probability arg-max records, one per CTA
     unsigned long long* trace;
 };
 
@@ -447,8 +450,9 @@ __device__ void producer_loop(const TokParams& P, const DescWindow* W, uint8_t* 
     iter_enter(it, P, W, lane);
     int ps = 0;
     uint32_t par = 0xffffffffu;   // a fresh barrier passes a wait on the phase "before the first": every stage starts free
-    // (a second cursor prefetching the tiles beyond the ring into L2 while the ring is full -- cp.async.bulk.prefetch.L2,
-    // 2 / 4 / 8 / 16 tiles per warp -- was measured 0.4 / 0.7 / 1.8 / 3.9 % SLOWER than none: profiles/r2/notes.md)
+    // (a second cursor prefetching the tiles beyond the ring into L2 -- cp.async.bulk.prefetch.L2, 2 / 4 / 8 / 16 tiles
+    // per warp whenever the ring is full -- was measured 0.4 / 0.7 / 1.8 / 3.9 % SLOWER than none: the bulk
+    // prefetches queue in front of the demand copies in the SM's TMA unit; profiles/r2/notes.md)
     while (it.op < P.n_ops) {
         if (mbar_test(&eb[ps], (par >> ps) & 1u)) {
             iter_issue(it, lane, stages + (size_t)ps * kStage, &fb[ps], policy);
@@ -1413,8 +1417,9 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) cc_token_kernel(const __gri
             const int oidx = __shfl_xor_sync(0xffffffffu, gb.idx, d);
             if (ov > gb.v || (ov == gb.v && oidx < gb.idx)) { gb.v = ov; gb.idx = oidx; }
         }
-        if (blockIdx.x == 0 && tid == 0 && P.token_out) P.token_out[0] = gb.idx;
-        if (P.probs_out && P.logits_out) {
+        if (!(P.probs_out && P.logits_out)) {
+            if (blockIdx.x == 0 && tid == 0 && P.token_out) P.token_out[0] = gb.idx;   // arg-max of the logits
+        } else {
             // softmax over the bf16 logits in fp32 (torch.softmax on a bf16 tensor), one bf16 rounding
             const TokOp& hop = *op_at(P, &win, P.n_ops - 1);
             int g0, nloc;
@@ -1435,9 +1440,51 @@ __global__ void __launch_bounds__(kLaunchThreads, 1) cc_token_kernel(const __gri
             cta_sync();
             float tot = 0.f;
             for (int c = 0; c < nc; ++c) tot += recs[c];  // CTA order: deterministic
+            // The reference samples arg-max of the bf16 PROBABILITIES (generation_utils.py:136-142): logits that
+            // differ by less than the bf16 resolution of their probabilities tie, and the first index wins.
+            HeadBest pb = {-1.f, 0x7fffffff};
             for (int i = tid; i < 2 * nloc; i += kTT) {
                 const float l = __bfloat162float(P.logits_out[2 * g0 + i]);
-                P.probs_out[2 * g0 + i] = __float2bfloat16_rn(__fdiv_rn(expf(l - gb.v), tot));
+                const __nv_bfloat16 pr = __float2bfloat16_rn(__fdiv_rn(expf(l - gb.v), tot));
+                P.probs_out[2 * g0 + i] = pr;
+                const float pv = __bfloat162float(pr);
+                if (pv > pb.v) { pb.v = pv; pb.idx = 2 * g0 + i; }   // i ascends: the first of equal values stays
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, pb.v, d);
+                const int oidx = __shfl_xor_sync(0xffffffffu, pb.idx, d);
+                if (ov > pb.v || (ov == pb.v && oidx < pb.idx)) { pb.v = ov; pb.idx = oidx; }
+            }
+            cta_sync();   // wbest / recs of the logit arg-max have been read by every warp
+            if (lane == 0) wbest[warp] = pb;
+            cta_sync();
+            uint64_t* rec3 = reinterpret_cast<uint64_t*>(P.scratch + P.rec3_off);
+            if (tid == 0) {
+                HeadBest cb3 = wbest[0];
+                for (int w = 1; w < kTW; ++w)
+                    if (wbest[w].v > cb3.v || (wbest[w].v == cb3.v && wbest[w].idx < cb3.idx)) cb3 = wbest[w];
+                ll_store(rec3 + 2 * blockIdx.x, __float_as_uint(cb3.v), tag);
+                ll_store(rec3 + 2 * blockIdx.x + 1, (uint32_t)cb3.idx, tag);
+            }
+            if (blockIdx.x == 0 && P.token_out) {
+                for (int i = tid; i < 2 * nc; i += kTT) recs[i] = __uint_as_float(ll_wait(rec3 + i, tag));
+                cta_sync();
+                if (warp == 0) {
+                    HeadBest g3 = {-1.f, 0x7fffffff};
+                    for (int c = lane; c < nc; c += 32) {
+                        const float v = recs[2 * c];
+                        const int idx = (int)__float_as_uint(recs[2 * c + 1]);
+                        if (v > g3.v || (v == g3.v && idx < g3.idx)) { g3.v = v; g3.idx = idx; }
+                    }
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, g3.v, d);
+                        const int oidx = __shfl_xor_sync(0xffffffffu, g3.idx, d);
+                        if (ov > g3.v || (ov == g3.v && oidx < g3.idx)) { g3.v = ov; g3.idx = oidx; }
+                    }
+                    if (lane == 0) P.token_out[0] = g3.idx;
+                }
             }
         }
     }
@@ -1527,7 +1574,7 @@ struct Layout {
     uint64_t total;
     std::vector<BufMap> bufs;   // per layer 7 entries, then one extra layer entry for the head input
     std::vector<uint64_t> x1, x2, x3;
-    uint64_t rec1, rec2;
+    uint64_t rec1, rec2, rec3;
 };
 
 static int token_policy_ok(const CcCacheState& st) {
@@ -1563,6 +1610,7 @@ static int build_layout(const CcTokenModel* m, int n_ctas, Layout* lay) {
     lay->bufs[(size_t)m->n_layers * 7 + 6] = {take(m->dim / 2), m->dim / 2};
     lay->rec1 = take(2 * (uint64_t)n_ctas);
     lay->rec2 = take((uint64_t)n_ctas);
+    lay->rec3 = take(2 * (uint64_t)n_ctas);
     lay->total = off;
     return CC_OK;
 }
@@ -1791,7 +1839,7 @@ int token_plan_create_impl(const CcTokenModel* m, void** out_plan) {
     p.xs_bytes = xs_bytes; p.n_stages = n_stages;
 
 
-    p.rec1_off = lay.rec1; p.rec2_off = lay.rec2;
+    p.rec1_off = lay.rec1; p.rec2_off = lay.rec2; p.rec3_off = lay.rec3;
     *out_plan = plan;
     return CC_OK;
 }

@@ -4,7 +4,7 @@ N=${1:-2}
 O=gpurun_out
 mkdir -p $O
 if [ "$N" = "2" ]; then
-  echo "== tp tests world 2"; timeout 900 python -m pytest tests/test_tp.py -x -q -m gpu -k world2 > $O/r2_tp2_tests.log 2>&1; echo "rc=$?"; tail -8 $O/r2_tp2_tests.log
+  echo "== tp tests world 2"; timeout 700 python -m pytest tests/test_tp.py -x -q -m gpu -k world2 > $O/r2_tp2_tests.log 2>&1; echo "rc=$?"; tail -8 $O/r2_tp2_tests.log
 fi
 if [ "$N" = "4" ]; then
   echo "== tp tests world 4"; timeout 900 python -m pytest tests/test_tp.py -x -q -m gpu -k world4 > $O/r2_tp4_tests.log 2>&1; echo "rc=$?"; tail -8 $O/r2_tp4_tests.log

@@ -9,7 +9,7 @@ import torch
 
 GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
 ALL_FIXTURES = sorted(p.stem for p in GOLDEN_DIR.glob("*.npz")
-                      if not p.stem.startswith(("prefill_", "debug_")) and "_bits" not in p.stem)
+                      if not p.stem.startswith(("prefill_", "debug_", "model_")) and "_bits" not in p.stem)
 GPU_FIXTURES = ALL_FIXTURES   # every decode trace, incl. the BASELINE cache shapes (cfg*), is verified on the B200
 
 

@@ -113,10 +113,12 @@ def test_kernel_register_budgets():
     seen = set()
     for name, spill, regs in entries:
         spill, regs = int(spill), int(regs)
-        # the whole-token kernel's attention stage keeps q[G][8] and acc[G][8] live: its G = 7 / 8 instances spill a few
-        # hundred bytes there (one CTA of 256 threads per SM at 255 registers); the headline G = 4 instance must not
-        big_group = "cc_token_kernel" in name and re.search(r"ILi\d+ELi[78]E", name)
-        assert spill <= (512 if big_group else 16), f"{name}: {spill} bytes of spills"
+        # the whole-token kernel: its producer warpgroup runs at 48 registers (setmaxnreg) and keeps two tile cursors
+        # there (a few dozen bytes of spills, off the consumers' path); the attention stage keeps q[G][8] and acc[G][8]
+        # live, so the G = 7 / 8 instances spill a few hundred bytes more
+        tok = "cc_token_kernel" in name
+        big_group = tok and re.search(r"ILi\d+ELi[78]E", name)
+        assert spill <= (512 if big_group else 128 if tok else 16), f"{name}: {spill} bytes of spills"
         for key, cap in (("rmsnorm_qkv_rope_kernel", 80), ("gemv_residual_kernel", 80), ("rmsnorm_ffn_gate_kernel", 80),
                          ("prefill_attn_kernel", 128)):
             if key in name:

@@ -52,4 +52,6 @@ def test_generate_py_runs_unmodified_on_the_gpu(tmp_path, extra):
               "--max_new_tokens", "8", "--prompt", "the cache keeps heavy hitters and recent tokens", *extra])
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
     assert "GENERATION:" in r.stdout and "KV CACHE STATISTICS:" in r.stdout
-    assert "Decode Tokens: 8.00" in r.stdout, r.stdout[-1500:]
+    import re
+    m = re.search(r"Decode Tokens: (\d+)\.", r.stdout)   # 8 unless the random model emits the tokenizer's eos id early
+    assert m and 1 <= int(m.group(1)) <= 8, r.stdout[-1500:]

@@ -44,6 +44,7 @@ def main():
     # reference's tokenizer.decode (generate.py:136) accepts
     sd["output.weight"][TOK_VOCAB:] = 0
     sd["output.weight"][:TOK_VOCAB] *= 8
+    sd["output.weight"][:3] = 0   # unk / bos / eos: an early eos would end generate.py's loop before max_new_tokens
     torch.save(sd, d / "model.pth")
     import sentencepiece as spm
     corpus = d / "corpus.txt"
