@@ -62,6 +62,15 @@ METRIC = "decode tokens/sec @ 8k ctx, 1024-slot heavy-hitter"   # BASELINE.json'
 PROMPT_LEN, MAX_NEW = CONFIGS[2]["prompt"], CONFIGS[2]["max_new"]   # (profiles/ scripts)
 
 
+def workload_config(cfg_id, world):
+    """The `config` object both arms print: it names the job (BASELINE config, shapes, how many ways it is split),
+    not how an arm executes it -- arm-specific facts go into `notes`."""
+    cfg = CONFIGS[cfg_id]
+    return {"workload": f"BASELINE config {cfg_id}: {cfg['model']}-shape random-init bf16, {cfg['what']}",
+            "global_batch": 1, "seq_len": cfg["prompt"] + cfg["max_new"],
+            "parallelism": "none" if world == 1 else f"tp{world}"}
+
+
 def metric_name(cfg_id):
     return METRIC if cfg_id in (2, 5) else f"decode tokens/sec (BASELINE config {cfg_id})"
 
@@ -373,12 +382,12 @@ def run_ours(args):
         "metric": metric_name(cfg_id), "value": round(args.steps / dev_s, 2), "unit": "tokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(dev_s / args.steps * 1e3, 4),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"BASELINE config {cfg_id}: {cfg['model']}-shape random-init bf16, {cfg['what']}",
-                   "global_batch": 1, "seq_len": P + MAXNEW, "parallelism": par,
-                   "decode_path": "one persistent kernel per token (cc_decode_token)" if token_kernel else
-                                  "per-layer kernels in one CUDA graph (" + str(getattr(model, "token_kernel_reason", "CC_TOKEN_KERNEL=0")) + ")",
-                   "l2": "per-step inputs (this rank's weights + live K/V) exceed the 126 MB L2",
-                   "prefill_seconds": round(prefill_s, 2)},
+        "config": workload_config(cfg_id, world),
+        "notes": {"parallelism": par,
+                  "decode_path": "one persistent kernel per token (cc_decode_token)" if token_kernel else
+                                 "per-layer kernels in one CUDA graph (" + str(getattr(model, "token_kernel_reason", "CC_TOKEN_KERNEL=0")) + ")",
+                  "l2": "per-step inputs (this rank's weights + live K/V) exceed the 126 MB L2",
+                  "prefill_seconds": round(prefill_s, 2)},
         "e2e": {"value": round(args.steps / e2e_s, 2), "unit": "tokens/s", "h2d_bytes_per_step": 8,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": ours_per_step * args.steps,
@@ -630,17 +639,17 @@ def run_reference(args):
         return
     cfg_id = args.config or (2 if args.gpus == 1 else 5)
     cfg = CONFIGS[cfg_id]
-    base = cpu_baseline(cfg_id, warmup=max(1, min(args.warmup, 3)), steps=args.steps)
+    warm = max(3, args.warmup)   # the same warm-up count as the GPU arm
+    base = cpu_baseline(cfg_id, warmup=warm, steps=args.steps)
     if base is None:
         print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref is missing and the port only covers configs 2 and 5"}), flush=True)
         return
     n = int(base["sample"].split()[0])
     out = {"impl": "reference", "metric": metric_name(cfg_id), "value": base["value"], "unit": "tokens/s", "n_gpus": args.gpus,
-           "steps": n, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": round(1e3 / base["value"], 3),
+           "steps": n, "warmup": warm, "ms_per_step": round(1e3 / base["value"], 3),
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-           "config": {"workload": f"BASELINE config {cfg_id}: {cfg['model']}-shape random-init bf16, {cfg['what']} "
-                                  "(reference CPU path on the host cores, unsharded)",
-                      "global_batch": 1, "seq_len": cfg["prompt"] + cfg["max_new"], "parallelism": "none"},
+           "config": workload_config(cfg_id, args.gpus),
+           "notes": {"parallelism": "the reference's CPU path on the host cores of rank 0, unsharded"},
            "cpu_baseline": base,
            "e2e": {"value": base["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
