@@ -68,7 +68,8 @@ def workload_config(cfg_id, world):
     cfg = CONFIGS[cfg_id]
     return {"workload": f"BASELINE config {cfg_id}: {cfg['model']}-shape random-init bf16, {cfg['what']}",
             "global_batch": 1, "seq_len": cfg["prompt"] + cfg["max_new"],
-            "parallelism": "none" if world == 1 else f"tp{world}"}
+            "parallelism": "none" if world == 1 else f"tp{world}",
+            "l2": "no flush needed: the inputs of a step (a rank's weights + live K/V, 2.8-15 GB) exceed the 126 MB L2"}
 
 
 def metric_name(cfg_id):
@@ -386,7 +387,6 @@ def run_ours(args):
         "notes": {"parallelism": par,
                   "decode_path": "one persistent kernel per token (cc_decode_token)" if token_kernel else
                                  "per-layer kernels in one CUDA graph (" + str(getattr(model, "token_kernel_reason", "CC_TOKEN_KERNEL=0")) + ")",
-                  "l2": "per-step inputs (this rank's weights + live K/V) exceed the 126 MB L2",
                   "prefill_seconds": round(prefill_s, 2)},
         "e2e": {"value": round(args.steps / e2e_s, 2), "unit": "tokens/s", "h2d_bytes_per_step": 8,
                 "d2h_bytes_per_step": 4},
