@@ -76,3 +76,31 @@ def test_full_cache_appends_at_first_unfilled_slot():
         assert int(got) == n
         if want is not None:
             assert int(want.view(-1)[0]) == n
+
+
+@pytest.mark.parametrize("strategy,bits", [("recent_global", None), ("heavy_hitter", None), ("heavy_hitter", 8), ("recent_global", 4),
+                                           ("l2", None), ("full", None), ("keep_it_odd", 2)])
+def test_cache_statistics_match_reference(strategy, bits):
+    """compute_statistics / compression_ratio / memory_usage (reference cache.py:229-281): same numbers from the same
+    counters, with and without --cache_bits."""
+    from cold_compress_b200.cache import get_cache_constructor
+    ref = _ref_cache_module()
+    kw = dict(max_cache_length=96, max_seq_length=4096, cache_bits=bits, global_tokens=4, recent_window=10,
+              history_window_size=1, attn_thresholding=False)
+    rcls, rrel = ref.get_cache_constructor(strategy)
+    ocls, orel = get_cache_constructor(strategy)
+    assert sorted(rrel) == sorted(orel)
+    r = rcls(1, 4, 64, torch.bfloat16, **{k: kw[k] for k in rrel})
+    o = ocls(1, 4, 64, torch.bfloat16, **{k: kw[k] for k in orel})
+    for filled, seq_len in ((96, 400), (50, 51), (96, 97)):
+        r.cache_cts.fill_(filled)
+        o.cache_cts.fill_(filled)
+        want, got = r.compute_statistics(seq_len), o.compute_statistics(seq_len)
+        assert set(want) == set(got)
+        assert got["compression_ratio"] == pytest.approx(want["compression_ratio"], rel=1e-6, abs=1e-9)
+        if bits is None:
+            assert got["cache_memory_gb"] == pytest.approx(want["cache_memory_gb"], rel=1e-6)
+        else:
+            # --cache_bits here keeps the packed codes AND the bf16 working copy the decode kernel streams (DESIGN.md
+            # section 7: the semantics of the quantised cache, not yet its footprint); the number reported is ours
+            assert got["cache_memory_gb"] >= want["cache_memory_gb"]
