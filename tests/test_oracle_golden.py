@@ -99,3 +99,27 @@ def test_exp_matches_libm_to_one_ulp():
     assert rel.max() < 2.0 ** -22, rel.max()
     assert np.all(np.abs(got[~normal].astype(np.float64) - want[~normal]) <= 1.5e-45)
     assert lib().cc_oracle_expf(float("-inf")) == 0.0 and lib().cc_oracle_expf(0.0) == 1.0
+
+
+def test_oracle_reproduces_the_whole_model_eviction_trace():
+    """tests/golden/model_cfg1.npz (the reference's generate() on the 32-layer model, BASELINE config 1): every layer's
+    recent_global cache starts from the compressed 128-token prompt (4 global tokens + the 60 most recent) and the
+    oracle, stepped with arbitrary q / k / v, overwrites the slots the reference overwrote and ends with its `pos`."""
+    from pathlib import Path
+    z = np.load(Path(__file__).resolve().parent / "golden" / "model_cfg1.npz")
+    fill, final_pos = z["fill_idx"], z["final_pos"]
+    P, L, g = z["prompt"].size, final_pos.shape[1], 4
+    Hkv, G, D = 8, 4, 128
+    gen = torch.Generator().manual_seed(0)
+    oc = OracleCache("recent_global", Hkv, G, D, L, g, L - g, 1)
+    pos0 = torch.cat([torch.arange(g), torch.arange(P - (L - g), P)]).int()
+    oc.load_state({"pos": pos0.view(1, L), "mask": torch.ones(Hkv, L, dtype=torch.bool), "cache_cts": torch.tensor([L]),
+                   "k_cache": torch.randn(Hkv, L, D, generator=gen).to(torch.bfloat16),
+                   "v_cache": torch.randn(Hkv, L, D, generator=gen).to(torch.bfloat16)})
+    for t in range(fill.shape[0]):
+        q = torch.randn(Hkv * G, D, generator=gen).to(torch.bfloat16)
+        k = torch.randn(Hkv, D, generator=gen).to(torch.bfloat16)
+        v = torch.randn(Hkv, D, generator=gen).to(torch.bfloat16)
+        _, idx, _ = oc.decode_step(q, k, v, P + t)
+        assert (fill[t] == int(idx.view(-1)[0])).all(), f"step {t}: oracle {idx.view(-1)[0]} reference {fill[t]}"
+    assert (final_pos == oc.pos.view(-1).numpy()).all()
