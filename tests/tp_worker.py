@@ -16,10 +16,17 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 
-def build(device, strategy, seed=0):
+def model_shape(world):
+    """(n_head, n_kv_heads, dim, intermediate): 8 / 4 heads for up to 4 ranks; 16 / 8 heads of 128 for 8 ranks (one KV
+    head and 256 q / 256 intermediate rows per rank: the smallest shard the whole-token kernel takes)."""
+    return (16, 8, 2048, 2048) if world > 4 else (8, 4, 1024, 1024)
+
+
+def build(device, strategy, seed=0, world=1):
     from cold_compress_b200.model import ModelArgs, Transformer
-    cfg = ModelArgs(block_size=512, vocab_size=1000, n_layer=2, n_head=8, dim=1024, n_local_heads=4,
-                    intermediate_size=1024, rope_base=500000)
+    n_head, n_kv, dim, inter = model_shape(world)
+    cfg = ModelArgs(block_size=512, vocab_size=1000, n_layer=2, n_head=n_head, dim=dim, n_local_heads=n_kv,
+                    intermediate_size=inter, rope_base=500000)
     torch.manual_seed(seed)
     model = Transformer(cfg)
     with torch.no_grad():
@@ -54,10 +61,13 @@ def main():
     device = f"cuda:{rank}" if use_cuda else "cpu"
     from cold_compress_b200 import generation_utils as gu
 
-    full = build(device, strategy)
-    sharded = build(device, strategy)
+    n_head, n_kv, dim, _ = model_shape(world)
+    hd = dim // n_head
+    full = build(device, strategy, world=world)
+    sharded = build(device, strategy, world=world)
     tp.apply_tp(sharded)
-    assert sharded.config.n_local_heads == 4 // world and sharded.layers[0].attention.wqkv.out_features == (8 + 8) * 128 // world
+    assert sharded.config.n_local_heads == n_kv // world
+    assert sharded.layers[0].attention.wqkv.out_features == (n_head + 2 * n_kv) * hd // world
     torch.manual_seed(11)
     # heavy_hitter: a prompt that fits the cache (SnapKV's top-k has exact ties at the cut-off, and torch.topk
     # does not promise the same tie choice for different batch shapes); recent_global: a compressed prompt
@@ -67,17 +77,18 @@ def main():
         if not use_cuda:
             # CPU (gloo): the cache kernels are CUDA-only, so exercise the sharded projections + all-reduces
             # through one block's prefill-style forward without caches
-            x = (torch.randn(1, 16, 1024) * 0.5).to(torch.bfloat16)
+            x = (torch.randn(1, 16, dim) * 0.5).to(torch.bfloat16)
             dist.broadcast(x, 0)
             fa, fs = full.layers[0], sharded.layers[0]
             ref = fa.feed_forward(fa.ffn_norm(x))
             got = fs.feed_forward(fs.ffn_norm(x))
-            assert torch.allclose(ref.float(), got.float(), atol=3e-2, rtol=3e-2), "sharded FFN != full FFN"
+            err, mag = (ref.float() - got.float()).abs().max().item(), ref.float().abs().max().item()
+            assert err <= 3e-2 * mag + 3e-2, f"sharded FFN != full FFN: max error {err} at magnitude {mag}"
             from cold_compress_b200.model import precompute_freqs_cis
-            fc = precompute_freqs_cis(64, 128, 500000, torch.bfloat16)[:16]
+            fc = precompute_freqs_cis(64, hd, 500000, torch.bfloat16)[:16]
             qf, kf, vf = fa.attention._project(fa.attention_norm(x), fc)
             qs, ks, vs = fs.attention._project(fs.attention_norm(x), fc)
-            hq, hk = 8 // world, 4 // world
+            hq, hk = n_head // world, n_kv // world
             assert torch.equal(qs, qf[:, rank * hq:(rank + 1) * hq]) and torch.equal(ks, kf[:, rank * hk:(rank + 1) * hk])
             assert torch.equal(vs, vf[:, rank * hk:(rank + 1) * hk])
             y = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf, is_causal=True, enable_gqa=True)
@@ -85,7 +96,8 @@ def main():
             out_ref = fa.attention.wo(y.transpose(1, 2).reshape(1, 16, -1))
             out = fs.attention.wo(ys.transpose(1, 2).reshape(1, 16, -1))
             dist.all_reduce(out)
-            assert torch.allclose(out_ref.float(), out.float(), atol=3e-2, rtol=3e-2), "sharded attention output != full"
+            err, mag = (out_ref.float() - out.float()).abs().max().item(), out_ref.float().abs().max().item()
+            assert err <= 3e-2 * mag + 3e-2, f"sharded attention output != full: max error {err} at magnitude {mag}"
             print(f"rank {rank}: tp host logic ok")
         else:
             caches(full, device, strategy)
@@ -96,7 +108,7 @@ def main():
                 tp.enable_fused_exchange(sharded)
             t_full, _ = gu.prefill(full, prompt.view(1, -1), torch.arange(S, device=device))
             t_sh, _ = gu.prefill(sharded, prompt.view(1, -1), torch.arange(S, device=device))
-            hk = 4 // world
+            hk = n_kv // world
             for lf, ls in zip(full.layers, sharded.layers):
                 cf, cs = lf.attention.kv_cache, ls.attention.kv_cache
                 if cf.pos.shape[1] > 1 and not compressed:
