@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: this call ran the build with the 48 / 232 setmaxnreg split: every cc_token_kernel launch hung, pytest and the
+# first bench hit their timeouts and the call was cut at its 2400 s limit (41 GPU-minutes, no data).  See r2/notes.md.
 # round 2, call L: the whole GPU suite on the final token kernel, then the stall-gated L2 prefetch sweep
 O=gpurun_out
 mkdir -p $O
